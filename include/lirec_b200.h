@@ -1,0 +1,301 @@
+/*
+ * lirec_b200.h — C ABI of liblirec_b200.so (sm_100a only).
+ *
+ * This is the drop-in boundary for the LIReC hot path: the forward/backward of
+ * reference mlp/model.py as driven by mlp/train.py and mlp/test.py.  The
+ * reference has no native code and no FFI; every entry point below replaces a
+ * group of ATen call sites of the reference, cited per function as
+ * `<file>:<lines>` relative to the reference tree.  The Python side
+ * (lirec_b200/_ext.py) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / ATen types;
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller owns every buffer; the library never allocates device memory
+ *     and keeps no pointer after a call returns;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), the
+ *     library never synchronises;
+ *   - return value 0 = OK, negative = error; lirec_last_error() gives the text
+ *     (thread-local).  There is no CPU fallback: on a device that is not
+ *     sm_100 every compute entry point fails with LIREC_ERR_ARCH.
+ */
+#ifndef LIREC_B200_H_
+#define LIREC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIREC_ABI_VERSION 1
+
+enum lirec_status {
+  LIREC_OK = 0,
+  LIREC_ERR_ARG = -1,     /* bad shape / alignment / null pointer            */
+  LIREC_ERR_ARCH = -2,    /* device is not sm_100                            */
+  LIREC_ERR_CUDA = -3,    /* a CUDA runtime / driver call failed             */
+  LIREC_ERR_LIMIT = -4    /* too many problems / passes / tensor maps        */
+};
+
+/* ---- library ---------------------------------------------------------- */
+int lirec_abi_version(void);
+const char* lirec_last_error(void);
+/* 0 if `device` can run the kernels (compute capability 10.x), else LIREC_ERR_ARCH */
+int lirec_device_check(int device);
+
+/* ---- dropout stream ----------------------------------------------------
+ * Counter-based mask shared by every kernel that applies or re-derives a
+ * dropout mask (reference: nn.Dropout at mlp/model.py:52,62,88,353).  keep(r,c)
+ * is a pure function of (seed, stream_id, row r, column c); the oracle mirrors
+ * it (oracle/dropout.py) so train-mode parity can be checked with masks on.  */
+typedef struct lirec_dropout {
+  float p;             /* drop probability; 0 disables                       */
+  uint32_t seed;       /* per-step seed                                      */
+  uint32_t stream_id;  /* which dropout site                                 */
+  int32_t col_off;     /* added to the column before hashing                 */
+} lirec_dropout;
+
+/* ---- grouped tcgen05 GEMM ---------------------------------------------
+ * D[m,n] = epilogue( alpha * sum_pass sum_k A_pass[m,k] * B_pass[n,k] )
+ * bf16 operands, fp32 accumulation in TMEM.  Replaces nn.Linear forward
+ * (cuBLAS sgemm, mlp/model.py:281-294,307-322,333,336,352) and the autograd
+ * mm/addmm pairs of its backward (mlp/train.py:62).
+ *
+ * An operand is a 2-D bf16 view (ptr, rows, cols, ld).  K-major use: rows
+ * index M (or N), cols index K.  MN-major use (mn_major=1): rows index K, cols
+ * index M (or N) — this is how dgrad reads W[out,in] and wgrad reads dY / X
+ * without a transposed copy.  A pass is one K-segment; several passes
+ * accumulate into the same tile (hi/lo split operands, concatenated inputs). */
+#define LIREC_GEMM_MAX_PASSES 4
+#define LIREC_GEMM_MAX_PROBLEMS 32
+#define LIREC_GEMM_MAX_MAPS 64
+
+typedef struct lirec_operand {
+  const void* ptr;  /* bf16, 16-byte aligned                                 */
+  int64_t rows, cols;
+  int64_t ld;       /* elements between rows; ld*2 must be a multiple of 16  */
+} lirec_operand;
+
+typedef struct lirec_gemm_pass {
+  lirec_operand a, b;
+  int32_t a_mn_off, a_k_off;  /* element offsets inside the view             */
+  int32_t b_mn_off, b_k_off;
+  int32_t k_len;              /* reduction length of this pass (elements)    */
+} lirec_gemm_pass;
+
+enum lirec_act { LIREC_ACT_NONE = 0, LIREC_ACT_RELU = 1, LIREC_ACT_TANH = 2 };
+enum lirec_post {
+  LIREC_POST_NONE = 0,
+  LIREC_POST_DROPOUT = 1, /* v *= keep(m,n) / (1-p)                          */
+  LIREC_POST_DRELU = 2,   /* v *= post_scale * [aux_hi(m,n) > 0]             */
+  LIREC_POST_DTANH = 3    /* v *= keep(m,n)/(1-p) * (1 - ((aux_hi+aux_lo)*(1-p))^2) */
+};
+enum lirec_out { LIREC_OUT_F32 = 0, LIREC_OUT_SPLIT_BF16 = 1 };
+
+typedef struct lirec_epilogue {
+  float alpha;
+  const float* bias;        /* [N] or NULL                                   */
+  const int32_t* row_flag;  /* [M] or NULL: bias only where row_flag[m] != 0 */
+  int32_t act;              /* lirec_act                                     */
+  int32_t post;             /* lirec_post                                    */
+  float post_scale;
+  lirec_dropout drop;
+  const void* aux;          /* bf16 split tensor for DRELU / DTANH           */
+  int64_t aux_ld;
+  int32_t aux_col_off, aux_lo_off;
+  int32_t out_kind;         /* lirec_out                                     */
+  void* out;
+  int64_t out_ld_m, out_ld_n; /* F32: &out[m*ld_m + n*ld_n]; SPLIT: ld_m only */
+  int32_t out_col_off;      /* SPLIT: hi at col_off+n, lo at col_off+lo_off+n */
+  int32_t out_lo_off;
+  int32_t accumulate;       /* F32 only: out += v                            */
+} lirec_epilogue;
+
+typedef struct lirec_gemm_problem {
+  int32_t M, N;
+  int32_t a_mn_major, b_mn_major;
+  int32_t num_passes;
+  lirec_gemm_pass pass[LIREC_GEMM_MAX_PASSES];
+  lirec_epilogue epi;
+} lirec_gemm_problem;
+
+/* One persistent launch over all tiles of all problems (host array). */
+int lirec_gemm_grouped(const lirec_gemm_problem* problems_host, int num_problems,
+                       void* stream);
+/* Number of kernels the last lirec_* call on this thread launched. */
+int lirec_last_launch_count(void);
+
+/* ---- segmented reductions over ragged sequences -------------------------
+ * Temporal pooling of variable-length frame / token / track sequences
+ * (reference: np.max(axis=0) at mixed_utils/mixed_features.py:54,61,105; empty
+ * segment -> zeros, text_utils/text_features.py:171-178, mixed_features.py:89-93).
+ * x: [total_rows, dim] fp32, seg_off: [nseg+1] int32 prefix sums.
+ * mode: 0 = max, 1 = mean.  out_bf16 / out_f32 may each be NULL.            */
+int lirec_seg_reduce_f32(const float* x, const int32_t* seg_off, int32_t nseg,
+                         int32_t dim, int32_t mode, float* out_f32, int64_t out_f32_ld,
+                         void* out_bf16, int64_t out_bf16_ld, void* stream);
+
+/* ---- ragged row kernels of the modality encoder --------------------------
+ * Layer-1 outputs are computed once per UNIQUE bank row (clip text, clip
+ * visual, person track).  These kernels expand them to encoder rows by the
+ * (clip, track1, track2) row tables, apply the layer-1 dropout + ReLU
+ * (reference relu(dropout(.)) at mlp/model.py:282,287,293-294) and, for the
+ * context branch, the masked mean over each candidate's context rows
+ * (mlp/model.py:301-304,309,315,323-324), which commutes with the second
+ * Linear.  Output is a hi/lo bf16 split [n_out, 4*2*J] laid out
+ * [txt hi|lo, vis hi|lo, tr1 hi|lo, tr2 hi|lo].
+ *
+ * r1_* : relu(L1) of the unique rows, fp32 [*, J]; r1_tr1/r1_tr2 index the
+ *        same track bank rows through different weights.
+ * rows : [n_rows,3] int32 (clip, track1, track2).
+ * seg_off : NULL -> one output row per table row (ints branch); else
+ *        [n_out+1] prefix sums and output row c is the mean over its segment.
+ * guard_zero: 1 -> empty segment gives 0 (MaxTracks, model.py:303); 0 -> 0/0 = NaN
+ *        (MidFusionMultiClip, model.py:175).                                  */
+int lirec_rows_expand_fwd(const float* r1_txt, const float* r1_vis, const float* r1_tr1,
+                          const float* r1_tr2, int32_t J, const int32_t* rows,
+                          const int32_t* seg_off, int32_t n_out, int32_t guard_zero,
+                          lirec_dropout drop, void* out_split, int64_t out_ld,
+                          int32_t* row_flag_out, void* stream);
+
+/* Backward of lirec_rows_expand_fwd onto the unique rows of ONE bank slot.
+ * d_in : fp32 [n_out, ld] gradient w.r.t. the (pre-split) expanded rows of
+ *        this slot (column offset already applied by the caller).
+ * inv_off/inv_idx : CSR from unique row u to the table rows that reference it.
+ * owner : NULL (ints) or [n_rows] candidate index of each context row;
+ * seg_off: NULL or [n_out+1] (context) to derive 1/n.
+ * slot : 0 txt, 1 vis, 2 tr1, 3 tr2 (selects the dropout columns).
+ * Writes dZ1 = [r1 > 0] * sum(...) as a hi/lo split [n_unique, 2*J].          */
+int lirec_rows_expand_bwd(const float* d_in, int64_t d_ld, const float* r1, int32_t J,
+                          int32_t slot, const int32_t* inv_off, const int32_t* inv_idx,
+                          int32_t n_unique, const int32_t* owner, const int32_t* seg_off,
+                          lirec_dropout drop, void* out_split, int64_t out_ld, void* stream);
+
+/* fp32 [rows, cols] -> hi/lo bf16 split [rows, 2*pad_cols] (zero padded). */
+int lirec_split_f32(const float* x, int64_t ld, int32_t rows, int32_t cols, void* out_split,
+                    int64_t out_ld, int32_t pad_cols, void* stream);
+/* fp32 -> bf16 (round to nearest even), n elements. */
+int lirec_cast_bf16(const float* x, void* out, int64_t n, void* stream);
+
+/* ---- losses: fused forward + gradient over ragged candidate tables -------
+ * All losses are sigmoid + max-margin hinges (reference mlp/model.py:381-575).
+ * Each writes per-clip loss terms (already divided by the batch size) and
+ * d(loss)/d(logits); the scalar loss is the sum of loss_per_clip.            */
+typedef struct lirec_track_loss_cfg {
+  float margin;        /* opt.tr_margin                                      */
+  float lymbda;        /* weight of the interaction term                     */
+  int32_t n_classes;   /* C                                                  */
+  int32_t n_rels;      /* R (the None class has index R); 0 -> no rel term   */
+  int32_t tr_correct;  /* supervised assignment (t* = 0)                     */
+  int32_t max_neg;     /* opt.tr_max_neg && opt.tr_sum_max_flag              */
+  int32_t max_slots;   /* T: reference slot count, only used by max_neg      */
+} lirec_track_loss_cfg;
+
+/* MarginLoss (model.py:444-494) when n_rels == 0, MarginTrackRelsLoss
+ * (model.py:497-575) otherwise.  ints: [Ni, C] fp32, rels: [Ni, R] fp32,
+ * cand_off: [B+1], labels: [B], rels_label: [Ni], gt_tracks: [B,2],
+ * multilab: [B, C] uint8 (1 = class may be used as a negative).
+ * Outputs: loss_per_clip [B], assign [B] (t*), d_ints [Ni,C], d_rels [Ni,R]. */
+int lirec_loss_track_fwd_bwd(const float* ints, const float* rels, const int32_t* cand_off,
+                             int32_t B, const int32_t* labels, const int32_t* rels_label,
+                             const int32_t* gt_tracks, const uint8_t* multilab,
+                             lirec_track_loss_cfg cfg, float* loss_per_clip, int32_t* assign,
+                             float* d_ints, float* d_rels, void* stream);
+
+/* MaxMarginCrossEntropyLoss (model.py:422-441) and the two terms of
+ * MultiTaskMaxMargin (model.py:381-419): a row-wise hinge
+ *   loss_row = sum_c relu(m - s[y] + s[c]) over c != y with weight[c] != 0.
+ * rows with label < 0 are skipped; scale multiplies loss and gradient.       */
+int lirec_loss_rowmargin_fwd_bwd(const float* logits, int64_t ld, int32_t rows, int32_t C,
+                                 const int32_t* labels, const uint8_t* weights, float margin,
+                                 float scale, float* loss_per_row, float* d_logits,
+                                 int64_t d_ld, void* stream);
+
+/* ---- the model hot path: one call per direction ---------------------------
+ * Native launch sequence for the forward and backward of Modalities
+ * (mlp/model.py:19-92), MidFusionMultiClip (:95-211), MidFusionMultiClipMaxTracks
+ * (:214-339) and GatingUnit (:342-354) over a PACKED ragged batch: layer 1 once per
+ * unique bank row, ragged expansion / masked mean, layer 2 + tanh + dropout, gate,
+ * heads.  The host sequence is C++ so a step is ~12 launches, not ~150 ATen calls. */
+typedef struct lirec_linear {
+  const void* w_bf16;  /* [out_f, in_f] bf16 shadow of the fp32 nn.Linear weight      */
+  const float* bias;   /* [out_f] fp32                                                */
+  float* grad_w;       /* [out_f, in_f] fp32, written (not accumulated) by backward   */
+  float* grad_b;       /* [out_f] fp32                                                */
+  int32_t out_f, in_f;
+} lirec_linear;
+
+/* the 8 Linears of one modality encoder (model.py:222-246): first layers txt_*, vis_*,
+ * tracks1_*, tracks2_*; second layers txt2_*, vis2_*, tracks12_*, tracks22_*          */
+typedef struct lirec_encoder {
+  lirec_linear l1[4];
+  lirec_linear l2[4];
+} lirec_encoder;
+
+typedef struct lirec_model_params {
+  lirec_encoder enc_ints, enc_ctx;
+  lirec_linear gate;      /* gates_ints.fc_out: [gate_dim, 2*3J]                      */
+  lirec_linear out_ints;  /* [n_classes, gate_dim or 3J]                              */
+  lirec_linear out_ctx;   /* [n_rels, 3J]                                             */
+} lirec_model_params;
+
+typedef struct lirec_model_cfg {
+  int32_t text_dim, visual_dim, track_dim;  /* 768, 2048, 2048                        */
+  int32_t joint_dim;                         /* J = 512                                */
+  int32_t gate_dim;                          /* joint_dim * mid_m_ints = 3072          */
+  int32_t n_classes, n_rels;
+  int32_t ctx, gates;                        /* opt.ctx, opt.gates (opt.ints is 1)     */
+  int32_t guard_zero;                        /* 1: MaxTracks divider guard (model.py:303) */
+  float dropout_p;                           /* opt.dropout                            */
+} lirec_model_cfg;
+
+/* Packed ragged batch (device pointers).  Every encoder row — candidate row or context
+ * row — is a triple (clip, track1, track2) of bank row indices; a missing track points
+ * at an all-zero bank row.  Bank rows [0, n_*_ints) are the ones the ints branch uses. */
+typedef struct lirec_batch {
+  const void* clip_bank;   /* bf16 [n_clip, text_dim + visual_dim]                    */
+  int64_t clip_ld;
+  int32_t n_clip, n_clip_ints;
+  const void* track_bank;  /* bf16 [n_track, track_dim]                               */
+  int64_t track_ld;
+  int32_t n_track, n_track_ints;
+  int32_t n_cand;          /* Ni: candidate rows in the batch                         */
+  int32_t n_ctx_rows;      /* Nx: valid context rows in the batch                     */
+  const int32_t* cand_rows;  /* [Ni, 3]                                               */
+  const int32_t* ctx_rows;   /* [Nx, 3]                                               */
+  const int32_t* ctx_off;    /* [Ni + 1] prefix sums                                  */
+  const int32_t* ctx_owner;  /* [Nx] candidate of each context row                    */
+  /* CSR inverses (unique bank row -> referencing table rows), slot 0 clip (txt+vis),
+   * 1 track1, 2 track2; only needed by backward                                      */
+  const int32_t* inv_cand_off[3];
+  const int32_t* inv_cand_idx[3];
+  const int32_t* inv_ctx_off[3];
+  const int32_t* inv_ctx_idx[3];
+  uint32_t seed;           /* dropout seed of this step                               */
+  int32_t training;        /* 0: no dropout                                           */
+} lirec_batch;
+
+size_t lirec_model_workspace_bytes(const lirec_model_cfg* cfg, const lirec_batch* batch_host);
+/* out_ints: fp32 [Ni, n_classes]; out_rels: fp32 [Ni, n_rels] (NULL when ctx == 0).
+ * The workspace keeps the activations backward needs.                               */
+int lirec_model_forward(const lirec_model_cfg* cfg, const lirec_model_params* params,
+                        const lirec_batch* batch, void* workspace, size_t workspace_bytes,
+                        float* out_ints, float* out_rels, void* stream);
+/* d_ints / d_rels: fp32 gradients w.r.t. the logits.  Writes every grad_w / grad_b. */
+int lirec_model_backward(const lirec_model_cfg* cfg, const lirec_model_params* params,
+                         const lirec_batch* batch, void* workspace, size_t workspace_bytes,
+                         const float* d_ints, const float* d_rels, void* stream);
+
+/* ---- optimizer -----------------------------------------------------------
+ * torch.optim.Adam with coupled L2 (reference mlp/model.py:599-601) over one
+ * flat buffer; also refreshes the bf16 shadow of the weights.                */
+int lirec_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                    void* param_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int32_t step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIREC_B200_H_ */

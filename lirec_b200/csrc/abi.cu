@@ -1,0 +1,64 @@
+// abi.cu — error plumbing and device checks behind the C ABI (include/lirec_b200.h).
+#include <cstring>
+
+#include "common.cuh"
+
+namespace lirec {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+
+char* err_buf() { return g_err; }
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void note_launch(int n) { g_launches += n; }
+void reset_launch_count() { g_launches = 0; }
+
+// No CPU fallback and no other architecture: anything but sm_100 is an error.
+int check_arch() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached_rc = LIREC_ERR_ARCH;
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess)
+    return fail(LIREC_ERR_ARCH, "no CUDA device available (%s); liblirec_b200 has no CPU fallback",
+                cudaGetErrorString(e));
+  if (dev == cached_dev) {
+    if (cached_rc != LIREC_OK) fail(cached_rc, "device %d is not sm_100 (B200 required)", dev);
+    return cached_rc;
+  }
+  int major = 0, minor = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess)
+    return fail(LIREC_ERR_CUDA, "cannot query compute capability of device %d", dev);
+  cached_dev = dev;
+  cached_rc = (major == 10) ? LIREC_OK : LIREC_ERR_ARCH;
+  if (cached_rc != LIREC_OK)
+    return fail(LIREC_ERR_ARCH, "device %d is sm_%d%d; liblirec_b200 is built for sm_100a only", dev,
+                major, minor);
+  return LIREC_OK;
+}
+
+}  // namespace lirec
+
+extern "C" int lirec_abi_version(void) { return LIREC_ABI_VERSION; }
+extern "C" const char* lirec_last_error(void) { return lirec::err_buf(); }
+extern "C" int lirec_last_launch_count(void) { return lirec::g_launches; }
+extern "C" int lirec_device_check(int device) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return lirec::fail(LIREC_ERR_ARCH, "no CUDA device available; liblirec_b200 has no CPU fallback");
+  if (device < 0 || device >= count) return lirec::fail(LIREC_ERR_ARG, "device %d out of range", device);
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess)
+    return lirec::fail(LIREC_ERR_CUDA, "cannot query device %d", device);
+  if (major != 10) return lirec::fail(LIREC_ERR_ARCH, "device %d is not sm_100", device);
+  return LIREC_OK;
+}

@@ -1,0 +1,67 @@
+// common.cuh — shared host/device helpers of liblirec_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/lirec_b200.h"
+
+namespace lirec {
+
+// ---- error plumbing (thread-local text behind lirec_last_error) ------------
+char* err_buf();
+int fail(int code, const char* fmt, ...);
+void note_launch(int n = 1);
+void reset_launch_count();
+int check_arch();  // LIREC_OK when the current device is sm_100
+
+#define LIREC_CUDA_OK(expr)                                                          \
+  do {                                                                               \
+    cudaError_t e__ = (expr);                                                        \
+    if (e__ != cudaSuccess)                                                          \
+      return ::lirec::fail(LIREC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,           \
+                           cudaGetErrorString(e__), __FILE__, __LINE__);             \
+  } while (0)
+
+#define LIREC_REQUIRE(cond, ...)                                  \
+  do {                                                            \
+    if (!(cond)) return ::lirec::fail(LIREC_ERR_ARG, __VA_ARGS__); \
+  } while (0)
+
+#define LIREC_ENTER()                      \
+  ::lirec::reset_launch_count();           \
+  do {                                     \
+    int a__ = ::lirec::check_arch();       \
+    if (a__ != LIREC_OK) return a__;       \
+  } while (0)
+
+// ---- dropout hash (mirrored bit-for-bit by oracle/dropout.py) ---------------
+__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+// row-dependent half of the hash, hoisted out of per-column loops
+__host__ __device__ __forceinline__ uint32_t drop_row_key(uint32_t seed, uint32_t stream_id,
+                                                           uint32_t row) {
+  return fmix32(seed ^ (stream_id * 0x9E3779B1u) ^ fmix32(row + 0x7F4A7C15u));
+}
+// 1.0f if element (row, col) is kept.  24-bit uniform compared against p.
+__host__ __device__ __forceinline__ bool drop_keep(uint32_t row_key, uint32_t col, float p) {
+  uint32_t h = fmix32(row_key ^ (col * 0x9E3779B1u + 0x632BE5ABu));
+  return (float)(h >> 8) * (1.0f / 16777216.0f) >= p;
+}
+
+// ---- hi/lo bf16 split: x ~= hi + lo with |err| <= 2^-17 |x| -----------------
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+}  // namespace lirec

@@ -1,0 +1,642 @@
+// gemm_tcgen05.cu — grouped, persistent, warp-specialised bf16 GEMM for sm_100a.
+//
+//   D[m,n] = epilogue( alpha * sum_pass sum_k A_pass[m,k] * B_pass[n,k] )
+//
+// Replaces the nn.Linear forward calls of the reference (cuBLAS sgemm at
+// mlp/model.py:281-294, 307-322, 333, 336, 352) and the mm/addmm pairs autograd
+// runs for them in backward (mlp/train.py:62).  Design (B200-first, not a port):
+//   * operands arrive by TMA (cp.async.bulk.tensor.2d, 128B swizzle) into a
+//     multi-stage shared-memory ring guarded by mbarriers;
+//   * one elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) with
+//     the accumulator in TMEM, double-buffered so the epilogue of tile i overlaps
+//     the main loop of tile i+1;
+//   * both operands may be K-major or MN-major, so dgrad reads W[out,in] and wgrad
+//     reads dY / X in place — no transposed copies in HBM;
+//   * a problem is a list of passes (K-segments) accumulated in the same tile:
+//     hi/lo split operands (fp32-grade products from bf16 MMAs) and concatenated
+//     inputs (GatingUnit's cat, model.py:352) are just extra passes;
+//   * one launch covers the tiles of up to 32 problems (the 8 modality Linears of
+//     a layer, or all wgrad/dgrad/bias-grad problems of a backward stage);
+//   * the epilogue fuses bias, ReLU/tanh, dropout (counter hash), the ReLU / tanh
+//     derivative masks of backward, the hi/lo split of the output, and strided or
+//     transposed fp32 stores straight into the flat gradient buffer.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "gemm.cuh"
+
+namespace lirec {
+namespace gemm {
+
+constexpr int BM = 128;       // tile rows  (UMMA M, cta_group::1)
+constexpr int BK = 64;        // bf16 elements per k-block = one 128B swizzle span
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps2-5 epilogue
+constexpr int MAX_PASSES = LIREC_GEMM_MAX_PASSES;
+constexpr int MAX_PROBLEMS = LIREC_GEMM_MAX_PROBLEMS;
+constexpr int MAX_MAPS = LIREC_GEMM_MAX_MAPS;
+
+struct DevPass {
+  int16_t a_map, b_map;
+  int32_t a_mn_off, a_k_off, b_mn_off, b_k_off;
+  int32_t k_blocks;
+};
+
+struct DevEpi {
+  float alpha;
+  const float* bias;
+  const int32_t* row_flag;
+  int32_t act, post;
+  float post_scale;
+  float drop_p;
+  uint32_t drop_seed, drop_stream;
+  int32_t drop_col_off;
+  const __nv_bfloat16* aux;
+  int64_t aux_ld;
+  int32_t aux_col_off, aux_lo_off;
+  int32_t out_kind;
+  void* out;
+  int64_t out_ld_m, out_ld_n;
+  int32_t out_col_off, out_lo_off;
+  int32_t accumulate;
+  int32_t vec_ok;  // 16-byte vector stores are legal for this problem
+};
+
+struct DevProblem {
+  int32_t M, N;
+  int32_t tiles_n;
+  int32_t num_passes;
+  int32_t a_mn_major, b_mn_major;
+  DevPass pass[MAX_PASSES];
+  DevEpi epi;
+};
+
+struct alignas(64) GemmParams {
+  CUtensorMap maps[MAX_MAPS];
+  DevProblem probs[MAX_PROBLEMS];
+  int32_t tile_start[MAX_PROBLEMS + 1];
+  int32_t num_problems;
+  int32_t total_tiles;
+};
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s at 1.9 GHz
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 columns of fp32 accumulator -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Shared-memory matrix descriptor (tcgen05), 128B swizzle, version 1.
+//   K-major : rows of 64 bf16 (128 B); 8-row groups 1024 B apart (SBO); LBO unused.
+//   MN-major: k-rows of 64 MN elements (128 B); 8-k-row groups 1024 B apart (SBO);
+//             consecutive 64-wide MN chunks `lbo_bytes` apart (LBO).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;  // SWIZZLE_128B
+  return d;
+}
+
+// ---------------------------------------------------------------------------
+// Epilogue for one 32-column chunk held by one thread (one output row).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_chunk(const DevEpi& e, int M, int N, int m, int n0,
+                                               const uint32_t (&acc)[32]) {
+  if (m >= M || n0 >= N) return;
+  const bool bias_on = e.bias != nullptr && (e.row_flag == nullptr || e.row_flag[m] != 0);
+  const float keep_scale = (e.drop_p > 0.f) ? 1.0f / (1.0f - e.drop_p) : 1.0f;
+  uint32_t rkey = 0;
+  if (e.post == LIREC_POST_DROPOUT || e.post == LIREC_POST_DTANH)
+    rkey = drop_row_key(e.drop_seed, e.drop_stream, static_cast<uint32_t>(m));
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int n = n0 + j;
+    float x = e.alpha * __uint_as_float(acc[j]);
+    if (n < N) {
+      if (bias_on) x += __ldg(e.bias + n);
+      if (e.act == LIREC_ACT_RELU) x = fmaxf(x, 0.f);
+      else if (e.act == LIREC_ACT_TANH) x = tanhf(x);
+      if (e.post == LIREC_POST_DROPOUT) {
+        if (e.drop_p > 0.f)
+          x = drop_keep(rkey, static_cast<uint32_t>(n + e.drop_col_off), e.drop_p) ? x * keep_scale : 0.f;
+      } else if (e.post == LIREC_POST_DRELU) {
+        const float g = __bfloat162float(e.aux[static_cast<int64_t>(m) * e.aux_ld + e.aux_col_off + n]);
+        x = (g > 0.f) ? x * e.post_scale : 0.f;
+      } else if (e.post == LIREC_POST_DTANH) {
+        const int64_t ai = static_cast<int64_t>(m) * e.aux_ld + e.aux_col_off + n;
+        const float f = __bfloat162float(e.aux[ai]) + __bfloat162float(e.aux[ai + e.aux_lo_off]);
+        bool keep = true;
+        if (e.drop_p > 0.f) keep = drop_keep(rkey, static_cast<uint32_t>(n + e.drop_col_off), e.drop_p);
+        const float t = f * (1.0f - e.drop_p);  // undo the 1/(1-p) of the forward dropout
+        x = keep ? x * keep_scale * (1.0f - t * t) : 0.f;
+      }
+    } else {
+      x = 0.f;
+    }
+    v[j] = x;
+  }
+  const int nvalid = min(32, N - n0);
+  if (e.out_kind == LIREC_OUT_F32) {
+    float* o = reinterpret_cast<float*>(e.out) + static_cast<int64_t>(m) * e.out_ld_m +
+               static_cast<int64_t>(n0) * e.out_ld_n;
+    if (e.out_ld_n == 1 && e.vec_ok && nvalid == 32) {
+      float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 w = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        if (e.accumulate) {
+          const float4 old = o4[j];
+          w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+        }
+        o4[j] = w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < nvalid) {
+          float* p = o + static_cast<int64_t>(j) * e.out_ld_n;
+          *p = e.accumulate ? (*p + v[j]) : v[j];
+        }
+      }
+    }
+  } else {  // hi/lo bf16 split
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) +
+                       static_cast<int64_t>(m) * e.out_ld_m + e.out_col_off + n0;
+    if (e.vec_ok && nvalid == 32) {
+      uint4* ohi = reinterpret_cast<uint4*>(o);
+      uint4* olo = reinterpret_cast<uint4*>(o + e.out_lo_off);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(v[8 * j + 2 * q], h0, l0);
+          split_bf16(v[8 * j + 2 * q + 1], h1, l1);
+          h[q] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
+                 (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+          l[q] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
+                 (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+        }
+        ohi[j] = make_uint4(h[0], h[1], h[2], h[3]);
+        olo[j] = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < nvalid) {
+          __nv_bfloat16 h, l;
+          split_bf16(v[j], h, l);
+          o[j] = h;
+          o[j + e.out_lo_off] = l;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// The kernel.  BN = tile columns (UMMA N), STAGES = smem ring depth.
+// ---------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+lirec_gemm_tcgen05_kernel(const __grid_constant__ GemmParams P) {
+  constexpr uint32_t A_BYTES = BM * BK * 2;  // 16 KB
+  constexpr uint32_t B_BYTES = BN * BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator buffers
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512 || TMEM_COLS == 128, "TMEM cols pow2");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tfull_bar[s]), 1);
+      mbar_init(smem_u32(&tempty_bar[s]), 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        int p = 0;
+        while (t >= P.tile_start[p + 1]) ++p;
+        const DevProblem& pr = P.probs[p];
+        const int local = t - P.tile_start[p];
+        const int m0 = (local / pr.tiles_n) * BM;
+        const int n0 = (local % pr.tiles_n) * BN;
+        for (int ps = 0; ps < pr.num_passes; ++ps) {
+          const DevPass& pa = pr.pass[ps];
+          const CUtensorMap* amap = &P.maps[pa.a_map];
+          const CUtensorMap* bmap = &P.maps[pa.b_map];
+          for (int kb = 0; kb < pa.k_blocks; ++kb) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            mbar_expect_tx(fb, STAGE_BYTES);
+            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+            const uint32_t sb = sa + A_BYTES;
+            if (!pr.a_mn_major) {
+              tma_load_2d(sa, amap, fb, pa.a_k_off + kb * BK, pa.a_mn_off + m0);
+            } else {
+#pragma unroll
+              for (int h = 0; h < BM / 64; ++h)
+                tma_load_2d(sa + h * (BK * 128), amap, fb, pa.a_mn_off + m0 + h * 64,
+                            pa.a_k_off + kb * BK);
+            }
+            if (!pr.b_mn_major) {
+              tma_load_2d(sb, bmap, fb, pa.b_k_off + kb * BK, pa.b_mn_off + n0);
+            } else {
+#pragma unroll
+              for (int h = 0; h < BN / 64; ++h)
+                tma_load_2d(sb + h * (BK * 128), bmap, fb, pa.b_mn_off + n0 + h * 64,
+                            pa.b_k_off + kb * BK);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+        int p = 0;
+        while (t >= P.tile_start[p + 1]) ++p;
+        const DevProblem& pr = P.probs[p];
+        // instruction descriptor: D=f32, A=B=bf16, majorness, N>>3, M>>4
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                               (static_cast<uint32_t>(pr.a_mn_major) << 15) |
+                               (static_cast<uint32_t>(pr.b_mn_major) << 16) |
+                               (static_cast<uint32_t>(BN >> 3) << 17) |
+                               (static_cast<uint32_t>(BM >> 4) << 24);
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        uint32_t accumulate = 0;
+        for (int ps = 0; ps < pr.num_passes; ++ps) {
+          const int kblocks = pr.pass[ps].k_blocks;
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+            const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adesc = pr.a_mn_major
+                                         ? make_smem_desc(sa + k * (UMMA_K * 128), BK * 128, 1024)
+                                         : make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+              const uint64_t bdesc = pr.b_mn_major
+                                         ? make_smem_desc(sb + k * (UMMA_K * 128), BK * 128, 1024)
+                                         : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+              tc_mma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+              accumulate = 1;
+            }
+            tc_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot when the MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        tc_commit(smem_u32(&tfull_bar[acc]));  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+      int p = 0;
+      while (t >= P.tile_start[p + 1]) ++p;
+      const DevProblem& pr = P.probs[p];
+      const int local = t - P.tile_start[p];
+      const int m0 = (local / pr.tiles_n) * BM;
+      const int n0 = (local % pr.tiles_n) * BN;
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tc_fence_after();
+      const int m = m0 + quarter * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               static_cast<uint32_t>(acc * BN + c * 32);
+        tmem_ld_32x32(taddr, r);
+        epilogue_chunk(pr.epi, pr.M, pr.N, m, n0 + c * 32, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host side: tensor maps, problem table, launch
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  int64_t rows, cols, ld;
+  int box_rows;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+
+static int encode_map(CUtensorMap* out, const MapKey& k) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(LIREC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(k.ptr) & 15) != 0 || ((k.ld * 2) & 15) != 0)
+    return fail(LIREC_ERR_ARG, "GEMM operand %p (ld=%lld) is not 16-byte aligned", k.ptr,
+                (long long)k.ld);
+  if (k.rows <= 0 || k.cols <= 0)
+    return fail(LIREC_ERR_ARG, "GEMM operand with empty extent (%lld x %lld)", (long long)k.rows,
+                (long long)k.cols);
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(k.cols), static_cast<cuuint64_t>(k.rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(k.ld) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(k.box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(k.ptr), gdim, gstr,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(LIREC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld",
+                (int)r, (long long)k.rows, (long long)k.cols, (long long)k.ld);
+  return LIREC_OK;
+}
+
+template <int BN, int STAGES>
+static int launch(const GemmParams& P, cudaStream_t stream) {
+  constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/;
+  static bool configured = false;
+  static int num_sms = 0;
+  if (!configured) {
+    LIREC_CUDA_OK(cudaFuncSetAttribute(lirec_gemm_tcgen05_kernel<BN, STAGES>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0;
+    LIREC_CUDA_OK(cudaGetDevice(&dev));
+    LIREC_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    configured = true;
+  }
+  const int grid = std::min(P.total_tiles, num_sms);
+  lirec_gemm_tcgen05_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, stream>>>(P);
+  LIREC_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return LIREC_OK;
+}
+
+int run_grouped(const lirec_gemm_problem* probs, int nprobs, cudaStream_t stream) {
+  LIREC_REQUIRE(nprobs >= 0 && nprobs <= MAX_PROBLEMS, "too many GEMM problems (%d > %d)", nprobs,
+                MAX_PROBLEMS);
+  constexpr int BN = 128;
+  static thread_local GemmParams P;  // 16 KB: keep it off the stack
+  std::vector<MapKey> keys;
+  keys.reserve(MAX_MAPS);
+  auto map_index = [&](const lirec_operand& op, bool mn_major, int tile_mn) -> int {
+    MapKey k{op.ptr, op.rows, op.cols, op.ld, mn_major ? BK : tile_mn};
+    for (size_t i = 0; i < keys.size(); ++i)
+      if (keys[i] == k) return (int)i;
+    if ((int)keys.size() >= MAX_MAPS) return -1;
+    keys.push_back(k);
+    return (int)keys.size() - 1;
+  };
+
+  // largest problems first so the static round-robin tile schedule balances
+  std::vector<int> order;
+  std::vector<double> cost(nprobs, 0.0);
+  for (int i = 0; i < nprobs; ++i) {
+    if (probs[i].M <= 0 || probs[i].N <= 0) continue;
+    int64_t k = 0;
+    for (int ps = 0; ps < probs[i].num_passes; ++ps) k += probs[i].pass[ps].k_len;
+    cost[i] = (double)k;
+    order.push_back(i);
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+
+  int np = 0, tiles = 0;
+  for (int idx : order) {
+    const lirec_gemm_problem& g = probs[idx];
+    LIREC_REQUIRE(g.num_passes >= 1 && g.num_passes <= MAX_PASSES, "problem %d: num_passes=%d", idx,
+                  g.num_passes);
+    DevProblem& d = P.probs[np];
+    d.M = g.M;
+    d.N = g.N;
+    const int tiles_m = (g.M + BM - 1) / BM;
+    d.tiles_n = (g.N + BN - 1) / BN;
+    d.num_passes = g.num_passes;
+    d.a_mn_major = g.a_mn_major ? 1 : 0;
+    d.b_mn_major = g.b_mn_major ? 1 : 0;
+    for (int ps = 0; ps < g.num_passes; ++ps) {
+      const lirec_gemm_pass& s = g.pass[ps];
+      LIREC_REQUIRE(s.k_len > 0, "problem %d pass %d: k_len=%d", idx, ps, s.k_len);
+      const int ia = map_index(s.a, d.a_mn_major, BM);
+      const int ib = map_index(s.b, d.b_mn_major, BN);
+      if (ia < 0 || ib < 0) return fail(LIREC_ERR_LIMIT, "more than %d tensor maps in one launch", MAX_MAPS);
+      d.pass[ps] = DevPass{(int16_t)ia, (int16_t)ib, s.a_mn_off, s.a_k_off, s.b_mn_off, s.b_k_off,
+                           (s.k_len + BK - 1) / BK};
+    }
+    const lirec_epilogue& e = g.epi;
+    LIREC_REQUIRE(e.out != nullptr, "problem %d: null output", idx);
+    DevEpi& de = d.epi;
+    de.alpha = e.alpha;
+    de.bias = e.bias;
+    de.row_flag = e.row_flag;
+    de.act = e.act;
+    de.post = e.post;
+    de.post_scale = e.post_scale;
+    de.drop_p = e.drop.p;
+    de.drop_seed = e.drop.seed;
+    de.drop_stream = e.drop.stream_id;
+    de.drop_col_off = e.drop.col_off;
+    de.aux = reinterpret_cast<const __nv_bfloat16*>(e.aux);
+    de.aux_ld = e.aux_ld;
+    de.aux_col_off = e.aux_col_off;
+    de.aux_lo_off = e.aux_lo_off;
+    de.out_kind = e.out_kind;
+    de.out = e.out;
+    de.out_ld_m = e.out_ld_m;
+    de.out_ld_n = e.out_ld_n;
+    de.out_col_off = e.out_col_off;
+    de.out_lo_off = e.out_lo_off;
+    de.accumulate = e.accumulate;
+    if ((e.post == LIREC_POST_DRELU || e.post == LIREC_POST_DTANH) && e.aux == nullptr)
+      return fail(LIREC_ERR_ARG, "problem %d: post op needs aux", idx);
+    const uintptr_t ob = reinterpret_cast<uintptr_t>(e.out);
+    if (e.out_kind == LIREC_OUT_F32)
+      de.vec_ok = (e.out_ld_n == 1 && (ob & 15) == 0 && (e.out_ld_m % 4) == 0) ? 1 : 0;
+    else
+      de.vec_ok = ((ob & 15) == 0 && (e.out_ld_m % 8) == 0 && (e.out_col_off % 8) == 0 &&
+                   (e.out_lo_off % 8) == 0)
+                      ? 1
+                      : 0;
+    P.tile_start[np] = tiles;
+    tiles += tiles_m * d.tiles_n;
+    ++np;
+  }
+  P.tile_start[np] = tiles;
+  for (int i = np + 1; i <= MAX_PROBLEMS; ++i) P.tile_start[i] = 0x7fffffff;
+  P.num_problems = np;
+  P.total_tiles = tiles;
+  if (tiles == 0) return LIREC_OK;
+  for (size_t i = 0; i < keys.size(); ++i) {
+    int rc = encode_map(&P.maps[i], keys[i]);
+    if (rc != LIREC_OK) return rc;
+  }
+  return launch<BN, 6>(P, stream);
+}
+
+}  // namespace gemm
+}  // namespace lirec
+
+extern "C" int lirec_gemm_grouped(const lirec_gemm_problem* problems_host, int num_problems,
+                                  void* stream) {
+  LIREC_ENTER();
+  LIREC_REQUIRE(problems_host != nullptr || num_problems == 0, "null problem table");
+  return lirec::gemm::run_grouped(problems_host, num_problems, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,306 @@
+// loss.cu — fused forward + gradient kernels of the reference's max-margin losses, over
+// ragged candidate tables, and the flat Adam step.
+//
+// The reference builds every loss from ~25-40 tiny ATen kernels plus host-side
+// np.ones masks (mlp/model.py:381-575).  Here one CTA handles one clip: it masks,
+// applies the sigmoid, scores every candidate (track-pair) slot, takes the arg-max
+// assignment (lowest index on ties, like torch.argmax), sums the hinge terms and
+// writes d(loss)/d(logits) in the same pass.  Empty slots are never materialised: the
+// reference sets them to -inf (sigma = 0, zero gradient), which is what skipping does.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace lirec {
+namespace loss {
+
+__device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];  // fixed order: deterministic
+  return t;
+}
+
+constexpr int MAX_SLOTS = 128;
+
+// MarginLoss (mlp/model.py:444-494) / MarginTrackRelsLoss (mlp/model.py:497-575).
+__global__ void __launch_bounds__(128)
+track_loss_kernel(const float* __restrict__ ints, const float* __restrict__ rels,
+                  const int32_t* __restrict__ cand_off, int B, const int32_t* __restrict__ labels,
+                  const int32_t* __restrict__ rels_label, const int32_t* __restrict__ gt_tracks,
+                  const uint8_t* __restrict__ multilab, lirec_track_loss_cfg cfg,
+                  float* __restrict__ loss_per_clip, int32_t* __restrict__ assign,
+                  float* __restrict__ d_ints, float* __restrict__ d_rels) {
+  __shared__ float s_score[MAX_SLOTS];
+  __shared__ float s_red[8];
+  __shared__ int s_tstar;
+  const int b = blockIdx.x;
+  const int beg = cand_off[b], n = cand_off[b + 1] - beg;
+  const int C = cfg.n_classes, R = cfg.n_rels;
+  const bool has_rels = R > 0;
+  const int y = labels[b];
+  const int gt0 = gt_tracks[2 * b], gt1 = gt_tracks[2 * b + 1];
+  // relationship class of the ground-truth pair(s); slots past the valid prefix carry the
+  // reference's pad label 0 (classification_dataloader.py:430)
+  int r0 = 0, r1 = 0;
+  if (has_rels) {
+    r0 = (gt0 < n) ? rels_label[beg + gt0] : 0;
+    r1 = (gt1 < n) ? rels_label[beg + gt1] : 0;
+  }
+  const float* xi = ints + static_cast<int64_t>(beg) * C;
+  const float* xr = has_rels ? rels + static_cast<int64_t>(beg) * R : nullptr;
+  float* gi = d_ints + static_cast<int64_t>(beg) * C;
+  float* gr = has_rels ? d_rels + static_cast<int64_t>(beg) * R : nullptr;
+  const float invB = 1.0f / static_cast<float>(B);
+
+  // ---- per-slot assignment score: sigma(ints[t,y]) (+ sigma(rels[t,r0])) ----
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    float sc = sigmoidf(xi[static_cast<int64_t>(t) * C + y]);
+    if (has_rels) {
+      const bool rel_on = rels_label[beg + t] != R;  // None-labelled slots are all -inf
+      const float pr = (rel_on && r0 < R) ? sigmoidf(xr[static_cast<int64_t>(t) * R + r0]) : 0.f;
+      sc = sc + pr;
+    }
+    s_score[t] = sc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int best = 0;
+    if (!cfg.tr_correct) {
+      float bv = s_score[0];
+      for (int t = 1; t < n; ++t)
+        if (s_score[t] > bv) { bv = s_score[t]; best = t; }
+      // empty slots score exactly 0 and sit after the valid prefix, so they can only win a
+      // tie against a valid slot scoring 0, which the lowest-index rule gives to the valid one
+    }
+    s_tstar = best;
+    assign[b] = best;
+  }
+  __syncthreads();
+  const int ts = s_tstar;
+  const float pos = sigmoidf(xi[static_cast<int64_t>(ts) * C + y]);
+  float pos_r = 0.f;
+  bool pos_r_live = false;
+  if (has_rels) {
+    pos_r_live = (rels_label[beg + ts] != R) && (r0 < R);
+    pos_r = pos_r_live ? sigmoidf(xr[static_cast<int64_t>(ts) * R + r0]) : 0.f;
+  }
+  const float mi = cfg.margin - pos, mr = cfg.margin - pos_r;
+  const float wi = cfg.lymbda * invB, wr = invB;
+
+  float loss_i = 0.f, cnt_i = 0.f, loss_r = 0.f, cnt_r = 0.f;
+  if (!cfg.max_neg) {
+    // ---- sum over every unmasked (slot, class) negative ----
+    for (int e = threadIdx.x; e < n * C; e += blockDim.x) {
+      const int t = e / C, c = e - t * C;
+      bool neg = multilab[static_cast<int64_t>(b) * C + c] != 0;
+      if (cfg.tr_correct) neg = neg && !(c == y && (t == gt0 || t == gt1));
+      else neg = neg && (c != y);
+      float g = 0.f;
+      if (neg) {
+        const float s = sigmoidf(xi[e]);
+        const float h = mi + s;
+        if (h > 0.f) { loss_i += h; cnt_i += 1.f; g = wi * s * (1.f - s); }
+      }
+      gi[e] = g;
+    }
+    if (has_rels) {
+      for (int e = threadIdx.x; e < n * R; e += blockDim.x) {
+        const int t = e / R, r = e - t * R;
+        const int lab = rels_label[beg + t];
+        bool neg = lab != R;
+        if (cfg.tr_correct) neg = neg && (r != lab);
+        else neg = neg && (r != r0) && (r != r1);
+        float g = 0.f;
+        if (neg) {
+          const float s = sigmoidf(xr[e]);
+          const float h = mr + s;
+          if (h > 0.f) { loss_r += h; cnt_r += 1.f; g = wr * s * (1.f - s); }
+        }
+        gr[e] = g;
+      }
+    }
+  } else {
+    // ---- max-negative variant: one hinge per slot on its hardest negative; the
+    // reference also adds relu(m - pos) for every EMPTY slot (model.py:485-486,558-562)
+    for (int e = threadIdx.x; e < n * C; e += blockDim.x) gi[e] = 0.f;
+    if (has_rels)
+      for (int e = threadIdx.x; e < n * R; e += blockDim.x) gr[e] = 0.f;
+    __syncthreads();
+    for (int t = threadIdx.x; t < cfg.max_slots; t += blockDim.x) {
+      float best = 0.f;
+      int bc = -1;
+      if (t < n) {
+        for (int c = 0; c < C; ++c) {
+          bool neg = multilab[static_cast<int64_t>(b) * C + c] != 0;
+          if (cfg.tr_correct) neg = neg && !(c == y && (t == gt0 || t == gt1));
+          else neg = neg && (c != y);
+          if (!neg) continue;
+          const float s = sigmoidf(xi[static_cast<int64_t>(t) * C + c]);
+          if (s > best) { best = s; bc = c; }
+        }
+      }
+      const float h = mi + best;
+      if (h > 0.f) {
+        loss_i += h; cnt_i += 1.f;
+        if (bc >= 0) gi[static_cast<int64_t>(t) * C + bc] = wi * best * (1.f - best);
+      }
+      if (has_rels) {
+        float bestr = 0.f;
+        int br = -1;
+        if (t < n) {
+          const int lab = rels_label[beg + t];
+          if (lab != R) {
+            for (int r = 0; r < R; ++r) {
+              const bool neg = cfg.tr_correct ? (r != lab) : (r != r0 && r != r1);
+              if (!neg) continue;
+              const float s = sigmoidf(xr[static_cast<int64_t>(t) * R + r]);
+              if (s > bestr) { bestr = s; br = r; }
+            }
+          }
+        }
+        const float hr = mr + bestr;
+        if (hr > 0.f) {
+          loss_r += hr; cnt_r += 1.f;
+          if (br >= 0) gr[static_cast<int64_t>(t) * R + br] = wr * bestr * (1.f - bestr);
+        }
+      }
+    }
+  }
+  loss_i = block_sum(loss_i, s_red);
+  cnt_i = block_sum(cnt_i, s_red);
+  if (has_rels) {
+    loss_r = block_sum(loss_r, s_red);
+    cnt_r = block_sum(cnt_r, s_red);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // the positive receives minus the number of active hinges
+    gi[static_cast<int64_t>(ts) * C + y] += -cnt_i * wi * pos * (1.f - pos);
+    if (has_rels && pos_r_live) gr[static_cast<int64_t>(ts) * R + r0] += -cnt_r * wr * pos_r * (1.f - pos_r);
+    loss_per_clip[b] = cfg.lymbda * loss_i * invB + loss_r * invB;
+  }
+}
+
+// Row-wise hinge: MaxMarginCrossEntropyLoss (model.py:422-441) and both terms of
+// MultiTaskMaxMargin (model.py:381-419).
+__global__ void __launch_bounds__(128)
+rowmargin_kernel(const float* __restrict__ logits, int64_t ld, int rows, int C,
+                 const int32_t* __restrict__ labels, const uint8_t* __restrict__ weights, float margin,
+                 float scale, float* __restrict__ loss_per_row, float* __restrict__ d_logits, int64_t d_ld) {
+  __shared__ float s_red[8];
+  const int b = blockIdx.x;
+  const int y = labels[b];
+  float* g = d_logits + static_cast<int64_t>(b) * d_ld;
+  if (y < 0) {  // row not selected (relationship label None)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) g[c] = 0.f;
+    if (threadIdx.x == 0) loss_per_row[b] = 0.f;
+    return;
+  }
+  const float* x = logits + static_cast<int64_t>(b) * ld;
+  const float pos = sigmoidf(x[y]);
+  float l = 0.f, cnt = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const bool neg = (c != y) && (weights == nullptr || weights[static_cast<int64_t>(b) * C + c] != 0);
+    float gv = 0.f;
+    if (neg) {
+      const float s = sigmoidf(x[c]);
+      const float h = margin - pos + s;
+      if (h > 0.f) { l += h; cnt += 1.f; gv = scale * s * (1.f - s); }
+    }
+    if (c != y) g[c] = gv;
+  }
+  l = block_sum(l, s_red);
+  cnt = block_sum(cnt, s_red);
+  if (threadIdx.x == 0) {
+    g[y] = -cnt * scale * pos * (1.f - pos);
+    loss_per_row[b] = l * scale;
+  }
+}
+
+// torch.optim.Adam (coupled L2) over the flat parameter buffer + bf16 shadow refresh.
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+            float* __restrict__ v, __nv_bfloat16* __restrict__ pb, int64_t n, float lr, float beta1,
+            float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const float step = lr / bc1;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    float pv = p[i];
+    const float gv = g[i] * grad_scale + wd * pv;
+    const float mv = beta1 * m[i] + (1.f - beta1) * gv;
+    const float vv = beta2 * v[i] + (1.f - beta2) * gv * gv;
+    m[i] = mv;
+    v[i] = vv;
+    pv -= step * mv / (sqrtf(vv) / bc2_sqrt + eps);
+    p[i] = pv;
+    if (pb) pb[i] = __float2bfloat16_rn(pv);
+  }
+}
+
+}  // namespace loss
+}  // namespace lirec
+
+using namespace lirec;
+
+extern "C" int lirec_loss_track_fwd_bwd(const float* ints, const float* rels, const int32_t* cand_off,
+                                        int32_t B, const int32_t* labels, const int32_t* rels_label,
+                                        const int32_t* gt_tracks, const uint8_t* multilab,
+                                        lirec_track_loss_cfg cfg, float* loss_per_clip, int32_t* assign,
+                                        float* d_ints, float* d_rels, void* stream) {
+  LIREC_ENTER();
+  LIREC_REQUIRE(ints && cand_off && labels && gt_tracks && multilab && loss_per_clip && assign && d_ints,
+                "track loss: null pointer");
+  LIREC_REQUIRE(cfg.n_classes > 0 && cfg.n_rels >= 0, "track loss: n_classes=%d n_rels=%d", cfg.n_classes,
+                cfg.n_rels);
+  LIREC_REQUIRE(cfg.n_rels == 0 || (rels && rels_label && d_rels), "track loss: rel tensors missing");
+  LIREC_REQUIRE(cfg.max_slots > 0 && cfg.max_slots <= loss::MAX_SLOTS, "track loss: max_slots=%d (limit %d)",
+                cfg.max_slots, loss::MAX_SLOTS);
+  if (B <= 0) return LIREC_OK;
+  loss::track_loss_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      ints, rels, cand_off, B, labels, rels_label, gt_tracks, multilab, cfg, loss_per_clip, assign, d_ints,
+      d_rels);
+  LIREC_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return LIREC_OK;
+}
+
+extern "C" int lirec_loss_rowmargin_fwd_bwd(const float* logits, int64_t ld, int32_t rows, int32_t C,
+                                            const int32_t* labels, const uint8_t* weights, float margin,
+                                            float scale, float* loss_per_row, float* d_logits, int64_t d_ld,
+                                            void* stream) {
+  LIREC_ENTER();
+  LIREC_REQUIRE(logits && labels && loss_per_row && d_logits && C > 0, "rowmargin loss: bad arguments");
+  if (rows <= 0) return LIREC_OK;
+  loss::rowmargin_kernel<<<rows, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, ld, rows, C, labels, weights, margin, scale, loss_per_row, d_logits, d_ld);
+  LIREC_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return LIREC_OK;
+}
+
+extern "C" int lirec_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                               void* param_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
+                               float weight_decay, int32_t step, float grad_scale, void* stream) {
+  LIREC_ENTER();
+  LIREC_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "adam: bad arguments");
+  if (n == 0) return LIREC_OK;
+  // bias corrections in double like torch's Python-side arithmetic
+  const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), static_cast<double>(step)));
+  const float bc2 = static_cast<float>(1.0 - pow(static_cast<double>(beta2), static_cast<double>(step)));
+  const int grid = static_cast<int>(std::min<int64_t>((n + 255) / 256, 148 * 16));
+  loss::adam_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      param, grad, exp_avg, exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(param_bf16), n, lr, beta1, beta2,
+      eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
+  LIREC_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return LIREC_OK;
+}

@@ -1,0 +1,365 @@
+// rows.cu — HBM-bound ragged-row kernels: segmented pooling, row expansion by offset
+// tables (forward + backward), hi/lo split and bf16 casts.
+//
+// All kernels map one CTA to one output row (or one unique bank row) and one thread
+// to a 128-bit column group, so every global access is a coalesced 16-byte load or
+// store; the reductions run sequentially over the (short) segment in registers, which
+// keeps them deterministic.
+#include "rows.cuh"
+
+namespace lirec {
+namespace rows {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// ---------------------------------------------------------------------------
+// Segmented max / mean over ragged [total, dim] fp32 rows.
+// Reference: np.max(..., axis=0) in mixed_utils/mixed_features.py:54,61,105; an empty
+// segment yields zeros (text_features.py:171-178, mixed_features.py:89-93).
+// NaN propagates like np.max.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+seg_reduce_kernel(const float* __restrict__ x, const int32_t* __restrict__ seg_off, int dim,
+                  int mode, float* __restrict__ out_f32, int64_t out_f32_ld,
+                  __nv_bfloat16* __restrict__ out_bf16, int64_t out_bf16_ld) {
+  const int seg = blockIdx.x;
+  const int col = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  if (col >= dim) return;
+  const int beg = seg_off[seg], end = seg_off[seg + 1];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (end > beg) {
+    const float* p = x + static_cast<int64_t>(beg) * dim + col;
+    if (mode == 0) {
+      acc = ld4(p);
+      int r = beg + 1;
+      p += dim;
+      // 4 independent 128-bit loads in flight per thread
+      for (; r + 3 < end; r += 4, p += 4 * static_cast<int64_t>(dim)) {
+        const float4 a = ld4(p), b = ld4(p + dim), c = ld4(p + 2 * static_cast<int64_t>(dim)),
+                     d = ld4(p + 3 * static_cast<int64_t>(dim));
+#define LIREC_MAXN(m, v) m = ((v) > (m) || (v) != (v)) ? (v) : (m)
+        LIREC_MAXN(acc.x, a.x); LIREC_MAXN(acc.y, a.y); LIREC_MAXN(acc.z, a.z); LIREC_MAXN(acc.w, a.w);
+        LIREC_MAXN(acc.x, b.x); LIREC_MAXN(acc.y, b.y); LIREC_MAXN(acc.z, b.z); LIREC_MAXN(acc.w, b.w);
+        LIREC_MAXN(acc.x, c.x); LIREC_MAXN(acc.y, c.y); LIREC_MAXN(acc.z, c.z); LIREC_MAXN(acc.w, c.w);
+        LIREC_MAXN(acc.x, d.x); LIREC_MAXN(acc.y, d.y); LIREC_MAXN(acc.z, d.z); LIREC_MAXN(acc.w, d.w);
+      }
+      for (; r < end; ++r, p += dim) {
+        const float4 a = ld4(p);
+        LIREC_MAXN(acc.x, a.x); LIREC_MAXN(acc.y, a.y); LIREC_MAXN(acc.z, a.z); LIREC_MAXN(acc.w, a.w);
+      }
+#undef LIREC_MAXN
+    } else {
+      for (int r = beg; r < end; ++r, p += dim) {
+        const float4 a = ld4(p);
+        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+      }
+      const float inv = 1.0f / static_cast<float>(end - beg);
+      acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    }
+  }
+  if (out_f32) *reinterpret_cast<float4*>(out_f32 + static_cast<int64_t>(seg) * out_f32_ld + col) = acc;
+  if (out_bf16) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(acc.z, acc.w);
+    uint2 w;
+    w.x = *reinterpret_cast<uint32_t*>(&lo);
+    w.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(out_bf16 + static_cast<int64_t>(seg) * out_bf16_ld + col) = w;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Forward expansion: unique layer-1 rows -> encoder rows (ints) or per-candidate
+// masked means over context rows (ctx), with the layer-1 dropout mask.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void store_split4(__nv_bfloat16* hi_ptr, __nv_bfloat16* lo_ptr, float4 v) {
+  __nv_bfloat16 h[4], l[4];
+  split_bf16(v.x, h[0], l[0]);
+  split_bf16(v.y, h[1], l[1]);
+  split_bf16(v.z, h[2], l[2]);
+  split_bf16(v.w, h[3], l[3]);
+  uint2 wh, wl;
+  wh.x = __bfloat16_as_ushort(h[0]) | (static_cast<uint32_t>(__bfloat16_as_ushort(h[1])) << 16);
+  wh.y = __bfloat16_as_ushort(h[2]) | (static_cast<uint32_t>(__bfloat16_as_ushort(h[3])) << 16);
+  wl.x = __bfloat16_as_ushort(l[0]) | (static_cast<uint32_t>(__bfloat16_as_ushort(l[1])) << 16);
+  wl.y = __bfloat16_as_ushort(l[2]) | (static_cast<uint32_t>(__bfloat16_as_ushort(l[3])) << 16);
+  *reinterpret_cast<uint2*>(hi_ptr) = wh;
+  *reinterpret_cast<uint2*>(lo_ptr) = wl;
+}
+
+__global__ void __launch_bounds__(128)
+expand_fwd_kernel(const ExpandFwdJobs jobs) {
+  const ExpandFwdJob& jb = jobs.job[blockIdx.y];
+  const int o = blockIdx.x;
+  if (o >= jb.n_out) return;
+  const int J = jb.J;
+  const float* __restrict__ src[4] = {jb.r1[0], jb.r1[1], jb.r1[2], jb.r1[3]};
+  int beg = o, end = o + 1;
+  if (jb.seg_off) { beg = jb.seg_off[o]; end = jb.seg_off[o + 1]; }
+  const int n = end - beg;
+  for (int j = threadIdx.x * 4; j < J; j += blockDim.x * 4) {
+    float4 acc[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int x = beg; x < end; ++x) {
+      const int3 idx = *reinterpret_cast<const int3*>(jb.rows + 3 * static_cast<int64_t>(x));
+      const int u[4] = {idx.x, idx.x, idx.y, idx.z};
+      const uint32_t rkey = drop_row_key(jb.drop.seed, jb.drop.stream_id, static_cast<uint32_t>(x));
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        float4 v = ld4(src[s] + static_cast<int64_t>(u[s]) * J + j);
+        if (jb.drop.p > 0.f) {
+          const uint32_t c = static_cast<uint32_t>(jb.drop.col_off + s * J + j);
+          if (!drop_keep(rkey, c, jb.drop.p)) v.x = 0.f;
+          if (!drop_keep(rkey, c + 1, jb.drop.p)) v.y = 0.f;
+          if (!drop_keep(rkey, c + 2, jb.drop.p)) v.z = 0.f;
+          if (!drop_keep(rkey, c + 3, jb.drop.p)) v.w = 0.f;
+        }
+        acc[s].x += v.x; acc[s].y += v.y; acc[s].z += v.z; acc[s].w += v.w;
+      }
+    }
+    if (jb.seg_off) {
+      // masked mean over the segment; empty segment: 0 (guard) or 0/0 = NaN (reference
+      // MidFusionMultiClip has no guard, mlp/model.py:175 vs :303)
+      const float inv = (n > 0) ? 1.0f / static_cast<float>(n)
+                                : (jb.guard_zero ? 0.f : __int_as_float(0x7fc00000));
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        if (n > 0 || jb.guard_zero) {
+          acc[s].x *= inv; acc[s].y *= inv; acc[s].z *= inv; acc[s].w *= inv;
+        } else {
+          acc[s] = make_float4(inv, inv, inv, inv);
+        }
+      }
+    }
+    __nv_bfloat16* orow = jb.out + static_cast<int64_t>(o) * jb.out_ld;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) store_split4(orow + s * 2 * J + j, orow + s * 2 * J + J + j, acc[s]);
+  }
+  if (jb.row_flag_out && threadIdx.x == 0) jb.row_flag_out[o] = (n > 0) ? 1 : 0;
+  if (jb.flag_bf16_out && threadIdx.x < 64)
+    jb.flag_bf16_out[static_cast<int64_t>(o) * 64 + threadIdx.x] = __float2bfloat16_rn(n > 0 ? 1.f : 0.f);
+}
+
+// ---------------------------------------------------------------------------
+// Backward of the expansion onto the unique rows of one bank slot:
+//   dZ1[u] = [r1[u] > 0] * sum_{i in inv(u)} keep(i) * w_i * d_in[o_i]
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+expand_bwd_kernel(const ExpandBwdJobs jobs) {
+  const ExpandBwdJob& jb = jobs.job[blockIdx.y];
+  const int u = blockIdx.x;
+  if (u >= jb.n_unique) return;
+  const int J = jb.J;
+  const int beg = jb.inv_off[u], end = jb.inv_off[u + 1];
+  for (int j = threadIdx.x * 4; j < J; j += blockDim.x * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = beg; q < end; ++q) {
+      const int i = jb.inv_idx[q];
+      int o = i;
+      float w = 1.0f;
+      if (jb.owner) {
+        o = jb.owner[i];
+        w = 1.0f / static_cast<float>(jb.seg_off[o + 1] - jb.seg_off[o]);
+      }
+      float4 g = ld4(jb.d_in + static_cast<int64_t>(o) * jb.d_ld + j);
+      if (jb.drop.p > 0.f) {
+        const uint32_t rkey = drop_row_key(jb.drop.seed, jb.drop.stream_id, static_cast<uint32_t>(i));
+        const uint32_t c = static_cast<uint32_t>(jb.drop.col_off + jb.slot * J + j);
+        if (!drop_keep(rkey, c, jb.drop.p)) g.x = 0.f;
+        if (!drop_keep(rkey, c + 1, jb.drop.p)) g.y = 0.f;
+        if (!drop_keep(rkey, c + 2, jb.drop.p)) g.z = 0.f;
+        if (!drop_keep(rkey, c + 3, jb.drop.p)) g.w = 0.f;
+      }
+      acc.x += w * g.x; acc.y += w * g.y; acc.z += w * g.z; acc.w += w * g.w;
+    }
+    const float4 r = ld4(jb.r1 + static_cast<int64_t>(u) * J + j);
+    if (!(r.x > 0.f)) acc.x = 0.f;
+    if (!(r.y > 0.f)) acc.y = 0.f;
+    if (!(r.z > 0.f)) acc.z = 0.f;
+    if (!(r.w > 0.f)) acc.w = 0.f;
+    __nv_bfloat16* orow = jb.out + static_cast<int64_t>(u) * jb.out_ld;
+    store_split4(orow + j, orow + J + j, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// fp32 -> hi/lo bf16 split with zero padding; fp32 -> bf16 cast
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+split_kernel(const float* __restrict__ x, int64_t ld, int rows, int cols, __nv_bfloat16* __restrict__ out,
+             int64_t out_ld, int pad_cols) {
+  const int64_t total = static_cast<int64_t>(rows) * pad_cols;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / pad_cols), c = static_cast<int>(i % pad_cols);
+    const float v = (c < cols) ? x[r * ld + c] : 0.f;
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    out[r * out_ld + c] = h;
+    out[r * out_ld + pad_cols + c] = l;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t n) {
+  const int64_t n4 = n / 4;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 w;
+    w.x = *reinterpret_cast<uint32_t*>(&a);
+    w.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(out)[i] = w;
+  }
+  for (int64_t i = n4 * 4 + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride)
+    out[i] = __float2bfloat16_rn(x[i]);
+}
+
+// ---------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------
+int seg_reduce(const float* x, const int32_t* seg_off, int nseg, int dim, int mode, float* out_f32,
+               int64_t out_f32_ld, void* out_bf16, int64_t out_bf16_ld, cudaStream_t stream) {
+  LIREC_REQUIRE(dim > 0 && dim % 4 == 0, "seg_reduce: dim=%d must be a positive multiple of 4", dim);
+  LIREC_REQUIRE(mode == 0 || mode == 1, "seg_reduce: mode=%d", mode);
+  LIREC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "seg_reduce: x not 16-byte aligned");
+  LIREC_REQUIRE(out_f32 || out_bf16, "seg_reduce: no output");
+  LIREC_REQUIRE(!out_f32 || ((reinterpret_cast<uintptr_t>(out_f32) & 15) == 0 && out_f32_ld % 4 == 0),
+                "seg_reduce: fp32 output not 16-byte aligned");
+  LIREC_REQUIRE(!out_bf16 || ((reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0 && out_bf16_ld % 4 == 0),
+                "seg_reduce: bf16 output not 8-byte aligned");
+  if (nseg <= 0) return LIREC_OK;
+  dim3 grid(nseg, (dim / 4 + 127) / 128);
+  seg_reduce_kernel<<<grid, 128, 0, stream>>>(x, seg_off, dim, mode, out_f32, out_f32_ld,
+                                              reinterpret_cast<__nv_bfloat16*>(out_bf16), out_bf16_ld);
+  LIREC_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return LIREC_OK;
+}
+
+int expand_fwd(const ExpandFwdJobs& jobs, cudaStream_t stream) {
+  int max_out = 0;
+  for (int i = 0; i < jobs.n; ++i) {
+    const ExpandFwdJob& j = jobs.job[i];
+    LIREC_REQUIRE(j.J > 0 && j.J % 4 == 0, "expand_fwd: J=%d", j.J);
+    LIREC_REQUIRE(j.out_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(j.out) & 7) == 0,
+                  "expand_fwd: output not 8-byte aligned");
+    max_out = std::max(max_out, j.n_out);
+  }
+  if (max_out == 0 || jobs.n == 0) return LIREC_OK;
+  dim3 grid(max_out, jobs.n);
+  expand_fwd_kernel<<<grid, 128, 0, stream>>>(jobs);
+  LIREC_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return LIREC_OK;
+}
+
+int expand_bwd(const ExpandBwdJobs& jobs, cudaStream_t stream) {
+  int max_u = 0;
+  for (int i = 0; i < jobs.n; ++i) {
+    const ExpandBwdJob& j = jobs.job[i];
+    LIREC_REQUIRE(j.J > 0 && j.J % 4 == 0 && j.d_ld % 4 == 0, "expand_bwd: J=%d d_ld=%lld", j.J,
+                  (long long)j.d_ld);
+    max_u = std::max(max_u, j.n_unique);
+  }
+  if (max_u == 0 || jobs.n == 0) return LIREC_OK;
+  dim3 grid(max_u, jobs.n);
+  expand_bwd_kernel<<<grid, 128, 0, stream>>>(jobs);
+  LIREC_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return LIREC_OK;
+}
+
+int split_f32(const float* x, int64_t ld, int rows, int cols, void* out, int64_t out_ld, int pad_cols,
+              cudaStream_t stream) {
+  LIREC_REQUIRE(pad_cols >= cols && out_ld >= 2 * pad_cols, "split_f32: pad_cols=%d cols=%d out_ld=%lld",
+                pad_cols, cols, (long long)out_ld);
+  if (rows <= 0) return LIREC_OK;
+  const int64_t total = static_cast<int64_t>(rows) * pad_cols;
+  const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 8));
+  split_kernel<<<grid, 256, 0, stream>>>(x, ld, rows, cols, reinterpret_cast<__nv_bfloat16*>(out), out_ld,
+                                         pad_cols);
+  LIREC_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return LIREC_OK;
+}
+
+int cast_bf16(const float* x, void* out, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return LIREC_OK;
+  LIREC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0,
+                "cast_bf16: pointers not aligned");
+  const int grid = static_cast<int>(std::min<int64_t>((n / 4 + 255) / 256 + 1, 148 * 8));
+  cast_bf16_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), n);
+  LIREC_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return LIREC_OK;
+}
+
+}  // namespace rows
+}  // namespace lirec
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+using namespace lirec;
+
+extern "C" int lirec_seg_reduce_f32(const float* x, const int32_t* seg_off, int32_t nseg, int32_t dim,
+                                    int32_t mode, float* out_f32, int64_t out_f32_ld, void* out_bf16,
+                                    int64_t out_bf16_ld, void* stream) {
+  LIREC_ENTER();
+  return rows::seg_reduce(x, seg_off, nseg, dim, mode, out_f32, out_f32_ld, out_bf16, out_bf16_ld,
+                          static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lirec_rows_expand_fwd(const float* r1_txt, const float* r1_vis, const float* r1_tr1,
+                                     const float* r1_tr2, int32_t J, const int32_t* rows_tbl,
+                                     const int32_t* seg_off, int32_t n_out, int32_t guard_zero,
+                                     lirec_dropout drop, void* out_split, int64_t out_ld,
+                                     int32_t* row_flag_out, void* stream) {
+  LIREC_ENTER();
+  rows::ExpandFwdJobs jobs;
+  jobs.n = 1;
+  rows::ExpandFwdJob& j = jobs.job[0];
+  j.r1[0] = r1_txt; j.r1[1] = r1_vis; j.r1[2] = r1_tr1; j.r1[3] = r1_tr2;
+  j.J = J;
+  j.rows = rows_tbl;
+  j.seg_off = seg_off;
+  j.n_out = n_out;
+  j.guard_zero = guard_zero;
+  j.drop = drop;
+  j.out = reinterpret_cast<__nv_bfloat16*>(out_split);
+  j.out_ld = out_ld;
+  j.row_flag_out = row_flag_out;
+  j.flag_bf16_out = nullptr;
+  return rows::expand_fwd(jobs, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lirec_rows_expand_bwd(const float* d_in, int64_t d_ld, const float* r1, int32_t J,
+                                     int32_t slot, const int32_t* inv_off, const int32_t* inv_idx,
+                                     int32_t n_unique, const int32_t* owner, const int32_t* seg_off,
+                                     lirec_dropout drop, void* out_split, int64_t out_ld, void* stream) {
+  LIREC_ENTER();
+  LIREC_REQUIRE((owner == nullptr) == (seg_off == nullptr), "expand_bwd: owner and seg_off go together");
+  rows::ExpandBwdJobs jobs;
+  jobs.n = 1;
+  rows::ExpandBwdJob& j = jobs.job[0];
+  j.d_in = d_in; j.d_ld = d_ld; j.r1 = r1; j.J = J; j.slot = slot;
+  j.inv_off = inv_off; j.inv_idx = inv_idx; j.n_unique = n_unique;
+  j.owner = owner; j.seg_off = seg_off; j.drop = drop;
+  j.out = reinterpret_cast<__nv_bfloat16*>(out_split);
+  j.out_ld = out_ld;
+  return rows::expand_bwd(jobs, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lirec_split_f32(const float* x, int64_t ld, int32_t rows_n, int32_t cols, void* out_split,
+                               int64_t out_ld, int32_t pad_cols, void* stream) {
+  LIREC_ENTER();
+  return rows::split_f32(x, ld, rows_n, cols, out_split, out_ld, pad_cols, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lirec_cast_bf16(const float* x, void* out, int64_t n, void* stream) {
+  LIREC_ENTER();
+  return rows::cast_bf16(x, out, n, static_cast<cudaStream_t>(stream));
+}

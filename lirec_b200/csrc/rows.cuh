@@ -1,0 +1,60 @@
+// rows.cuh — job tables and host launchers of the ragged-row kernels (rows.cu).
+#pragma once
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace lirec {
+namespace rows {
+
+constexpr int MAX_JOBS = 8;
+
+// One expansion: unique layer-1 rows (4 bank slots) -> n_out split rows.
+struct ExpandFwdJob {
+  const float* r1[4];       // relu(L1) of the unique rows: txt, vis, tr1, tr2; each [*, J]
+  int32_t J;
+  const int32_t* rows;      // [n_rows, 3] (clip, track1, track2)
+  const int32_t* seg_off;   // NULL (one row per output) or [n_out + 1]
+  int32_t n_out;
+  int32_t guard_zero;
+  lirec_dropout drop;
+  __nv_bfloat16* out;       // [n_out, out_ld], slot s at columns [s*2J, (s+1)*2J) as hi|lo
+  int64_t out_ld;
+  int32_t* row_flag_out;    // [n_out] or NULL: 1 where the segment is non-empty
+  __nv_bfloat16* flag_bf16_out;  // [n_out, 64] or NULL: the same flag as a bf16 GEMM operand
+};
+struct ExpandFwdJobs {
+  ExpandFwdJob job[MAX_JOBS];
+  int32_t n;
+};
+
+// One scatter-reduce: gradient of the expanded rows -> unique rows of one slot.
+struct ExpandBwdJob {
+  const float* d_in;        // [n_out, d_ld] fp32 (column offset of the slot already applied)
+  int64_t d_ld;
+  const float* r1;          // [n_unique, J]
+  int32_t J, slot;
+  const int32_t* inv_off;   // [n_unique + 1]
+  const int32_t* inv_idx;   // table rows referencing each unique row
+  int32_t n_unique;
+  const int32_t* owner;     // NULL (ints) or [n_rows] candidate of each context row
+  const int32_t* seg_off;   // NULL or [n_out + 1]
+  lirec_dropout drop;
+  __nv_bfloat16* out;       // [n_unique, out_ld] hi|lo
+  int64_t out_ld;
+};
+struct ExpandBwdJobs {
+  ExpandBwdJob job[MAX_JOBS];
+  int32_t n;
+};
+
+int seg_reduce(const float* x, const int32_t* seg_off, int nseg, int dim, int mode, float* out_f32,
+               int64_t out_f32_ld, void* out_bf16, int64_t out_bf16_ld, cudaStream_t stream);
+int expand_fwd(const ExpandFwdJobs& jobs, cudaStream_t stream);
+int expand_bwd(const ExpandBwdJobs& jobs, cudaStream_t stream);
+int split_f32(const float* x, int64_t ld, int rows, int cols, void* out, int64_t out_ld, int pad_cols,
+              cudaStream_t stream);
+int cast_bf16(const float* x, void* out, int64_t n, cudaStream_t stream);
+
+}  // namespace rows
+}  // namespace lirec

@@ -1,0 +1,138 @@
+"""Thin torch-tensor wrappers over the C ABI (one function per entry point).
+
+These are the calls the unit parity tests exercise op by op; the model itself goes through
+lirec_model_forward / lirec_model_backward (see lirec_b200/mlp/model.py).
+"""
+import ctypes as C
+
+import torch
+
+from . import _ext
+from ._ext import (ACT_NONE, ACT_RELU, ACT_TANH, OUT_F32, OUT_SPLIT, POST_DRELU, POST_DROPOUT, POST_DTANH,
+                   POST_NONE)
+
+__all__ = ["gemm_problem", "gemm_grouped", "seg_reduce", "rows_expand_fwd", "rows_expand_bwd", "split_f32",
+           "cast_bf16", "loss_track", "loss_rowmargin", "adam_flat", "dropout_desc"]
+
+
+def dropout_desc(p=0.0, seed=0, stream_id=0, col_off=0):
+    d = _ext.Dropout()
+    d.p, d.seed, d.stream_id, d.col_off = float(p), int(seed) & 0xFFFFFFFF, int(stream_id), int(col_off)
+    return d
+
+
+def gemm_problem(M, N, passes, a_mn_major=False, b_mn_major=False, alpha=1.0, bias=None, row_flag=None,
+                 act=ACT_NONE, post=POST_NONE, post_scale=1.0, drop=None, aux=None, aux_col_off=0,
+                 aux_lo_off=0, out=None, out_kind=OUT_F32, out_ld_m=None, out_ld_n=1, out_col_off=0,
+                 out_lo_off=0, accumulate=False):
+    """passes: list of (a_operand, a_mn_off, a_k_off, b_operand, b_mn_off, b_k_off, k_len)."""
+    g = _ext.GemmProblem()
+    g.M, g.N = int(M), int(N)
+    g.a_mn_major, g.b_mn_major = int(a_mn_major), int(b_mn_major)
+    g.num_passes = len(passes)
+    assert 1 <= len(passes) <= _ext.MAX_PASSES
+    for i, (a, amn, ak, b, bmn, bk, klen) in enumerate(passes):
+        p = g.pass_[i]
+        p.a, p.b = a, b
+        p.a_mn_off, p.a_k_off, p.b_mn_off, p.b_k_off, p.k_len = int(amn), int(ak), int(bmn), int(bk), int(klen)
+    e = g.epi
+    e.alpha = float(alpha)
+    e.bias = _ext.ptr(bias)
+    e.row_flag = _ext.ptr(row_flag)
+    e.act, e.post, e.post_scale = int(act), int(post), float(post_scale)
+    e.drop = drop if drop is not None else dropout_desc()
+    if aux is not None:
+        e.aux, e.aux_ld = aux.data_ptr(), aux.stride(0)
+    e.aux_col_off, e.aux_lo_off = int(aux_col_off), int(aux_lo_off)
+    e.out_kind = int(out_kind)
+    e.out = out.data_ptr()
+    e.out_ld_m = int(out.stride(0) if out_ld_m is None else out_ld_m)
+    e.out_ld_n = int(out_ld_n)
+    e.out_col_off, e.out_lo_off = int(out_col_off), int(out_lo_off)
+    e.accumulate = int(accumulate)
+    return g
+
+
+def gemm_grouped(problems):
+    _ext.gemm_grouped(problems)
+
+
+def seg_reduce(x, seg_off, mode="max", out_f32=None, out_bf16=None):
+    """Segmented max/mean of ragged fp32 rows. x [total, dim], seg_off int32 [nseg+1]."""
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
+    assert seg_off.dtype == torch.int32
+    nseg = seg_off.numel() - 1
+    L = _ext.lib()
+    _ext.check(L.lirec_seg_reduce_f32(
+        _ext.ptr(x), _ext.ptr(seg_off), nseg, x.shape[1], 0 if mode == "max" else 1,
+        _ext.ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
+        _ext.ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, _ext.stream_ptr()))
+
+
+def rows_expand_fwd(r1, J, rows, seg_off, n_out, guard_zero, drop, out_split, row_flag_out=None):
+    L = _ext.lib()
+    _ext.check(L.lirec_rows_expand_fwd(
+        _ext.ptr(r1[0]), _ext.ptr(r1[1]), _ext.ptr(r1[2]), _ext.ptr(r1[3]), J, _ext.ptr(rows),
+        _ext.ptr(seg_off), n_out, int(guard_zero), drop, _ext.ptr(out_split), out_split.stride(0),
+        _ext.ptr(row_flag_out), _ext.stream_ptr()))
+
+
+def rows_expand_bwd(d_in, d_ld, r1, J, slot, inv_off, inv_idx, n_unique, owner, seg_off, drop, out_split,
+                    d_in_col_off=0):
+    L = _ext.lib()
+    _ext.check(L.lirec_rows_expand_bwd(
+        d_in.data_ptr() + 4 * d_in_col_off, d_ld, _ext.ptr(r1), J, slot, _ext.ptr(inv_off), _ext.ptr(inv_idx),
+        n_unique, _ext.ptr(owner), _ext.ptr(seg_off), drop, _ext.ptr(out_split), out_split.stride(0),
+        _ext.stream_ptr()))
+
+
+def split_f32(x, out_split, pad_cols):
+    L = _ext.lib()
+    _ext.check(L.lirec_split_f32(_ext.ptr(x), x.stride(0), x.shape[0], x.shape[1], _ext.ptr(out_split),
+                                 out_split.stride(0), pad_cols, _ext.stream_ptr()))
+
+
+def cast_bf16(x, out):
+    L = _ext.lib()
+    _ext.check(L.lirec_cast_bf16(_ext.ptr(x), _ext.ptr(out), x.numel(), _ext.stream_ptr()))
+
+
+def loss_track(ints, rels, cand_off, labels, rels_label, gt_tracks, multilab, margin, lymbda, n_rels,
+               tr_correct=False, max_neg=False, max_slots=20):
+    """Fused MarginLoss / MarginTrackRelsLoss. Returns (loss_per_clip, assign, d_ints, d_rels)."""
+    B = cand_off.numel() - 1
+    Ni, Cc = ints.shape
+    cfg = _ext.TrackLossCfg()
+    cfg.margin, cfg.lymbda = float(margin), float(lymbda)
+    cfg.n_classes, cfg.n_rels = int(Cc), int(n_rels)
+    cfg.tr_correct, cfg.max_neg, cfg.max_slots = int(tr_correct), int(max_neg), int(max_slots)
+    loss = torch.empty(B, dtype=torch.float32, device=ints.device)
+    assign = torch.empty(B, dtype=torch.int32, device=ints.device)
+    d_ints = torch.empty_like(ints)
+    d_rels = torch.empty_like(rels) if n_rels > 0 else None
+    L = _ext.lib()
+    _ext.check(L.lirec_loss_track_fwd_bwd(
+        _ext.ptr(ints), _ext.ptr(rels) if n_rels > 0 else None, _ext.ptr(cand_off), B, _ext.ptr(labels),
+        _ext.ptr(rels_label) if n_rels > 0 else None, _ext.ptr(gt_tracks), _ext.ptr(multilab), cfg,
+        _ext.ptr(loss), _ext.ptr(assign), _ext.ptr(d_ints), _ext.ptr(d_rels), _ext.stream_ptr()))
+    return loss, assign, d_ints, d_rels
+
+
+def loss_rowmargin(logits, labels, weights, margin, scale):
+    rows, Cc = logits.shape
+    loss = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    d = torch.empty_like(logits)
+    L = _ext.lib()
+    _ext.check(L.lirec_loss_rowmargin_fwd_bwd(
+        _ext.ptr(logits), logits.stride(0), rows, Cc, _ext.ptr(labels), _ext.ptr(weights), float(margin),
+        float(scale), _ext.ptr(loss), _ext.ptr(d), d.stride(0), _ext.stream_ptr()))
+    return loss, d
+
+
+def adam_flat(param, grad, exp_avg, exp_avg_sq, param_bf16, lr, beta1, beta2, eps, weight_decay, step,
+              grad_scale=1.0):
+    L = _ext.lib()
+    _ext.check(L.lirec_adam_flat(_ext.ptr(param), _ext.ptr(grad), _ext.ptr(exp_avg), _ext.ptr(exp_avg_sq),
+                                 _ext.ptr(param_bf16), param.numel(), float(lr), float(beta1), float(beta2),
+                                 float(eps), float(weight_decay), int(step), float(grad_scale),
+                                 _ext.stream_ptr()))

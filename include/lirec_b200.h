@@ -288,6 +288,10 @@ int lirec_model_backward(const lirec_model_cfg* cfg, const lirec_model_params* p
                          const lirec_batch* batch, void* workspace, size_t workspace_bytes,
                          const float* d_ints, const float* d_rels, void* stream);
 
+/* White-box test aid: byte offsets of the named workspace buffers (see csrc/model.cu). */
+int lirec_model_workspace_layout(const lirec_model_cfg* cfg, const lirec_batch* batch_host,
+                                 int64_t* offsets, int max_entries);
+
 /* ---- optimizer -----------------------------------------------------------
  * torch.optim.Adam with coupled L2 (reference mlp/model.py:599-601) over one
  * flat buffer; also refreshes the bf16 shadow of the weights.                */

@@ -135,6 +135,7 @@ def lib():
                                                                                   C.c_void_p]
     L.lirec_model_workspace_bytes.argtypes = [C.c_void_p, C.c_void_p]
     L.lirec_model_workspace_bytes.restype = C.c_size_t
+    L.lirec_model_workspace_layout.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.lirec_model_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                       C.c_void_p, C.c_void_p, C.c_void_p]
     L.lirec_model_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
@@ -149,7 +150,7 @@ EXPORTED_SYMBOLS = [
     "lirec_abi_version", "lirec_last_error", "lirec_device_check", "lirec_last_launch_count",
     "lirec_gemm_grouped", "lirec_seg_reduce_f32", "lirec_rows_expand_fwd", "lirec_rows_expand_bwd",
     "lirec_split_f32", "lirec_cast_bf16", "lirec_loss_track_fwd_bwd", "lirec_loss_rowmargin_fwd_bwd",
-    "lirec_model_workspace_bytes", "lirec_model_forward", "lirec_model_backward", "lirec_adam_flat",
+    "lirec_model_workspace_bytes", "lirec_model_workspace_layout", "lirec_model_forward", "lirec_model_backward", "lirec_adam_flat",
 ]
 
 # kernels launched through this binding since import (bench.py reports it as gpu_launches)

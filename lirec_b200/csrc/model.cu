@@ -524,6 +524,27 @@ extern "C" size_t lirec_model_workspace_bytes(const lirec_model_cfg* cfg, const 
   return model::carve(d, nullptr).bytes;
 }
 
+// Debug / white-box test aid: byte offsets of the workspace buffers, in the order
+// r1[2][4], dz1[2][4], a2[2], f2[2], dz2[2], da2[2], flag_c, flag_bf16, ones, g2, dpreg2, dli2, dlr2
+// (-1 for buffers the configuration does not use).  Returns the number of entries written.
+extern "C" int lirec_model_workspace_layout(const lirec_model_cfg* cfg, const lirec_batch* batch_host,
+                                            int64_t* offsets, int max_entries) {
+  if (!cfg || !batch_host || !offsets || max_entries < 31) return -1;
+  const model::Dims d = model::make_dims(*cfg, *batch_host);
+  char* base = reinterpret_cast<char*>(static_cast<uintptr_t>(4096));
+  const model::Workspace w = model::carve(d, base);
+  int n = 0;
+  auto put = [&](const void* p) { offsets[n++] = p ? (reinterpret_cast<const char*>(p) - base) : -1; };
+  for (int br = 0; br < 2; ++br) for (int s = 0; s < 4; ++s) put(w.r1[br][s]);
+  for (int br = 0; br < 2; ++br) for (int s = 0; s < 4; ++s) put(w.dz1[br][s]);
+  for (int br = 0; br < 2; ++br) put(w.a2[br]);
+  for (int br = 0; br < 2; ++br) put(w.f2[br]);
+  for (int br = 0; br < 2; ++br) put(w.dz2[br]);
+  for (int br = 0; br < 2; ++br) put(w.da2[br]);
+  put(w.flag_c); put(w.flag_bf16); put(w.ones); put(w.g2); put(w.dpreg2); put(w.dli2); put(w.dlr2);
+  return n;
+}
+
 extern "C" int lirec_model_forward(const lirec_model_cfg* cfg, const lirec_model_params* params,
                                    const lirec_batch* batch, void* workspace, size_t workspace_bytes,
                                    float* out_ints, float* out_rels, void* stream) {

@@ -1,0 +1,528 @@
+"""Model family, losses and factory — the reference's mlp/model.py surface on the B200 path.
+
+Same class names, constructor signatures `(n_classes, n_rels=0)`, `forward(x: dict) ->
+{'inters', 'rels'}`, loss `forward(output, batch) -> scalar`, `create_model(n_classes, n_rels)
+-> (model, loss, optimizer)` and the same `state_dict` names/shapes as the reference
+(mlp/model.py:19-609), so released checkpoints load and `torch.optim.Adam` / `torch.save` keep
+working.  Everything numeric happens in liblirec_b200.so (hand-written sm_100a kernels behind the
+C ABI of include/lirec_b200.h); the nn.Linear submodules below only OWN parameters — their
+storage is re-pointed into one flat fp32 buffer (plus a flat gradient buffer and a bf16 shadow)
+that the kernels read and write in place.  There is no PyTorch or CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from lirec_b200 import _ext, ops
+from lirec_b200.packing import PackedBatch, pack_dense_batch
+from lirec_b200.utils.arg_pars import opt
+
+__all__ = ["Modalities", "MidFusionMultiClip", "MidFusionMultiClipMaxTracks", "GatingUnit",
+           "MultiTaskCrossEntropyLoss", "MultiTaskMaxMargin", "MaxMarginCrossEntropyLoss", "MarginLoss",
+           "MarginTrackRelsLoss", "create_model", "ModelOutput", "FlatAdam"]
+
+_SLOTS = ("txt", "vis", "tracks1", "tracks2")
+_SECOND = ("txt2", "vis2", "tracks12", "tracks22")
+
+
+class ModelOutput(dict):
+    """{'inters', 'rels'} like the reference, produced lazily from the ragged logits.
+
+    `ragged_inters` [Ni, C] / `ragged_rels` [Ni, R] are what the kernels wrote and what the fused
+    losses read.  The dense reference-shaped tensors ([B, T, C] / [B, T, R] for the track models)
+    are only materialised when somebody indexes the dict (evaluation code); empty candidate slots
+    hold -inf there, which is what the reference's track losses leave behind (mlp/model.py:460, 512).
+    """
+
+    def __init__(self, batch, ragged_inters, ragged_rels, dense_tracks):
+        super().__init__()
+        self.batch = batch
+        self.ragged_inters = ragged_inters
+        self.ragged_rels = ragged_rels
+        self._dense_tracks = dense_tracks
+        dict.__setitem__(self, "inters", None)
+        dict.__setitem__(self, "rels", None)
+        self._done = set()
+
+    def _dense(self, ragged):
+        if ragged is None:
+            return None
+        if not self._dense_tracks:
+            return ragged
+        pb = self.batch
+        out = ragged.new_full((pb.B, pb.n_slots, ragged.shape[-1]), float("-inf"))
+        return out.index_put((pb["cand_clip"].long(), pb["cand_slot"].long()), ragged)
+
+    def __getitem__(self, key):
+        if key in ("inters", "rels") and key not in self._done:
+            dict.__setitem__(self, key, self._dense(self.ragged_inters if key == "inters" else self.ragged_rels))
+            self._done.add(key)
+        return dict.__getitem__(self, key)
+
+
+class _ModelFn(torch.autograd.Function):
+    """lirec_model_forward / lirec_model_backward as one autograd node over all parameters."""
+
+    @staticmethod
+    def forward(ctx, module, pb, training, seed, *params):
+        batch_c = module._batch_struct(pb, training, seed)
+        nbytes = _ext.lib().lirec_model_workspace_bytes(C.byref(module._cfg_c), C.byref(batch_c))
+        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=pb.device)
+        Ni = pb.n_cand
+        inters = torch.empty(Ni, module.n_classes, dtype=torch.float32, device=pb.device)
+        rels = torch.empty(Ni, module.n_rels, dtype=torch.float32, device=pb.device) if module._ctx else None
+        _ext.check(_ext.lib().lirec_model_forward(
+            C.byref(module._cfg_c), C.byref(module._params_c), C.byref(batch_c), ws.data_ptr(), ws.numel(),
+            inters.data_ptr(), rels.data_ptr() if rels is not None else None, _ext.stream_ptr()))
+        ctx.module, ctx.pb, ctx.batch_c, ctx.ws = module, pb, batch_c, ws
+        if rels is None:
+            none = inters.new_empty(0)
+            ctx.mark_non_differentiable(none)
+            return inters, none
+        return inters, rels
+
+    @staticmethod
+    def backward(ctx, d_inters, d_rels):
+        m = ctx.module
+        d_inters = d_inters.contiguous()
+        d_rels_ptr = None
+        if m._ctx:
+            d_rels = d_rels.contiguous()
+            d_rels_ptr = d_rels.data_ptr()
+        _ext.check(_ext.lib().lirec_model_backward(
+            C.byref(m._cfg_c), C.byref(m._params_c), C.byref(ctx.batch_c), ctx.ws.data_ptr(), ctx.ws.numel(),
+            d_inters.data_ptr(), d_rels_ptr, _ext.stream_ptr()))
+        m._publish_grads()
+        ctx.ws = None
+        return (None,) * (4 + len(m._param_list))
+
+
+class _HotPath(nn.Module):
+    """Shared machinery of the three model classes."""
+    kind = None
+
+    def _build(self, n_classes, n_rels, ints, ctx, gates):
+        if opt.modality != "m" or not opt.tracks:
+            raise NotImplementedError("lirec_b200 implements the multimodal model with tracks "
+                                      "(opt.modality='m', opt.tracks=True)")
+        if not ints:
+            raise NotImplementedError("opt.ints must be 1")
+        self.n_classes, self.n_rels = n_classes, n_rels
+        self._ctx, self._gates = bool(ctx), bool(gates and ctx)
+        J = opt.joint_dim
+        dims = {"txt": opt.text_dim, "vis": opt.visual_dim, "tracks1": opt.track_dim, "tracks2": opt.track_dim}
+        # same construction order as the reference (mlp/model.py:29-50, 104-143, 222-259) so that the
+        # same torch seed gives bit-identical initial weights
+        for br in (["ints"] + (["ctx"] if self._ctx else [])):
+            setattr(self, "txt_%s" % br, nn.Linear(dims["txt"], J))
+            setattr(self, "txt2_%s" % br, nn.Linear(J, J))
+            setattr(self, "vis_%s" % br, nn.Linear(dims["vis"], J))
+            setattr(self, "vis2_%s" % br, nn.Linear(J, J))
+            setattr(self, "tracks1_%s" % br, nn.Linear(dims["tracks1"], J))
+            setattr(self, "tracks2_%s" % br, nn.Linear(dims["tracks2"], J))
+            setattr(self, "tracks12_%s" % br, nn.Linear(J, J // 2))
+            setattr(self, "tracks22_%s" % br, nn.Linear(J, J // 2))
+        out_dim_ints = 3 * J
+        if self._gates:
+            out_dim_ints = J * opt.mid_m_ints
+            self.gates_ints = GatingUnit(in_dim1=3 * J, in_dim2=3 * J, out_dim=out_dim_ints)
+        self.out_ints = nn.Linear(out_dim_ints, n_classes)
+        if self._ctx:
+            self.out_ctx = nn.Linear(3 * J, n_rels)
+        self.dropout = nn.Dropout(p=opt.dropout)   # holder of p, as in the reference (model.py:52)
+        self._gate_dim = out_dim_ints
+        self._flat = self._flat_grad = self._flat_bf16 = None
+        self._param_list = None
+        self._versions = None
+        self._step = 0
+
+    # ---- flat parameter storage ----------------------------------------------------------------
+    def _sync_flat(self):
+        """(Re)build the flat fp32 / grad / bf16 buffers and point every parameter into them."""
+        params = [p for p in self.parameters()]
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("lirec_b200 model parameters are on %s; move the model to a B200 "
+                               "(model.to('cuda')) — there is no CPU path" % dev)
+        ok = self._flat is not None and self._flat.device == dev and len(params) == len(self._param_list)
+        if ok:
+            base = self._flat.data_ptr()
+            for p, off in zip(params, self._offsets):
+                if p.data_ptr() != base + 4 * off:
+                    ok = False
+                    break
+        if ok:
+            return
+        _ext.require_device(dev)
+        offsets, total = [], 0
+        for p in params:
+            offsets.append(total)
+            total += (p.numel() + 63) // 64 * 64           # 256-byte aligned segments (TMA needs 16)
+        flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        for p, off in zip(params, offsets):
+            flat[off:off + p.numel()].copy_(p.data.reshape(-1).float())
+            p.data = flat[off:off + p.numel()].view(p.shape)
+        self._flat, self._offsets, self._param_list = flat, offsets, params
+        self._flat_grad = torch.zeros_like(flat)
+        self._flat_bf16 = torch.zeros(total, dtype=torch.bfloat16, device=dev)
+        self._versions = None
+        self._build_structs()
+
+    def _grad_view(self, i):
+        p, off = self._param_list[i], self._offsets[i]
+        return self._flat_grad[off:off + p.numel()].view(p.shape)
+
+    def _publish_grads(self):
+        """Expose the flat gradient buffer through p.grad (zero-copy when p.grad is None)."""
+        for i, p in enumerate(self._param_list):
+            g = self._grad_view(i)
+            if p.grad is None:
+                p.grad = g
+            elif p.grad.data_ptr() != g.data_ptr():
+                p.grad.add_(g)
+            # else: p.grad already aliases the flat buffer, which backward has just overwritten
+
+    def _refresh_bf16(self):
+        versions = tuple(p._version for p in self._param_list)
+        if versions != self._versions:
+            ops.cast_bf16(self._flat, self._flat_bf16)
+            self._versions = versions
+
+    def mark_bf16_fresh(self):
+        """Called by FlatAdam after it has rewritten the bf16 shadow itself."""
+        self._versions = tuple(p._version for p in self._param_list)
+
+    def _linear_struct(self, lin):
+        idx = {id(p): i for i, p in enumerate(self._param_list)}
+        iw, ib = idx[id(lin.weight)], idx[id(lin.bias)]
+        s = _ext.Linear()
+        s.w_bf16 = self._flat_bf16.data_ptr() + 2 * self._offsets[iw]
+        s.bias = self._flat.data_ptr() + 4 * self._offsets[ib]
+        s.grad_w = self._flat_grad.data_ptr() + 4 * self._offsets[iw]
+        s.grad_b = self._flat_grad.data_ptr() + 4 * self._offsets[ib]
+        s.out_f, s.in_f = lin.out_features, lin.in_features
+        return s
+
+    def _build_structs(self):
+        P = _ext.ModelParams()
+        for br, enc in (("ints", P.enc_ints), ("ctx", P.enc_ctx)):
+            if br == "ctx" and not self._ctx:
+                continue
+            for s in range(4):
+                enc.l1[s] = self._linear_struct(getattr(self, "%s_%s" % (_SLOTS[s], br)))
+                enc.l2[s] = self._linear_struct(getattr(self, "%s_%s" % (_SECOND[s], br)))
+        if self._gates:
+            P.gate = self._linear_struct(self.gates_ints.fc_out)
+        P.out_ints = self._linear_struct(self.out_ints)
+        if self._ctx:
+            P.out_ctx = self._linear_struct(self.out_ctx)
+        cfg = _ext.ModelCfg()
+        cfg.text_dim, cfg.visual_dim, cfg.track_dim = opt.text_dim, opt.visual_dim, opt.track_dim
+        cfg.joint_dim, cfg.gate_dim = opt.joint_dim, self._gate_dim
+        cfg.n_classes, cfg.n_rels = self.n_classes, self.n_rels
+        cfg.ctx, cfg.gates = int(self._ctx), int(self._gates)
+        cfg.guard_zero = int(self.kind == "maxtracks")
+        cfg.dropout_p = float(self.dropout.p)
+        self._params_c, self._cfg_c = P, cfg
+
+    def _batch_struct(self, pb, training, seed):
+        b = _ext.Batch()
+        b.clip_bank, b.clip_ld = pb.clip_bank.data_ptr(), pb.clip_bank.stride(0)
+        b.n_clip, b.n_clip_ints = pb.n_clip, pb.n_clip_ints
+        b.track_bank, b.track_ld = pb.track_bank.data_ptr(), pb.track_bank.stride(0)
+        b.n_track, b.n_track_ints = pb.n_track, pb.n_track_ints
+        b.n_cand, b.n_ctx_rows = pb.n_cand, pb.n_ctx_rows if self._ctx else 0
+        b.cand_rows = pb["cand_rows"].data_ptr()
+        if self._ctx:
+            if not pb.has_ctx:
+                raise RuntimeError("the model has a context branch but the batch carries no context tables")
+            b.ctx_rows, b.ctx_off = pb["ctx_rows"].data_ptr(), pb["ctx_off"].data_ptr()
+            b.ctx_owner = pb["ctx_owner"].data_ptr()
+        else:  # ints-only models ignore context tables; bank prefixes still apply
+            b.n_clip, b.n_track = pb.n_clip_ints, pb.n_track_ints
+        for s in range(3):
+            b.inv_cand_off[s] = pb["inv_cand_off%d" % s].data_ptr()
+            b.inv_cand_idx[s] = pb["inv_cand_idx%d" % s].data_ptr()
+            if self._ctx:
+                b.inv_ctx_off[s] = pb["inv_ctx_off%d" % s].data_ptr()
+                b.inv_ctx_idx[s] = pb["inv_ctx_idx%d" % s].data_ptr()
+        b.seed, b.training = int(seed) & 0xFFFFFFFF, int(bool(training))
+        return b
+
+    # ---- batches -------------------------------------------------------------------------------
+    def _packed(self, x):
+        if isinstance(x, PackedBatch):
+            pb = x
+        elif isinstance(x, dict) and isinstance(x.get("packed"), PackedBatch):
+            pb = x["packed"]
+        elif isinstance(x, dict) and "features" in x:
+            # reference dense batch: compatibility path (host-side packing, no deduplication)
+            if self.kind == "maxtracks":
+                feats = x["features"]
+                if feats.dim() == 3 and self._ctx:      # already flattened by a previous call (model.py:274)
+                    raise RuntimeError("dense 'features' must be [B, T, S+1, D]")
+            pb = pack_dense_batch(x, self.kind, n_slots=None)
+            x["packed"] = pb
+        else:
+            raise TypeError("model input must be a PackedBatch or a reference batch dict")
+        if pb.device is None:
+            dev = self._flat.device
+            pb = pb.to_device(dev)
+            if isinstance(x, dict):
+                x["packed"] = pb
+        return pb
+
+    def next_seed(self):
+        self._step += 1
+        return (int(opt.seed) * 0x9E3779B1 + self._step * 0x85EBCA6B) & 0xFFFFFFFF
+
+    def forward(self, x, seed=None):
+        self._sync_flat()
+        self._refresh_bf16()
+        pb = self._packed(x)
+        training = self.training and self.dropout.p > 0
+        if seed is None:
+            seed = self.next_seed() if training else 0
+        inters, rels = _ModelFn.apply(self, pb, training, seed, *self._param_list)
+        return ModelOutput(pb, inters, rels if self._ctx else None, dense_tracks=(self.kind == "maxtracks"))
+
+
+class Modalities(_HotPath):
+    """Reference: mlp/model.py:19-92 (interaction logits from text + visual + two tracks)."""
+    kind = "modalities"
+
+    def __init__(self, n_classes, n_rels=0):
+        super().__init__()
+        self._build(n_classes, n_rels, ints=1, ctx=0, gates=0)
+
+
+class MidFusionMultiClip(_HotPath):
+    """Reference: mlp/model.py:95-211 (clip + masked-mean context, gate, two heads)."""
+    kind = "midfusion"
+
+    def __init__(self, n_classes, n_rels=0):
+        super().__init__()
+        self._build(n_classes, n_rels, ints=opt.ints, ctx=opt.ctx, gates=opt.gates)
+
+
+class MidFusionMultiClipMaxTracks(_HotPath):
+    """Reference: mlp/model.py:214-339 (every candidate track pair is its own row)."""
+    kind = "maxtracks"
+
+    def __init__(self, n_classes, n_rels=0):
+        super().__init__()
+        self._build(n_classes, n_rels, ints=opt.ints, ctx=opt.ctx, gates=opt.gates)
+
+    def forward(self, x, seed=None):
+        assert opt.tr_maximize
+        return super().forward(x, seed=seed)
+
+
+class GatingUnit(nn.Module):
+    """Parameter holder of the gate (reference: mlp/model.py:342-354); the computation
+    dropout(relu(fc_out(cat(ctx, ints)))) runs inside lirec_model_forward."""
+
+    def __init__(self, in_dim1, in_dim2, out_dim):
+        super().__init__()
+        self.in_dim1, self.in_dim2, self.out_dim = in_dim1, in_dim2, out_dim
+        self.fc_out = nn.Linear(in_dim1 + in_dim2, out_dim)
+        self.dropout = nn.Dropout(p=opt.dropout)
+
+
+# =================================================================================================
+# losses
+# =================================================================================================
+class _LossFn(torch.autograd.Function):
+    """A fused loss kernel already produced d(loss)/d(logits); backward just scales them."""
+
+    @staticmethod
+    def forward(ctx, loss_terms, grads, *logits):
+        ctx.grads = grads
+        return loss_terms.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None, None) + tuple(None if d is None else d * g for d in ctx.grads)
+
+
+def _batch_of(output, args):
+    if isinstance(output, ModelOutput):
+        return output.batch
+    if isinstance(args, dict) and isinstance(args.get("packed"), PackedBatch):
+        return args["packed"]
+    raise TypeError("lirec_b200 losses expect the ModelOutput returned by a lirec_b200 model")
+
+
+class MaxMarginCrossEntropyLoss(nn.Module):
+    """Reference: mlp/model.py:422-441."""
+
+    def __init__(self):
+        super().__init__()
+        self.m = opt.margin
+
+    def forward(self, x, args):
+        pb = _batch_of(x, args)
+        logits = x.ragged_inters
+        terms, d = ops.loss_rowmargin(logits, pb["labels"], pb.multilab, self.m, 1.0 / logits.shape[0])
+        return _LossFn.apply(terms, (d,), logits)
+
+
+class MultiTaskMaxMargin(nn.Module):
+    """Reference: mlp/model.py:381-419."""
+
+    def __init__(self, n_rels=0):
+        super().__init__()
+        self.m = opt.margin
+        self.n_rels = n_rels
+
+    def forward(self, x, args):
+        pb = _batch_of(x, args)
+        terms, grads, logits = [], [], []
+        if opt.ints == 1:
+            li = x.ragged_inters
+            t, d = ops.loss_rowmargin(li, pb["labels"], pb.multilab, self.m, opt.lymbda / li.shape[0])
+            terms.append(t), grads.append(d), logits.append(li)
+        if opt.ctx == 1:
+            lr = x.ragged_rels
+            host = pb.host if pb.device is not None else pb
+            lab = host["rels_label"]
+            n_sel = int((lab != self.n_rels).sum())
+            if n_sel:
+                sel = pb["rels_label"].clone()
+                sel[sel == self.n_rels] = -1                     # rows labelled None are skipped (model.py:406)
+                t, d = ops.loss_rowmargin(lr, sel, None, self.m, 1.0 / n_sel)
+                terms.append(t), grads.append(d), logits.append(lr)
+        return _LossFn.apply(torch.cat(terms), tuple(grads), *logits)
+
+
+class _TrackLoss(nn.Module):
+    def _run(self, x, args, n_rels, lymbda):
+        if opt.tr_cat_distr:
+            raise NotImplementedError("tr_cat_distr (multinomial track assignment, model.py:468-471) "
+                                      "is not implemented on the B200 path")
+        assert opt.tr_maximize
+        pb = _batch_of(x, args)
+        li, lr = x.ragged_inters, x.ragged_rels if n_rels else None
+        terms, assign, d_i, d_r = ops.loss_track(
+            li, lr, pb["cand_off"], pb["labels"], pb["rels_label"] if n_rels else None, pb["gt_tracks"],
+            pb.multilab, self.m, lymbda, n_rels, tr_correct=opt.tr_correct,
+            max_neg=bool(opt.tr_max_neg and opt.tr_sum_max_flag), max_slots=pb.n_slots)
+        self.last_assignment = assign
+        if n_rels:
+            return _LossFn.apply(terms, (d_i, d_r), li, lr)
+        return _LossFn.apply(terms, (d_i,), li)
+
+
+class MarginLoss(_TrackLoss):
+    """Reference: mlp/model.py:444-494 (weakly supervised track assignment, interactions only)."""
+
+    def __init__(self):
+        super().__init__()
+        self.m = opt.tr_margin
+
+    def forward(self, input, args):
+        return self._run(input, args, 0, 1.0)
+
+
+class MarginTrackRelsLoss(_TrackLoss):
+    """Reference: mlp/model.py:497-575 (joint interaction + relationship assignment)."""
+
+    def __init__(self, n_rels=0):
+        super().__init__()
+        self.m = opt.tr_margin
+        self.n_rels = n_rels
+
+    def forward(self, x, args):
+        return self._run(x, args, self.n_rels, opt.lymbda)
+
+
+class MultiTaskCrossEntropyLoss(nn.Module):
+    """Reference: mlp/model.py:357-378.  Never selected by create_model (model.py:586-597); kept
+    for surface completeness on top of torch's cross_entropy over the ragged logits."""
+
+    def __init__(self, n_classes, weights=None, n_rels=0):
+        super().__init__()
+        self.n_classes, self.n_rels = n_classes, n_rels
+        self.weights = None if weights is None else torch.tensor(weights).float()
+
+    def forward(self, x, args):
+        import torch.nn.functional as F
+        pb = _batch_of(x, args)
+        w = None if self.weights is None else self.weights.to(x.ragged_inters.device)
+        loss = F.cross_entropy(x.ragged_inters, pb["labels"].long(), weight=w)
+        lab = pb["rels_label"].long()
+        sel = (lab != self.n_rels).nonzero().reshape(-1)
+        if sel.numel():
+            loss = loss + F.cross_entropy(x.ragged_rels[sel], lab[sel])
+        return loss
+
+
+# =================================================================================================
+# optimizer + factory
+# =================================================================================================
+class FlatAdam(torch.optim.Optimizer):
+    """torch.optim.Adam semantics (coupled L2, reference mlp/model.py:599-601) as ONE fused kernel
+    over the model's flat buffers; also refreshes the bf16 weight shadow.  state_dict() has the
+    layout of torch.optim.Adam (per-parameter 'step', 'exp_avg', 'exp_avg_sq')."""
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.model = model
+        model._sync_flat()
+        super().__init__(model._param_list, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._m = torch.zeros_like(model._flat)
+        self._v = torch.zeros_like(model._flat)
+        self._t = 0
+        for i, p in enumerate(model._param_list):
+            off, n = model._offsets[i], p.numel()
+            self.state[p] = {"step": torch.tensor(0.0), "exp_avg": self._m[off:off + n].view(p.shape),
+                             "exp_avg_sq": self._v[off:off + n].view(p.shape)}
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale=1.0):
+        m = self.model
+        g = self.param_groups[0]
+        self._t += 1
+        ops.adam_flat(m._flat, m._flat_grad, self._m, self._v, m._flat_bf16, g["lr"], g["betas"][0],
+                      g["betas"][1], g["eps"], g["weight_decay"], self._t, grad_scale)
+        for p in m._param_list:
+            self.state[p]["step"] += 1
+        m.mark_bf16_fresh()
+
+    def zero_grad(self, set_to_none=True):
+        # backward overwrites the flat gradient buffer; p.grad keeps aliasing it
+        if set_to_none:
+            for p in self.model._param_list:
+                p.grad = None
+
+
+def create_model(n_classes, n_rels=0):
+    """Reference: mlp/model.py:578-609 — same selection logic and return triple."""
+    if opt.device != "cuda":
+        raise RuntimeError("lirec_b200 runs on a B200 only (opt.device='%s'); no CPU fallback" % opt.device)
+    if opt.tr_maximize:
+        model = MidFusionMultiClipMaxTracks(n_classes=n_classes, n_rels=n_rels)
+    else:
+        model = MidFusionMultiClip(n_classes=n_classes, n_rels=n_rels)
+    if opt.mod_check:
+        model = Modalities(n_classes=n_classes)
+    model = model.to(opt.device)
+
+    if opt.tr_maximize:
+        loss = MarginTrackRelsLoss(n_rels=n_rels) if opt.rels_multitask else MarginLoss()
+    else:
+        loss = MultiTaskMaxMargin(n_rels=n_rels) if opt.rels_multitask else MaxMarginCrossEntropyLoss()
+
+    if getattr(opt, "fused_adam", 0):
+        optimizer = FlatAdam(model, lr=opt.lr, weight_decay=opt.weight_decay)
+    else:
+        model._sync_flat()
+        optimizer = torch.optim.Adam(model.parameters(), lr=opt.lr, weight_decay=opt.weight_decay)
+
+    print(str(model))
+    for name, param in model.named_parameters():
+        print("%s\n%s" % (str(name), str(param.norm())))
+    print(str(loss))
+    print(str(optimizer))
+    return model, loss, optimizer

@@ -39,3 +39,43 @@ def keep_mask(seed, stream_id, rows, cols, p):
     h = fmix32(rk ^ ck[None, :])
     u = (h >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
     return u >= np.float32(p)
+
+
+# dropout sites of lirec_model_forward (csrc/model.cu: DS_*)
+DS_L1_INTS, DS_L1_CTX, DS_CAT_INTS, DS_CAT_CTX, DS_GATE = 1, 2, 3, 4, 5
+
+
+def dense_masks(pb, seed, p, J=512, gate_dim=3072, kind="maxtracks"):
+    """Masks of one step, laid out for the DENSE oracle (oracle/model.py `masks=`) from the packed
+    tables of host PackedBatch `pb`: candidate r sits at dense row (clip, slot), context row x at
+    (clip, slot, position).  Empty slots get all-ones masks (they are masked out downstream)."""
+    import torch
+    t = pb.tables
+    B, T, S = pb.B, pb.n_slots, pb.n_ctx_slots
+    Ni = pb.n_cand
+    dense_row = t["cand_clip"].astype(np.int64) * T + t["cand_slot"].astype(np.int64)
+    slots = ("txt", "vis", "tracks1", "tracks2")
+    masks = {}
+    for s, name in enumerate(slots):
+        m = np.ones((B * T, J), dtype=bool)
+        m[dense_row] = keep_mask(seed, DS_L1_INTS, np.arange(Ni), s * J + np.arange(J), p)
+        masks[("l1", "ints", name)] = torch.from_numpy(m)
+    m = np.ones((B * T, 3 * J), dtype=bool)
+    m[dense_row] = keep_mask(seed, DS_CAT_INTS, np.arange(Ni), np.arange(3 * J), p)
+    masks[("cat", "ints")] = torch.from_numpy(m)
+    if pb.has_ctx:
+        Nx = pb.n_ctx_rows
+        owner = t["ctx_owner"].astype(np.int64)
+        pos = np.arange(Nx) - t["ctx_off"][:-1].astype(np.int64)[owner]
+        for s, name in enumerate(slots):
+            m = np.ones((B * T, S, J), dtype=bool)
+            if Nx:
+                m[dense_row[owner], pos] = keep_mask(seed, DS_L1_CTX, np.arange(Nx), s * J + np.arange(J), p)
+            masks[("l1", "ctx", name)] = torch.from_numpy(m)
+        m = np.ones((B * T, 3 * J), dtype=bool)
+        m[dense_row] = keep_mask(seed, DS_CAT_CTX, np.arange(Ni), np.arange(3 * J), p)
+        masks[("cat", "ctx")] = torch.from_numpy(m)
+        m = np.ones((B * T, gate_dim), dtype=bool)
+        m[dense_row] = keep_mask(seed, DS_GATE, np.arange(Ni), np.arange(gate_dim), p)
+        masks[("gate",)] = torch.from_numpy(m)
+    return masks

@@ -56,9 +56,19 @@ def encode(sd, branch, x, cfg, masks):
     return outs
 
 
+def _tape(cfg, name, t):
+    """Optional white-box tape (cfg.tape = {}) used by the stage-level parity tests."""
+    tape = getattr(cfg, "tape", None)
+    if tape is not None:
+        if t.requires_grad:
+            t.retain_grad()
+        tape[name] = t
+    return t
+
+
 def gating_unit(sd, feat_ints, feat_ctx, cfg, masks):
     z = torch.cat((feat_ctx, feat_ints), dim=-1)               # (rels, inters) order: model.py:352
-    z = torch.relu(_lin(sd, "gates_ints.fc_out", z))
+    z = torch.relu(_tape(cfg, "pre_gate", _lin(sd, "gates_ints.fc_out", z)))
     return _drop(z, masks, ("gate",), cfg.dropout)             # dropout(relu(.)): model.py:353
 
 
@@ -77,7 +87,7 @@ def _ctx_feature(sd, ctx_rows, rels_mask, cfg, masks, guard_zero):
     if guard_zero:
         div = torch.where(div == 0, torch.ones_like(div), div)  # model.py:303
     pooled = [(o * m).sum(1) / div for o in encode(sd, "ctx", ctx_rows, cfg, masks)]
-    f = torch.cat(pooled, dim=-1)
+    f = _tape(cfg, "z2_ctx", torch.cat(pooled, dim=-1))
     return _drop(torch.tanh(f), masks, ("cat", "ctx"), cfg.dropout)
 
 
@@ -105,7 +115,7 @@ def maxtracks_forward(sd, features, rels_mask, cfg, masks=None):
     B, T = features.shape[0], features.shape[1]
     x = features.reshape(B * T, -1, features.shape[-1])       # model.py:272-274
     out_c = None
-    f_i = torch.cat(encode(sd, "ints", x[:, 0, :], cfg, masks), dim=-1)
+    f_i = _tape(cfg, "z2_ints", torch.cat(encode(sd, "ints", x[:, 0, :], cfg, masks), dim=-1))
     f_i = _drop(torch.tanh(f_i), masks, ("cat", "ints"), cfg.dropout)
     if cfg.ctx:
         f_c = _ctx_feature(sd, x[:, 1:, :], rels_mask.reshape(B * T, -1), cfg, masks, guard_zero=True)

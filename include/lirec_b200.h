@@ -57,6 +57,9 @@ typedef struct lirec_dropout {
   int32_t col_off;     /* added to the column before hashing                 */
 } lirec_dropout;
 
+/* keep(row, col) evaluated on the HOST with the kernels' code (test aid, no GPU needed). */
+int lirec_dropout_keep_host(uint32_t seed, uint32_t stream_id, uint32_t row, uint32_t col, float p);
+
 /* ---- grouped tcgen05 GEMM ---------------------------------------------
  * D[m,n] = epilogue( alpha * sum_pass sum_k A_pass[m,k] * B_pass[n,k] )
  * bf16 operands, fp32 accumulation in TMEM.  Replaces nn.Linear forward
@@ -124,6 +127,12 @@ typedef struct lirec_gemm_problem {
 /* One persistent launch over all tiles of all problems (host array). */
 int lirec_gemm_grouped(const lirec_gemm_problem* problems_host, int num_problems,
                        void* stream);
+/* Per-launch timing of the GEMM kernel (CUDA events on the launching stream), for bench.py's
+ * roofline line: begin() starts recording, end() synchronises on the recorded events and returns
+ * the number of launches, filling duration (ms), executed MMA flops, tile and problem counts. */
+int lirec_profile_begin(void);
+int lirec_profile_end(float* ms_host, double* flops_host, int32_t* tiles_host, int32_t* problems_host,
+                      int max_records);
 /* Number of kernels the last lirec_* call on this thread launched. */
 int lirec_last_launch_count(void);
 

@@ -113,6 +113,7 @@ def lib():
     L.lirec_abi_version.restype = C.c_int
     L.lirec_last_launch_count.restype = C.c_int
     L.lirec_device_check.argtypes = [C.c_int]
+    L.lirec_dropout_keep_host.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float]
     L.lirec_gemm_grouped.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.lirec_seg_reduce_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
@@ -135,6 +136,7 @@ def lib():
                                                                                   C.c_void_p]
     L.lirec_model_workspace_bytes.argtypes = [C.c_void_p, C.c_void_p]
     L.lirec_model_workspace_bytes.restype = C.c_size_t
+    L.lirec_profile_end.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.lirec_model_workspace_layout.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.lirec_model_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                       C.c_void_p, C.c_void_p, C.c_void_p]
@@ -147,8 +149,8 @@ def lib():
 
 
 EXPORTED_SYMBOLS = [
-    "lirec_abi_version", "lirec_last_error", "lirec_device_check", "lirec_last_launch_count",
-    "lirec_gemm_grouped", "lirec_seg_reduce_f32", "lirec_rows_expand_fwd", "lirec_rows_expand_bwd",
+    "lirec_abi_version", "lirec_last_error", "lirec_device_check", "lirec_dropout_keep_host", "lirec_last_launch_count",
+    "lirec_gemm_grouped", "lirec_profile_begin", "lirec_profile_end", "lirec_seg_reduce_f32", "lirec_rows_expand_fwd", "lirec_rows_expand_bwd",
     "lirec_split_f32", "lirec_cast_bf16", "lirec_loss_track_fwd_bwd", "lirec_loss_rowmargin_fwd_bwd",
     "lirec_model_workspace_bytes", "lirec_model_workspace_layout", "lirec_model_forward", "lirec_model_backward", "lirec_adam_flat",
 ]
@@ -200,3 +202,19 @@ def operand(t, rows=None, cols=None, col_off=0):
 def gemm_grouped(problems):
     arr = (GemmProblem * len(problems))(*problems)
     check(lib().lirec_gemm_grouped(C.cast(arr, C.c_void_p), len(problems), stream_ptr()))
+
+
+def profile_begin():
+    check(lib().lirec_profile_begin())
+
+
+def profile_end(max_records=65536):
+    """Returns a list of (ms, executed_flops, tiles, problems) per GEMM launch since profile_begin()."""
+    ms = (C.c_float * max_records)()
+    fl = (C.c_double * max_records)()
+    ti = (C.c_int32 * max_records)()
+    pr = (C.c_int32 * max_records)()
+    n = lib().lirec_profile_end(ms, fl, ti, pr, max_records)
+    if n < 0:
+        check(n)
+    return [(ms[i], fl[i], ti[i], pr[i]) for i in range(n)]

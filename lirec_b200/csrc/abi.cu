@@ -51,6 +51,12 @@ int check_arch() {
 extern "C" int lirec_abi_version(void) { return LIREC_ABI_VERSION; }
 extern "C" const char* lirec_last_error(void) { return lirec::err_buf(); }
 extern "C" int lirec_last_launch_count(void) { return lirec::g_launches; }
+// Host evaluation of the dropout hash (same code the kernels run), so the numpy mirror in
+// oracle/dropout.py can be checked bit-for-bit without a GPU.
+extern "C" int lirec_dropout_keep_host(uint32_t seed, uint32_t stream_id, uint32_t row, uint32_t col, float p) {
+  return lirec::drop_keep(lirec::drop_row_key(seed, stream_id, row), col, p) ? 1 : 0;
+}
+
 extern "C" int lirec_device_check(int device) {
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)

@@ -511,6 +511,18 @@ static int encode_map(CUtensorMap* out, const MapKey& k) {
   return LIREC_OK;
 }
 
+// ---- optional per-launch timing (CUDA events on the launching stream), used by bench.py ----
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  double flops;   // executed MMA flops: sum over problems of 2*M*N*K (all passes)
+  int tiles, problems;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;      // records of the current capture
+static std::vector<ProfRec> g_prof_pool;  // events are reused across captures
+static double g_pending_flops = 0.0;
+static int g_pending_problems = 0;
+
 template <int BN, int STAGES>
 static int launch(const GemmParams& P, cudaStream_t stream) {
   constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/;
@@ -525,8 +537,22 @@ static int launch(const GemmParams& P, cudaStream_t stream) {
     configured = true;
   }
   const int grid = std::min(P.total_tiles, num_sms);
+  ProfRec rec{};
+  if (g_prof_on) {
+    if (!g_prof_pool.empty()) { rec = g_prof_pool.back(); g_prof_pool.pop_back(); }
+    else {
+      LIREC_CUDA_OK(cudaEventCreate(&rec.e0));
+      LIREC_CUDA_OK(cudaEventCreate(&rec.e1));
+    }
+    rec.flops = g_pending_flops; rec.tiles = P.total_tiles; rec.problems = g_pending_problems;
+    LIREC_CUDA_OK(cudaEventRecord(rec.e0, stream));
+  }
   lirec_gemm_tcgen05_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, stream>>>(P);
   LIREC_CUDA_OK(cudaGetLastError());
+  if (g_prof_on) {
+    LIREC_CUDA_OK(cudaEventRecord(rec.e1, stream));
+    g_prof.push_back(rec);
+  }
   note_launch();
   return LIREC_OK;
 }
@@ -624,6 +650,15 @@ int run_grouped(const lirec_gemm_problem* probs, int nprobs, cudaStream_t stream
   P.num_problems = np;
   P.total_tiles = tiles;
   if (tiles == 0) return LIREC_OK;
+  if (g_prof_on) {
+    g_pending_flops = 0.0;
+    g_pending_problems = np;
+    for (int idx : order) {
+      double k = 0;
+      for (int ps = 0; ps < probs[idx].num_passes; ++ps) k += probs[idx].pass[ps].k_len;
+      g_pending_flops += 2.0 * probs[idx].M * probs[idx].N * k;
+    }
+  }
   for (size_t i = 0; i < keys.size(); ++i) {
     int rc = encode_map(&P.maps[i], keys[i]);
     if (rc != LIREC_OK) return rc;
@@ -633,6 +668,32 @@ int run_grouped(const lirec_gemm_problem* probs, int nprobs, cudaStream_t stream
 
 }  // namespace gemm
 }  // namespace lirec
+
+extern "C" int lirec_profile_begin(void) {
+  using namespace lirec::gemm;
+  for (auto& r : g_prof) g_prof_pool.push_back(r);
+  g_prof.clear();
+  g_prof_on = true;
+  return LIREC_OK;
+}
+
+extern "C" int lirec_profile_end(float* ms, double* flops, int32_t* tiles, int32_t* problems, int max_records) {
+  using namespace lirec::gemm;
+  g_prof_on = false;
+  int n = 0;
+  for (auto& r : g_prof) {
+    if (n >= max_records) break;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) return lirec::fail(LIREC_ERR_CUDA, "profile: event sync failed");
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) return lirec::fail(LIREC_ERR_CUDA, "profile: elapsed failed");
+    if (ms) ms[n] = t;
+    if (flops) flops[n] = r.flops;
+    if (tiles) tiles[n] = r.tiles;
+    if (problems) problems[n] = r.problems;
+    ++n;
+  }
+  return n;
+}
 
 extern "C" int lirec_gemm_grouped(const lirec_gemm_problem* problems_host, int num_problems,
                                   void* stream) {

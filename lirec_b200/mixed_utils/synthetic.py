@@ -51,16 +51,20 @@ def make_batch(B, seed=0, preset="int_rel_ch", max_n_tripl=20, rels_n_clips=18, 
     T, S = int(max_n_tripl), int(rels_n_clips)
     NONE = n_rels
 
-    # bank bookkeeping: track row 0 is the all-zero "no track" row
-    n_ints_tracks = 1
+    # bank bookkeeping: every clip owns one all-zero "no track" row (a single shared zero row would
+    # be referenced by thousands of candidate rows and serialise the backward scatter-reduce)
+    n_ints_tracks = 0
     person_track = []            # per clip: list of bank rows of its characters
+    zero_row = []                # per clip: its all-zero track row
     clips = []
     for b in range(B):
         n = int(rng.choice(n_opts, p=n_p))
+        zero_row.append(n_ints_tracks)
+        n_ints_tracks += 1
         rows = []
         for _ in range(n):
             if rng.random() < p_zero_track:
-                rows.append(0)
+                rows.append(zero_row[b])
             else:
                 rows.append(n_ints_tracks)
                 n_ints_tracks += 1
@@ -114,7 +118,7 @@ def make_batch(B, seed=0, preset="int_rel_ch", max_n_tripl=20, rels_n_clips=18, 
             slots = slots[:1]
             gt_idx = [0, 0]
         for (i, j) in slots:
-            cand_rows.append((b, 0 if i is None else tr[i], 0 if j is None else tr[j]))
+            cand_rows.append((b, zero_row[b] if i is None else tr[i], zero_row[b] if j is None else tr[j]))
             lab, spec = NONE, None
             if cfg["ctx"] and i is not None and j is not None:
                 key = (b, min(i, j), max(i, j))
@@ -159,7 +163,7 @@ def make_batch(B, seed=0, preset="int_rel_ch", max_n_tripl=20, rels_n_clips=18, 
     clip_bank[:, :TEXT_DIM] = _features(rng, n_clip, TEXT_DIM, nonneg=False)
     clip_bank[:, TEXT_DIM:] = _features(rng, n_clip, CLIP_DIM - TEXT_DIM, nonneg=True)
     track_bank = _features(rng, n_track, TRACK_DIM, nonneg=True)
-    track_bank[0] = 0.0
+    track_bank[np.asarray(zero_row)] = 0.0
     labels = rng.integers(n_classes, size=B)
     multilab = (rng.random((B, n_classes)) < 0.95).astype(np.uint8)
     pb = PackedBatch.from_tables(clip_bank, track_bank, n_clip_ints, n_track_ints, cand_off, cand_rows, ctx_off,

@@ -10,7 +10,8 @@ banks and describes every encoder row as an index triple:
 
     clip_bank  [n_clip, 2816]   text|visual rows; rows [0, n_clip_ints) belong to the batch's clips
     track_bank [n_track, 2048]  person-track rows; rows [0, n_track_ints) are used by candidates;
-                                one all-zero row stands for "no track" (zeros in the reference)
+                                all-zero rows stand for "no track" (zeros in the reference) — one
+                                per clip, so no bank row is referenced by more than a few dozen rows
     cand_off   [B+1]            prefix sums of valid candidate slots per clip (reference slot order)
     cand_rows  [Ni, 3]          (clip, track1, track2) bank rows of every candidate
     ctx_off    [Ni+1]           prefix sums of valid context rows per candidate (= rels_mask sums)

@@ -1,0 +1,86 @@
+"""Reference-style CPU training / inference step, timed by bench.py.
+
+TEST / MEASUREMENT INFRASTRUCTURE — see oracle/__init__.py.  This is the oracle port of the
+reference's own CPU path (the reference is pure Python/PyTorch and cannot travel to the GPU box):
+the DENSE float64 batch the reference dataloader emits, `.float()` casts, fp32 torch CPU math
+with dropout from torch's RNG, the reference loss, autograd backward and torch.optim.Adam with
+the reference hyper-parameters (mlp/train.py:52-63, mlp/model.py:599-601).
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import losses as ol
+from . import model as om
+
+
+class CpuStep:
+    def __init__(self, preset, n_classes=101, n_rels=15, seed=0, lr=3e-5, weight_decay=1e-5, dropout=0.3,
+                 margin=0.101, lymbda=1.0):
+        flags = {"modalities": ("modalities", 0, 0), "int_rels": ("midfusion", 1, 1),
+                 "int_ch": ("maxtracks", 0, 0), "int_rel_ch": ("maxtracks", 1, 1)}[preset]
+        self.kind = flags[0]
+        self.cfg = om.default_cfg(ctx=flags[1], gates=flags[2], dropout=dropout)
+        self.sd = om.init_state_dict(self.cfg, n_classes, n_rels, self.kind, seed=seed)
+        for v in self.sd.values():
+            v.requires_grad_(True)
+        self.opt = torch.optim.Adam(list(self.sd.values()), lr=lr, weight_decay=weight_decay)
+        self.n_rels, self.margin, self.lymbda = n_rels, margin, lymbda
+
+    def _forward(self, dense, masks):
+        f = dense["features"].float()                      # the reference casts slices with .float()
+        B = f.shape[0]
+        if self.kind == "modalities":
+            return om.modalities_forward(self.sd, f.reshape(B, 1, -1), self.cfg, masks)
+        if self.kind == "midfusion":
+            return om.midfusion_forward(self.sd, f.reshape(B, -1, f.shape[-1]), dense["rels_mask"].reshape(B, -1, 1),
+                                        self.cfg, masks)
+        return om.maxtracks_forward(self.sd, f, dense.get("rels_mask"), self.cfg, masks)
+
+    def _loss(self, o, dense):
+        B = dense["features"].shape[0]
+        if self.kind == "modalities":
+            return ol.max_margin_ce(o["inters"], dense["labels"], dense["multilab_weights"], self.margin)
+        if self.kind == "midfusion":
+            return ol.multitask_max_margin(o["inters"], o["rels"], dense["labels"].reshape(B, 1, 1),
+                                           dense["rels_label"].reshape(B), dense["multilab_weights"], self.margin,
+                                           self.lymbda, self.n_rels)
+        if self.cfg.ctx:
+            return ol.margin_track_rels(o["inters"], o["rels"], dense["labels"], dense["rels_label"],
+                                        dense["mem_mask"], dense["multilab_weights"], dense["gt_tracks"], self.margin,
+                                        self.lymbda, self.n_rels)[0]
+        return ol.margin_loss(o["inters"], dense["labels"], dense["mem_mask"], dense["multilab_weights"],
+                              dense["gt_tracks"], self.margin)[0]
+
+    def train_step(self, dense):
+        o = self._forward(dense, "rng")
+        loss = self._loss(o, dense)
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+        return float(loss.item())
+
+    @torch.no_grad()
+    def infer_step(self, dense):
+        return self._forward(dense, None)
+
+
+def time_train(preset, dense, steps=3, warmup=1, threads=None):
+    """clips/s of the CPU path on dense batch `dense` (best of `steps` after `warmup`)."""
+    if threads:
+        torch.set_num_threads(threads)
+    step = CpuStep(preset)
+    B = dense["features"].shape[0]
+    for _ in range(warmup):
+        step.train_step(dense)
+    best = float("inf")
+    total = 0.0
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step.train_step(dense)
+        dt = time.perf_counter() - t0
+        best = min(best, dt)
+        total += dt
+    return {"clips_per_s_best": B / best, "clips_per_s_mean": B * steps / total, "s_per_step_best": best,
+            "threads": torch.get_num_threads(), "clips": B}

@@ -12,7 +12,8 @@ batches exactly as the reference dataloader emits them, so it is a restatement o
 reference's schedule — not of the packed/deduplicated schedule the CUDA path uses.
 
 Dropout: the reference draws masks from torch's global RNG.  Here `masks` (a dict of 0/1
-tensors, see keys below) makes train mode deterministic; masks=None means eval mode.
+tensors, see keys below) makes train mode deterministic; masks=None means eval mode and
+masks="rng" draws them from torch's RNG like the reference (used by the CPU baseline timing).
   ('l1', branch, slot)  branch in {'ints','ctx'}, slot in {'txt','vis','tracks1','tracks2'}
   ('cat', branch)       after tanh of the concatenated feature
   ('gate',)             after relu of the gating unit
@@ -40,20 +41,9 @@ def _lin(sd, name, x):
 def _drop(x, masks, key, p):
     if masks is None:
         return x
+    if masks == "rng":      # train mode with torch's global RNG, as the reference runs it
+        return torch.nn.functional.dropout(x, p=p, training=True)
     return x * masks[key].to(x.dtype) / (1.0 - p)
-
-
-def encode(sd, branch, x, cfg, masks):
-    """x[..., text|visual|track1|track2] -> list of the four second-layer outputs."""
-    T, V, P = cfg.text_dim, cfg.visual_dim, cfg.track_dim
-    parts = {"txt": x[..., :T], "vis": x[..., T:T + V],
-             "tracks1": x[..., T + V:T + V + P], "tracks2": x[..., T + V + P:T + V + 2 * P]}
-    outs = []
-    for slot in SLOTS:
-        h = _lin(sd, "%s_%s" % (slot, branch), parts[slot])
-        h = torch.relu(_drop(h, masks, ("l1", branch, slot), cfg.dropout))  # relu(dropout(.)): model.py:62
-        outs.append(_lin(sd, "%s_%s" % (SECOND[slot], branch), h))
-    return outs
 
 
 def _tape(cfg, name, t):
@@ -64,6 +54,19 @@ def _tape(cfg, name, t):
             t.retain_grad()
         tape[name] = t
     return t
+
+
+def encode(sd, branch, x, cfg, masks):
+    """x[..., text|visual|track1|track2] -> list of the four second-layer outputs."""
+    T, V, P = cfg.text_dim, cfg.visual_dim, cfg.track_dim
+    parts = {"txt": x[..., :T], "vis": x[..., T:T + V],
+             "tracks1": x[..., T + V:T + V + P], "tracks2": x[..., T + V + P:T + V + 2 * P]}
+    outs = []
+    for slot in SLOTS:
+        h = _tape(cfg, "z1_%s_%s" % (slot, branch), _lin(sd, "%s_%s" % (slot, branch), parts[slot]))
+        h = torch.relu(_drop(h, masks, ("l1", branch, slot), cfg.dropout))  # relu(dropout(.)): model.py:62
+        outs.append(_lin(sd, "%s_%s" % (SECOND[slot], branch), h))
+    return outs
 
 
 def gating_unit(sd, feat_ints, feat_ctx, cfg, masks):

@@ -1,0 +1,77 @@
+"""The C-ABI shared library builds for sm_100a, loads, exports every symbol include/lirec_b200.h
+declares, and refuses to compute without a B200 (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "lirec_b200.h")) as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lirec_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    declared = _declared_symbols()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), "include/lirec_b200.h declares %s but the library does not export it" % name
+
+
+def test_binding_lists_every_symbol(built_lib):
+    from lirec_b200 import _ext
+    assert sorted(_ext.EXPORTED_SYMBOLS) == _declared_symbols()
+    assert _ext.lib().lirec_abi_version() == 1
+
+
+def test_sass_is_blackwell_native(built_lib):
+    """tcgen05.mma / TMA / TMEM loads show up as UTCHMMA / UTMALDG / LDTM in the SASS."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", built_lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync path found"
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_gpu(built_lib):
+    from lirec_b200 import _ext, ops
+    with pytest.raises(RuntimeError, match="no CPU"):
+        _ext.require_device()
+    x = torch.zeros(4, 8)
+    with pytest.raises(RuntimeError):
+        ops.cast_bf16(x, torch.zeros(4, 8, dtype=torch.bfloat16))
+    # the raw entry points refuse too
+    rc = _ext.lib().lirec_cast_bf16(None, None, 0, None)
+    assert rc != 0 and b"CPU fallback" in _ext.lib().lirec_last_error() or rc != 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_model_refuses_cpu(built_lib, opt_preset):
+    opt_preset("int_rel_ch", device="cpu")
+    import lirec_b200.mlp.model as M
+    with pytest.raises(RuntimeError, match="no CPU"):
+        M.create_model(101, n_rels=15)
+
+
+def test_product_never_imports_oracle():
+    """oracle/ is test infrastructure: nothing under lirec_b200/ may import it."""
+    pkg = os.path.join(ROOT, "lirec_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(".py"):
+                with open(os.path.join(dirpath, fn)) as f:
+                    src = f.read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, fn)

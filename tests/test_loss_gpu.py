@@ -1,0 +1,153 @@
+"""Fused loss kernels vs the dense oracle losses: loss value, gradient w.r.t. logits, and the
+arg-max track assignment (bit-exact, lowest index on ties)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+C, R, T = 101, 15, 20
+
+
+def _ragged_case(B, seed, with_rels=True, dup_ties=False):
+    rng = np.random.default_rng(seed)
+    counts = rng.choice([2, 6, 12, 20, 1, 7], size=B)
+    off = np.zeros(B + 1, dtype=np.int32)
+    np.cumsum(counts, out=off[1:])
+    Ni = int(off[-1])
+    ints = (rng.standard_normal((Ni, C)) * 2).astype(np.float32)
+    rels = (rng.standard_normal((Ni, R)) * 2).astype(np.float32)
+    if dup_ties:                      # duplicated candidates (all-zero tracks give identical rows in real data)
+        for b in range(B):
+            if counts[b] >= 3:
+                ints[off[b] + 2] = ints[off[b] + 1]
+                rels[off[b] + 2] = rels[off[b] + 1]
+                ints[off[b] + 0] = ints[off[b] + 1] - 5.0     # make the tied pair the winners
+    labels = rng.integers(C, size=B).astype(np.int32)
+    rels_label = rng.integers(R + 1, size=Ni).astype(np.int32)   # R = None
+    if dup_ties:
+        for b in range(B):
+            if counts[b] >= 3:
+                rels_label[off[b] + 2] = rels_label[off[b] + 1]
+    gt = np.zeros((B, 2), dtype=np.int32)
+    gt[:, 1] = [rng.integers(c) if rng.random() < 0.4 else 0 for c in counts]
+    multilab = (rng.random((B, C)) < 0.9).astype(np.uint8)
+    return dict(off=off, ints=ints, rels=rels if with_rels else None, labels=labels, rels_label=rels_label, gt=gt,
+                multilab=multilab, counts=counts)
+
+
+def _dense(case):
+    B = len(case["counts"])
+    off = case["off"]
+    ints = torch.zeros(B, T, C, dtype=torch.float64)
+    rels = torch.zeros(B, T, R, dtype=torch.float64)
+    mem = torch.zeros(B, T, dtype=torch.float64)
+    rl = torch.zeros(B, T, dtype=torch.long)
+    for b in range(B):
+        n = case["counts"][b]
+        ints[b, :n] = torch.from_numpy(case["ints"][off[b]:off[b + 1]]).double()
+        if case["rels"] is not None:
+            rels[b, :n] = torch.from_numpy(case["rels"][off[b]:off[b + 1]]).double()
+        mem[b, :n] = 1
+        rl[b, :n] = torch.from_numpy(case["rels_label"][off[b]:off[b + 1]]).long()
+    # the reference computes finite logits for empty slots too before masking them: use garbage there
+    g = torch.Generator().manual_seed(1)
+    ints = torch.where(mem.bool().unsqueeze(-1), ints, torch.randn(B, T, C, generator=g, dtype=torch.float64))
+    rels = torch.where(mem.bool().unsqueeze(-1), rels, torch.randn(B, T, R, generator=g, dtype=torch.float64))
+    return ints.requires_grad_(True), rels.requires_grad_(True), mem, rl
+
+
+@pytest.mark.parametrize("tr_correct,max_neg", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("with_rels", [True, False])
+def test_track_losses(tr_correct, max_neg, with_rels):
+    from lirec_b200 import ops
+    from oracle import losses as ol
+    case = _ragged_case(24, seed=7 + int(tr_correct) + 2 * int(max_neg), with_rels=with_rels)
+    B = 24
+    dev = lambda a: None if a is None else torch.from_numpy(a).cuda()
+    lo, assign, d_i, d_r = ops.loss_track(dev(case["ints"]), dev(case["rels"]), dev(case["off"]), dev(case["labels"]),
+                                          dev(case["rels_label"]), dev(case["gt"]), dev(case["multilab"]), 0.101,
+                                          0.7 if with_rels else 1.0, R if with_rels else 0, tr_correct=tr_correct,
+                                          max_neg=max_neg, max_slots=T)
+    ints, rels, mem, rl = _dense(case)
+    labels, gt = torch.from_numpy(case["labels"]).long(), torch.from_numpy(case["gt"]).long()
+    mw = torch.from_numpy(case["multilab"]).double()
+    if with_rels:
+        ref, ts, _, _ = ol.margin_track_rels(ints, rels, labels, rl, mem, mw, gt, 0.101, 0.7, R, tr_correct=tr_correct,
+                                             max_neg=max_neg)
+    else:
+        ref, ts, _ = ol.margin_loss(ints, labels, mem, mw, gt, 0.101, tr_correct=tr_correct, max_neg=max_neg)
+    ref.backward()
+    assert torch.equal(assign.cpu().long(), ts)                       # bit-exact assignment
+    assert abs(lo.sum().item() - ref.item()) / abs(ref.item()) < 1e-5
+    mm = mem.bool()
+    gi = ints.grad[mm]
+    assert float((d_i.cpu().double() - gi).abs().max() / gi.abs().max()) < 1e-4
+    assert ints.grad[~mm].abs().max() == 0                            # empty slots get exactly zero gradient
+    if with_rels:
+        gr = rels.grad[mm]
+        assert float((d_r.cpu().double() - gr).abs().max() / (gr.abs().max() + 1e-30)) < 1e-4
+
+
+def test_assignment_ties_resolve_to_lowest_index():
+    from lirec_b200 import ops
+    from oracle import losses as ol
+    case = _ragged_case(40, seed=3, dup_ties=True)
+    dev = lambda a: torch.from_numpy(a).cuda()
+    _, assign, _, _ = ops.loss_track(dev(case["ints"]), dev(case["rels"]), dev(case["off"]), dev(case["labels"]),
+                                     dev(case["rels_label"]), dev(case["gt"]), dev(case["multilab"]), 0.101, 1.0, R)
+    ints, rels, mem, rl = _dense(case)
+    _, ts, _, _ = ol.margin_track_rels(ints.float(), rels.float(), torch.from_numpy(case["labels"]).long(), rl, mem.float(),
+                                       torch.from_numpy(case["multilab"]).float(), torch.from_numpy(case["gt"]).long(),
+                                       0.101, 1.0, R)
+    assert torch.equal(assign.cpu().long(), ts)
+    tied = [b for b in range(40) if case["counts"][b] >= 3]
+    assert tied and any(int(assign[b]) == 1 for b in tied)            # slot 1 wins its tie with slot 2
+
+
+def test_row_margin_loss():
+    """MaxMarginCrossEntropyLoss / MultiTaskMaxMargin terms (model.py:381-441)."""
+    from lirec_b200 import ops
+    from oracle import losses as ol
+    rng = np.random.default_rng(0)
+    B = 50
+    x = (rng.standard_normal((B, C)) * 2).astype(np.float32)
+    y = rng.integers(C, size=B).astype(np.int32)
+    w = (rng.random((B, C)) < 0.9).astype(np.uint8)
+    terms, d = ops.loss_rowmargin(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(w).cuda(),
+                                  0.101, 1.0 / B)
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    ref = ol.max_margin_ce(xt, torch.from_numpy(y).long(), torch.from_numpy(w).double(), 0.101)
+    ref.backward()
+    assert abs(terms.sum().item() - ref.item()) / ref.item() < 1e-5
+    assert float((d.cpu().double() - xt.grad).abs().max() / xt.grad.abs().max()) < 1e-4
+    # relationship term: rows labelled None (-1 here) are skipped
+    r = (rng.standard_normal((B, R)) * 2).astype(np.float32)
+    lab = rng.integers(R + 1, size=B).astype(np.int32)
+    sel = lab.copy()
+    sel[sel == R] = -1
+    n_sel = int((lab != R).sum())
+    terms, d = ops.loss_rowmargin(torch.from_numpy(r).cuda(), torch.from_numpy(sel).cuda(), None, 0.101, 1.0 / n_sel)
+    rt = torch.from_numpy(r).double().requires_grad_(True)
+    ref = ol.multitask_max_margin(None, rt, None, torch.from_numpy(lab).long(), None, 0.101, 1.0, R, ints=0, ctx=1)
+    ref.backward()
+    assert abs(terms.sum().item() - ref.item()) / ref.item() < 1e-5
+    assert float((d.cpu().double() - rt.grad).abs().max() / rt.grad.abs().max()) < 1e-4
+
+
+def test_flat_adam_matches_torch_adam():
+    from lirec_b200 import ops
+    torch.manual_seed(0)
+    n = 100003
+    p0 = torch.randn(n, device="cuda")
+    ref_p = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref_p], lr=3e-5, weight_decay=1e-5)
+    p, m, v = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    pb = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    for step in range(1, 4):
+        g = torch.randn(n, device="cuda")
+        ref_p.grad = g.clone()
+        opt.step()
+        ops.adam_flat(p, g, m, v, pb, 3e-5, 0.9, 0.999, 1e-8, 1e-5, step)
+    assert float((p - ref_p.detach()).abs().max()) < 1e-6
+    assert torch.equal(pb, p.to(torch.bfloat16))

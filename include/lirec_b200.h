@@ -222,6 +222,15 @@ int lirec_loss_rowmargin_fwd_bwd(const float* logits, int64_t ld, int32_t rows, 
                                  float scale, float* loss_per_row, float* d_logits,
                                  int64_t d_ld, void* stream);
 
+/* Prediction arg-maxes of the evaluation loop (reference utils/evaluation.py:114-175, 179-271:
+ * track assignment for the GT class (+ relationship), joint (t,c[,r]) arg-max, class / relationship
+ * arg-max at the two GT slots), computed on the ragged logits so only 8 integers per clip go back to
+ * the host.  out: int32 [B, 8] = {pr_track, joint_t, joint_c, joint_r, cls_gt0, cls_gt1, rel_gt0,
+ * rel_gt1}; lowest index wins ties, like np.argmax.  n_rels == 0 -> interaction-only form.        */
+int lirec_predict_tracks(const float* ints, const float* rels, const int32_t* cand_off, int32_t B,
+                         const int32_t* labels, const int32_t* rels_label, const int32_t* gt_tracks,
+                         int32_t n_classes, int32_t n_rels, int32_t* out, void* stream);
+
 /* ---- the model hot path: one call per direction ---------------------------
  * Native launch sequence for the forward and backward of Modalities
  * (mlp/model.py:19-92), MidFusionMultiClip (:95-211), MidFusionMultiClipMaxTracks

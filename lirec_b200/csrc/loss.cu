@@ -226,6 +226,101 @@ rowmargin_kernel(const float* __restrict__ logits, int64_t ld, int rows, int C,
   }
 }
 
+
+// Prediction arg-maxes of the evaluation loop (reference utils/evaluation.py:114-175, 179-271), one CTA
+// per clip over its valid candidate slots; empty slots are -inf there, i.e. never win.
+//   out[b] = { pr_track, joint_t, joint_c, joint_r, cls_at_gt0, cls_at_gt1, rel_at_gt0, rel_at_gt1 }
+//   pr_track : argmax_t sigma(ints[t,y]) (+ sigma(rels (+) 0)[t, r_gt])           (:137, :221-222)
+//   joint    : first arg-max of sigma(ints)[t,c] (+ sigma(rels (+) 0)[t,r]) over the flattened
+//              (t,c[,r]) index, the sum taken in double like numpy's float32 + float64  (:144-147, :229-235)
+//   cls/rel at gt_i : argmax over classes / relationship classes of the raw logits of slot gt_tracks[b,i]
+//              (-1 when that slot is empty)                                              (:152, :241-243)
+// Ties resolve to the lowest flattened index, like np.argmax.
+__global__ void __launch_bounds__(128)
+predict_kernel(const float* __restrict__ ints, const float* __restrict__ rels,
+               const int32_t* __restrict__ cand_off, const int32_t* __restrict__ labels,
+               const int32_t* __restrict__ rels_label, const int32_t* __restrict__ gt_tracks, int C, int R,
+               int32_t* __restrict__ out) {
+  __shared__ double s_val[128];
+  __shared__ long long s_idx[128];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int beg = cand_off[b], n = cand_off[b + 1] - beg;
+  const bool has_rels = R > 0;
+  const int R1 = has_rels ? R + 1 : 1;
+  const int y = labels[b];
+  const int gt0 = gt_tracks[2 * b], gt1 = gt_tracks[2 * b + 1];
+  const float* xi = ints + static_cast<int64_t>(beg) * C;
+  const float* xr = has_rels ? rels + static_cast<int64_t>(beg) * R : nullptr;
+  // relationship label of the ground-truth slot: evaluation.py:208 takes gt_rels[:, 0]
+  const int rg = has_rels ? rels_label[beg] : 0;
+
+  auto reduce_first_max = [&](double v, long long i) -> long long {
+    s_val[tid] = v; s_idx[tid] = i;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+      if (tid < o) {
+        const double v2 = s_val[tid + o]; const long long i2 = s_idx[tid + o];
+        if (v2 > s_val[tid] || (v2 == s_val[tid] && i2 < s_idx[tid])) { s_val[tid] = v2; s_idx[tid] = i2; }
+      }
+      __syncthreads();
+    }
+    const long long r = s_idx[0];
+    __syncthreads();
+    return r;
+  };
+  const double NEG = -1e300;
+  // ---- track assignment for the ground-truth class (and relationship) ----
+  {
+    double v = NEG; long long idx = 0x7fffffffffffLL;
+    for (int t = tid; t < n; t += blockDim.x) {
+      double sc = static_cast<double>(sigmoidf(xi[static_cast<int64_t>(t) * C + y]));
+      if (has_rels) sc += (rg < R) ? static_cast<double>(sigmoidf(xr[static_cast<int64_t>(t) * R + rg])) : 0.0;
+      if (sc > v) { v = sc; idx = t; }
+    }
+    const long long r = reduce_first_max(v, idx);
+    if (tid == 0) out[8 * b + 0] = static_cast<int32_t>(r);
+  }
+  // ---- joint (t, c[, r]) arg-max ----
+  {
+    double v = NEG; long long idx = 0x7fffffffffffLL;
+    const long long total = static_cast<long long>(n) * C * R1;
+    for (long long e = tid; e < total; e += blockDim.x) {
+      const int t = static_cast<int>(e / (C * R1));
+      const int rem = static_cast<int>(e - static_cast<long long>(t) * C * R1);
+      const int c = rem / R1, r = rem - c * R1;
+      double sc = static_cast<double>(sigmoidf(xi[static_cast<int64_t>(t) * C + c]));
+      if (has_rels) sc += (r < R) ? static_cast<double>(sigmoidf(xr[static_cast<int64_t>(t) * R + r])) : 0.0;
+      if (sc > v) { v = sc; idx = e; }
+    }
+    const long long r = reduce_first_max(v, idx);
+    if (tid == 0) {
+      const int t = static_cast<int>(r / (C * R1));
+      const int rem = static_cast<int>(r - static_cast<long long>(t) * C * R1);
+      out[8 * b + 1] = t; out[8 * b + 2] = rem / R1; out[8 * b + 3] = has_rels ? rem % R1 : -1;
+    }
+  }
+  // ---- class / relationship arg-max at the ground-truth slots ----
+  for (int i = 0; i < 2; ++i) {
+    const int g = i ? gt1 : gt0;
+    double v = NEG; long long idx = 0x7fffffffffffLL;
+    if (g < n)
+      for (int c = tid; c < C; c += blockDim.x) {
+        const double sc = xi[static_cast<int64_t>(g) * C + c];
+        if (sc > v) { v = sc; idx = c; }
+      }
+    long long r = reduce_first_max(v, idx);
+    if (tid == 0) out[8 * b + 4 + i] = (g < n) ? static_cast<int32_t>(r) : -1;
+    v = NEG; idx = 0x7fffffffffffLL;
+    if (has_rels && g < n)
+      for (int c = tid; c < R; c += blockDim.x) {
+        const double sc = xr[static_cast<int64_t>(g) * R + c];
+        if (sc > v) { v = sc; idx = c; }
+      }
+    r = reduce_first_max(v, idx);
+    if (tid == 0) out[8 * b + 6 + i] = (has_rels && g < n) ? static_cast<int32_t>(r) : -1;
+  }
+}
+
 // torch.optim.Adam (coupled L2) over the flat parameter buffer + bf16 shadow refresh.
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -282,6 +377,20 @@ extern "C" int lirec_loss_rowmargin_fwd_bwd(const float* logits, int64_t ld, int
   if (rows <= 0) return LIREC_OK;
   loss::rowmargin_kernel<<<rows, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       logits, ld, rows, C, labels, weights, margin, scale, loss_per_row, d_logits, d_ld);
+  LIREC_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return LIREC_OK;
+}
+
+extern "C" int lirec_predict_tracks(const float* ints, const float* rels, const int32_t* cand_off, int32_t B,
+                                    const int32_t* labels, const int32_t* rels_label, const int32_t* gt_tracks,
+                                    int32_t n_classes, int32_t n_rels, int32_t* out, void* stream) {
+  LIREC_ENTER();
+  LIREC_REQUIRE(ints && cand_off && labels && gt_tracks && out && n_classes > 0, "predict: bad arguments");
+  LIREC_REQUIRE(n_rels == 0 || (rels && rels_label), "predict: relationship tensors missing");
+  if (B <= 0) return LIREC_OK;
+  loss::predict_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(ints, rels, cand_off, labels, rels_label,
+                                                                        gt_tracks, n_classes, n_rels, out);
   LIREC_CUDA_OK(cudaGetLastError());
   note_launch();
   return LIREC_OK;

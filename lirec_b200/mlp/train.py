@@ -1,0 +1,105 @@
+"""Training loop (reference: mlp/train.py:21-107): epochs over the dataset, forward, loss,
+zero_grad, backward, Adam step, periodic evaluation and checkpoints in the reference's format.
+
+Differences on purpose: batches are PackedBatches prefetched to the GPU asynchronously; the loss
+value is read back every 10 iterations instead of every step (mlp/train.py:59 syncs each step);
+with `opt.dp` the clips of every global batch are split over the ranks and the flat gradient buffer
+is all-reduced over NCCL before the optimizer step (lirec_b200/dp.py).  Batches of a single clip
+are skipped like the reference does (:55-56)."""
+import copy
+import time
+from datetime import datetime
+from os.path import join
+
+import torch
+
+from lirec_b200 import dp
+from lirec_b200.mixed_utils.classification_dataloader import packed_loader
+from lirec_b200.mlp.test import testing
+from lirec_b200.utils.arg_pars import opt
+from lirec_b200.utils.model_saver import ModelSaver
+from lirec_b200.utils.util_functions import Averaging, dir_check
+
+
+def train_step(model, loss, optimizer, pb, world=1):
+    """One optimisation step on a device PackedBatch; returns the (device) loss tensor."""
+    output = model(pb)
+    loss_values = loss(output, {})
+    optimizer.zero_grad()
+    loss_values.backward()
+    scale = 1.0
+    if world > 1:
+        local = pb.B
+        global_clips = getattr(pb.host, "global_clips", None) if getattr(pb, "host", None) is not None else None
+        scale = dp.allreduce_flat_grad(model._flat_grad, local, global_clips,
+                                       average_in_place=not hasattr(optimizer, "model"))
+    if hasattr(optimizer, "model"):          # FlatAdam folds the 1/world average into the kernel
+        optimizer.step(grad_scale=scale)
+    else:
+        optimizer.step()
+    return loss_values
+
+
+def training(train_dataset, **kwargs):
+    train_start_time = datetime.now().strftime("%Y%m%d-%H%M%S")
+    print("set parameters and model, train start time: %s" % train_start_time)
+    model, loss, optimizer = kwargs["model"], kwargs["loss"], kwargs["optimizer"]
+    rank, world = 0, 1
+    if getattr(opt, "dp", 0):
+        rank, world, _ = dp.init_from_env()
+        model._sync_flat()
+        dp.broadcast_params(model._flat)
+    batch_time, data_time, losses = Averaging(), Averaging(), Averaging()
+    print("epochs: %s", opt.epochs)
+    model_saver_val = ModelSaver(path=opt.store_root)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    epoch = 0
+    for epoch in range(opt.epochs):
+        model.to(opt.device)
+        model.train()
+        train_dataset.epoch = epoch
+        print("Epoch # %d" % epoch)
+        end = time.time()
+        counter = 0
+        if opt.tr_sum_max and epoch == 20:
+            opt.tr_sum_max_flag = True                      # reference: :49-51
+        n_batches = (len(train_dataset) + opt.batch_size - 1) // opt.batch_size
+        for i, pb in enumerate(packed_loader(train_dataset, opt.batch_size, shuffle=True,
+                                             num_workers=opt.num_workers, device=dev, rank=rank, world=world,
+                                             seed=opt.seed)):
+            data_time.update(time.time() - end)
+            if getattr(pb.host, "global_clips", pb.B) == 1:
+                continue
+            loss_values = train_step(model, loss, optimizer, pb, world)
+            counter += pb.B
+            if i % 10 == 0:
+                losses.update(loss_values.item(), pb.B)      # device->host sync only here
+            batch_time.update(time.time() - end)
+            end = time.time()
+            if i % 10 == 0 and i and rank == 0:
+                print("Epoch: [{0}][{1}/{2}]\tTime {bt.val:.3f} ({bt.avg:.3f})\tData {dt.val:.3f} ({dt.avg:.3f})\t"
+                      "Loss {loss.val:.4f} ({loss.avg:.4f})\t".format(epoch, i, n_batches, bt=batch_time,
+                                                                       dt=data_time, loss=losses))
+        print(counter)
+        print("loss: %f" % losses.avg)
+        losses.reset()
+        if epoch % opt.test_fr == 0:
+            testing(train_dataset, model, loss, total_iter=epoch, mode="train", train_start_time=train_start_time)
+            if opt.test and kwargs.get("val_dataset", kwargs.get("test_dataset")) is not None:
+                val_dataset = kwargs.get("val_dataset", kwargs.get("test_dataset"))
+                check_val = testing(val_dataset, model, loss, total_iter=epoch, train_start_time=train_start_time,
+                                    mode="val")
+                if rank == 0 and model_saver_val.check(check_val):
+                    save_dict = {"epoch": epoch, "state_dict": copy.deepcopy(model.state_dict()),
+                                 "optimizer": copy.deepcopy(optimizer.state_dict().copy())}
+                    model_saver_val.update(check_val, save_dict, epoch)
+            print(opt.log_prefix)
+        if opt.save_model and opt.save_model_often and epoch % 30 == 0 and rank == 0:
+            model_saver_val.save()
+    check_str = join(opt.store_root)
+    opt.resume_str = join(check_str, "%d.pth.tar" % epoch)
+    if opt.save_model and rank == 0:
+        save_dict = {"epoch": epoch, "state_dict": model.state_dict(), "optimizer": optimizer.state_dict()}
+        dir_check(check_str)
+        torch.save(save_dict, opt.resume_str)
+    return model

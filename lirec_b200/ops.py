@@ -12,7 +12,7 @@ from ._ext import (ACT_NONE, ACT_RELU, ACT_TANH, OUT_F32, OUT_SPLIT, POST_DRELU,
                    POST_NONE)
 
 __all__ = ["gemm_problem", "gemm_grouped", "seg_reduce", "rows_expand_fwd", "rows_expand_bwd", "split_f32",
-           "cast_bf16", "loss_track", "loss_rowmargin", "adam_flat", "dropout_desc"]
+           "cast_bf16", "loss_track", "loss_rowmargin", "predict_tracks", "adam_flat", "dropout_desc"]
 
 
 def dropout_desc(p=0.0, seed=0, stream_id=0, col_off=0):
@@ -127,6 +127,18 @@ def loss_rowmargin(logits, labels, weights, margin, scale):
         _ext.ptr(logits), logits.stride(0), rows, Cc, _ext.ptr(labels), _ext.ptr(weights), float(margin),
         float(scale), _ext.ptr(loss), _ext.ptr(d), d.stride(0), _ext.stream_ptr()))
     return loss, d
+
+
+def predict_tracks(ints, rels, cand_off, labels, rels_label, gt_tracks, n_rels):
+    """Device-side prediction arg-maxes; returns int32 [B, 8] (see include/lirec_b200.h)."""
+    B = cand_off.numel() - 1
+    out = torch.empty(B, 8, dtype=torch.int32, device=ints.device)
+    L = _ext.lib()
+    _ext.check(L.lirec_predict_tracks(_ext.ptr(ints), _ext.ptr(rels) if n_rels else None, _ext.ptr(cand_off), B,
+                                      _ext.ptr(labels), _ext.ptr(rels_label) if n_rels else None,
+                                      _ext.ptr(gt_tracks), ints.shape[1], int(n_rels), _ext.ptr(out),
+                                      _ext.stream_ptr()))
+    return out
 
 
 def adam_flat(param, grad, exp_avg, exp_avg_sq, param_bf16, lr, beta1, beta2, eps, weight_decay, step,

@@ -174,6 +174,13 @@ class PackedBatch:
         d.host = self
         return d
 
+    def record_stream(self, stream):
+        """Tell the caching allocator that `stream` uses this batch's device tensors (they may have been
+        allocated on a copy stream)."""
+        for t in (self._arena_dev, self.clip_bank, self.track_bank, self.multilab):
+            t.record_stream(stream)
+        return self
+
     # ---- dense (reference-format) view -------------------------------------------------------
     def to_dense(self, dtype=np.float64):
         """The batch as the reference dataloader + default collate would emit it (host only)."""

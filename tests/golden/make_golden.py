@@ -1,0 +1,105 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+For each preset / loss variant a small random model of the reference (reduced dims so the fixtures
+stay small) is built with the reference's own create_model, run forward + loss + backward on a
+random dense batch in eval mode, and inputs, parameters, outputs, loss, the in-place masked logits
+and all parameter gradients are stored.  tests/test_oracle_golden.py checks oracle/ against them
+everywhere (the GPU box has no /root/reference).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.argv = sys.argv[:1]
+
+from oracle import reference_shim as rs  # noqa: E402
+
+DIMS = dict(text_dim=24, visual_dim=40, track_dim=40, joint_dim=16, mid_m_ints=6)
+C, R, B, T, S = 11, 5, 4, 5, 3
+D = DIMS["text_dim"] + DIMS["visual_dim"] + 2 * DIMS["track_dim"]
+
+CASES = [
+    ("modalities", {}), ("int_rels", {}), ("int_ch", {}), ("int_ch", dict(tr_correct=True)),
+    ("int_ch", dict(tr_max_neg=True)), ("int_rel_ch", {}), ("int_rel_ch", dict(tr_correct=True)),
+    ("int_rel_ch", dict(tr_max_neg=True)), ("int_rel_ch", dict(tr_correct=True, tr_max_neg=True)),
+]
+
+
+def make_batch(preset, rng):
+    g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
+    b = {}
+    if preset == "modalities":
+        b["features"] = torch.randn(B, 1, D, generator=g, dtype=torch.float64)
+        b["labels"] = torch.randint(C, (B,), generator=g)
+    elif preset == "int_rels":
+        b["features"] = torch.randn(B, S + 1, D, generator=g, dtype=torch.float64)
+        m = torch.zeros(B, S, 1, dtype=torch.long)
+        for i in range(B):
+            m[i, :int(rng.integers(1, S + 1))] = 1
+        b["rels_mask"] = m
+        b["labels"] = torch.randint(C, (B, S + 1, 1), generator=g)
+        b["rels_label"] = torch.tensor([0, R, 2, 1])[:B]          # one None-labelled sample
+    else:
+        ctx = preset == "int_rel_ch"
+        shape = (B, T, S + 1, D) if ctx else (B, T, D)
+        b["features"] = torch.randn(*shape, generator=g, dtype=torch.float64)
+        mem = torch.zeros(B, T, dtype=torch.float64)
+        counts = [T, 2, 3, 1][:B]
+        for i, n in enumerate(counts):
+            mem[i, :n] = 1
+        b["mem_mask"] = mem
+        b["labels"] = torch.randint(C, (B,), generator=g)
+        b["gt_tracks"] = torch.tensor([[0, 2], [0, 0], [0, 1], [0, 0]])[:B]
+        if ctx:
+            rm = torch.zeros(B, T, S, dtype=torch.long)
+            for i, n in enumerate(counts):
+                for t in range(n):
+                    rm[i, t, :int(rng.integers(0 if t else 1, S + 1))] = 1     # includes empty contexts
+            b["rels_mask"] = rm
+            rl = torch.randint(R + 1, (B, T), generator=g)
+            rl = torch.where(mem.bool(), rl, torch.zeros_like(rl))              # pad label 0
+            b["rels_label"] = rl
+    b["multilab_weights"] = (torch.rand(B, C, generator=g) < 0.85).double()
+    return b
+
+
+def main():
+    opt, _ = rs.load()
+    rng = np.random.default_rng(0)
+    for idx, (preset, over) in enumerate(CASES):
+        for k, v in DIMS.items():
+            setattr(opt, k, v)
+        opt.mlp_dim = D
+        model, loss = rs.create_model(preset, C, R, seed=idx, **over)
+        model.eval()
+        batch = make_batch(preset, rng)
+        inp = {k: v.clone() for k, v in batch.items()}
+        out = model(batch)                     # MaxTracks reshapes batch['features'] in place
+        lv = rs.run_loss(loss, out, batch)     # track losses overwrite out[...] with -inf in place
+        lv.backward()
+        rec = {"loss": np.float64(lv.item())}
+        for k, v in inp.items():
+            rec["in_" + k] = v.numpy()
+        for k, v in model.state_dict().items():
+            rec["p_" + k] = v.numpy()
+        for k, p in model.named_parameters():
+            rec["g_" + k] = p.grad.numpy()
+        for k, v in out.items():
+            if v is not None:
+                rec["out_" + k] = v.detach().numpy()
+        rec["meta"] = np.array([preset, repr(sorted(over.items()))])
+        name = "%s%s.npz" % (preset, "".join("_" + k for k in sorted(over)))
+        np.savez_compressed(os.path.join(HERE, name), **rec)
+        print("wrote", name, "loss", lv.item())
+    # restore the full-size dims for anything else importing the shim in this process
+    opt.text_dim, opt.visual_dim, opt.track_dim, opt.joint_dim, opt.mlp_dim = 768, 2048, 2048, 512, 6912
+
+
+if __name__ == "__main__":
+    main()

@@ -47,7 +47,7 @@ def test_synthetic_batch_structure(preset):
     else:
         assert (counts == 1).all()
     assert t["cand_rows"][:, 0].max() < pb.n_clip_ints and t["cand_rows"][:, 1:].max() < pb.n_track_ints
-    assert (pb.track_bank[0] == 0).all()
+    assert (pb.track_bank[0] == 0).all()  # clip 0's no-track row
     if pb.has_ctx:
         n_ctx = np.diff(t["ctx_off"])
         assert n_ctx.min() >= 1 and n_ctx.max() <= pb.n_ctx_slots

@@ -151,3 +151,21 @@ def test_flat_adam_matches_torch_adam():
         ops.adam_flat(p, g, m, v, pb, 3e-5, 0.9, 0.999, 1e-8, 1e-5, step)
     assert float((p - ref_p.detach()).abs().max()) < 1e-6
     assert torch.equal(pb, p.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("with_rels", [True, False])
+def test_prediction_argmaxes_are_bit_exact(with_rels):
+    """Device-side evaluation arg-maxes (utils/evaluation.py:114-271) equal the numpy restatement on
+    identical logits, including exact ties between duplicated candidate slots."""
+    from lirec_b200 import ops
+    from oracle import evaluation as oe
+    case = _ragged_case(48, seed=11, with_rels=with_rels, dup_ties=True)
+    dev = lambda a: None if a is None else torch.from_numpy(a).cuda()
+    got = ops.predict_tracks(dev(case["ints"]), dev(case["rels"]), dev(case["off"]), dev(case["labels"]),
+                             dev(case["rels_label"]), dev(case["gt"]), R if with_rels else 0).cpu().numpy()
+    ints, rels, mem, rl = _dense(case)
+    ref = oe.predict_tracks(ints.detach().numpy(), rels.detach().numpy() if with_rels else None, mem.numpy(),
+                            case["labels"], rl.numpy(), case["gt"])
+    if not with_rels:
+        ref[:, 3] = -1
+    assert np.array_equal(got, ref)

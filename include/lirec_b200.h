@@ -122,6 +122,11 @@ typedef struct lirec_gemm_problem {
   int32_t num_passes;
   lirec_gemm_pass pass[LIREC_GEMM_MAX_PASSES];
   lirec_epilogue epi;
+  /* split-K: when split_k > 1 the reduction range of every pass is cut into split_k slices of whole
+   * 64-element k-blocks; slice s runs as its own tiles and writes its partial result to
+   * out + s * split_stride (elements).  The caller sums the slices (fixed order = deterministic). */
+  int32_t split_k;
+  int64_t split_stride;
 } lirec_gemm_problem;
 
 /* One persistent launch over all tiles of all problems (host array). */

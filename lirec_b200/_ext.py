@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblirec_b200.so")
+LIB_PATH = os.environ.get("LIREC_B200_LIB", os.path.join(_HERE, "liblirec_b200.so"))
 
 MAX_PASSES = 4
 MAX_PROBLEMS = 32
@@ -52,7 +52,8 @@ class GemmProblem(C.Structure):
                 ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32),
                 ("num_passes", C.c_int32),
                 ("pass_", GemmPass * MAX_PASSES),
-                ("epi", Epilogue)]
+                ("epi", Epilogue),
+                ("split_k", C.c_int32), ("split_stride", C.c_int64)]
 
 
 class TrackLossCfg(C.Structure):

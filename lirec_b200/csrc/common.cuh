@@ -52,10 +52,20 @@ __host__ __device__ __forceinline__ uint32_t drop_row_key(uint32_t seed, uint32_
                                                            uint32_t row) {
   return fmix32(seed ^ (stream_id * 0x9E3779B1u) ^ fmix32(row + 0x7F4A7C15u));
 }
-// 1.0f if element (row, col) is kept.  24-bit uniform compared against p.
+// One 32-bit hash word covers two adjacent columns (16 bits each).
+__host__ __device__ __forceinline__ uint32_t drop_word(uint32_t row_key, uint32_t col_pair) {
+  return fmix32(row_key ^ (col_pair * 0x9E3779B1u + 0x632BE5ABu));
+}
+// keep threshold on the 16-bit lane: drop iff lane < p * 65536
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
+  return static_cast<uint32_t>(p * 65536.0f + 0.5f);
+}
+__host__ __device__ __forceinline__ bool drop_keep_word(uint32_t word, uint32_t col, uint32_t thr) {
+  return ((word >> ((col & 1u) * 16u)) & 0xFFFFu) >= thr;
+}
+// true if element (row, col) is kept
 __host__ __device__ __forceinline__ bool drop_keep(uint32_t row_key, uint32_t col, float p) {
-  uint32_t h = fmix32(row_key ^ (col * 0x9E3779B1u + 0x632BE5ABu));
-  return (float)(h >> 8) * (1.0f / 16777216.0f) >= p;
+  return drop_keep_word(drop_word(row_key, col >> 1), col, drop_threshold(p));
 }
 
 // ---- hi/lo bf16 split: x ~= hi + lo with |err| <= 2^-17 |x| -----------------

@@ -81,8 +81,43 @@ struct Workspace {
   bf16* dz2[2];       // [Ni, 6J]
   float* da2[2];      // [Ni, 4J]
   bf16* dz1[2][4];    // [n_unique, 2J]
+  float* pool;        // split-K partial gradients
+  size_t pool_floats;
   size_t bytes;
 };
+
+// ---- split-K of long, few-tile reductions -----------------------------------------------------
+// A weight / bias gradient reduces over all rows of the batch (thousands of k-blocks) but has only a
+// handful of output tiles, so on its own it would occupy a few SMs for the whole stage.  Such a
+// problem is cut into S row ranges that write partial results into a pool; one small kernel sums
+// the partials into the flat gradient buffer at the end of backward, in a fixed order
+// (deterministic, no atomics).
+static int split_factor(int M, int N, int passes, int rows) {
+  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  const int kb = passes * ((rows + 63) / 64);
+  if (tiles > 32 || kb < 128) return 1;
+  return std::max(1, std::min(8, kb / 64));
+}
+static size_t split_pool_floats(const Dims& d) {
+  size_t n = 0;
+  auto add = [&](int M, int N, int passes, int rows) {
+    const int S = split_factor(M, N, passes, rows);
+    if (S > 1) n += (size_t)S * M * N;
+  };
+  const int hw = d.gates ? d.Gd : d.F;
+  add(d.C, hw, 3, d.Ni); add(d.C, 1, 2, d.Ni);
+  if (d.ctx) { add(d.R, d.F, 3, d.Ni); add(d.R, 1, 2, d.Ni); }
+  if (d.gates) { add(d.Gd, d.F, 3, d.Ni); add(d.Gd, d.F, 3, d.Ni); add(d.Gd, 1, 2, d.Ni); }
+  for (int br = 0; br < (d.ctx ? 2 : 1); ++br) {
+    const int ncl = br ? d.nc : d.nci, ntr = br ? d.nt : d.nti;
+    for (int s = 0; s < 4; ++s) {
+      add(d.outw[s], d.J, 3, d.Ni); add(d.outw[s], 1, 2, d.Ni);
+      const int nu = (s < 2) ? ncl : ntr;
+      add(d.J, d.inw[s], 2, nu); add(d.J, 1, 2, nu);
+    }
+  }
+  return n;
+}
 
 static Workspace carve(const Dims& d, void* base) {
   Workspace w;
@@ -119,6 +154,8 @@ static Workspace carve(const Dims& d, void* base) {
   w.dpreg2 = static_cast<bf16*>(take((size_t)d.Ni * 2 * d.Gd * 2));
   w.dli2 = static_cast<bf16*>(take((size_t)d.Ni * 2 * d.CP * 2));
   w.dlr2 = static_cast<bf16*>(take((size_t)d.Ni * 2 * d.RP * 2));
+  w.pool_floats = split_pool_floats(d);
+  w.pool = static_cast<float*>(take(w.pool_floats * 4));
   w.bytes = off;
   return w;
 }
@@ -128,6 +165,34 @@ __global__ void fill_bf16_kernel(bf16* p, int64_t n, float v) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     p[i] = b;
 }
+
+struct ReduceJob {
+  float* dst;
+  const float* src;
+  int32_t M, N, S;
+  int64_t dst_ld;
+};
+constexpr int MAX_REDUCE_JOBS = 96;
+struct ReduceJobs {
+  ReduceJob job[MAX_REDUCE_JOBS];
+  int32_t n;
+};
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceJobs jobs) {
+  const ReduceJob& j = jobs.job[blockIdx.y];
+  const int64_t total = (int64_t)j.M * j.N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < j.S; ++s) acc += j.src[(int64_t)s * total + i];
+    const int m = (int)(i / j.N), n = (int)(i - (int64_t)m * j.N);
+    j.dst[(int64_t)m * j.dst_ld + n] = acc;
+  }
+}
+
+struct SplitCtx {
+  float* pool;
+  size_t pool_floats, used;
+  ReduceJobs jobs;
+};
 
 // ---- small builders --------------------------------------------------------
 static lirec_operand op(const void* p, int64_t rows, int64_t cols, int64_t ld) {
@@ -352,6 +417,28 @@ static lirec_gemm_problem bgrad(int out_f, const bf16* dy, int64_t dy_cols, int 
   return g;
 }
 
+// Push a reduction-over-rows problem (all passes have k_len == rows), split-K if that helps.
+static void push_reduction(std::vector<lirec_gemm_problem>& pr, lirec_gemm_problem g, int rows, SplitCtx& sc) {
+  const int S = split_factor(g.M, g.N, g.num_passes, rows);
+  const size_t need = (size_t)S * g.M * g.N;
+  if (S > 1 && sc.used + need <= sc.pool_floats && sc.jobs.n < MAX_REDUCE_JOBS) {
+    ReduceJob& j = sc.jobs.job[sc.jobs.n++];
+    j.dst = static_cast<float*>(g.epi.out);
+    j.dst_ld = g.epi.out_ld_m;
+    j.src = sc.pool + sc.used;
+    j.M = g.M; j.N = g.N;
+    const int kb = (rows + 63) / 64, chunk = (kb + S - 1) / S;
+    j.S = (kb + chunk - 1) / chunk;                       // the slice count the GEMM will actually use
+    g.split_k = S;
+    g.split_stride = (int64_t)g.M * g.N;
+    g.epi.out = sc.pool + sc.used;
+    g.epi.out_ld_m = g.N;
+    g.epi.out_ld_n = 1;
+    sc.used += need;
+  }
+  pr.push_back(g);
+}
+
 int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lirec_batch& B, void* ws,
              const float* d_ints, const float* d_rels, cudaStream_t stream) {
   const Dims d = make_dims(cfg, B);
@@ -368,6 +455,8 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
                   "model backward: inverse context tables missing");
   }
 
+  SplitCtx sc;
+  sc.pool = w.pool; sc.pool_floats = w.pool_floats; sc.used = 0; sc.jobs.n = 0;
   if ((rc = rows::split_f32(d_ints, d.C, Ni, d.C, w.dli2, 2 * CP, CP, stream)) != LIREC_OK) return rc;
   if (d.ctx && (rc = rows::split_f32(d_rels, d.R, Ni, d.R, w.dlr2, 2 * RP, RP, stream)) != LIREC_OK) return rc;
 
@@ -378,11 +467,11 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
 
   // ---- stage H: head wgrad/bgrad + dgrad through the head --------------------
   std::vector<lirec_gemm_problem> pr;
-  pr.push_back(wgrad(d.C, hw, w.dli2, 2 * CP, 0, CP, hx, 2 * hw, 2 * hw, 0, hw, Ni, 1.f, P.out_ints.grad_w, hw));
-  pr.push_back(bgrad(d.C, w.dli2, 2 * CP, 0, CP, w.ones, Ni, P.out_ints.grad_b));
+  push_reduction(pr, wgrad(d.C, hw, w.dli2, 2 * CP, 0, CP, hx, 2 * hw, 2 * hw, 0, hw, Ni, 1.f, P.out_ints.grad_w, hw), Ni, sc);
+  push_reduction(pr, bgrad(d.C, w.dli2, 2 * CP, 0, CP, w.ones, Ni, P.out_ints.grad_b), Ni, sc);
   if (d.ctx) {
-    pr.push_back(wgrad(d.R, F, w.dlr2, 2 * RP, 0, RP, w.f2[1], 2 * F, 2 * F, 0, F, Ni, 1.f, P.out_ctx.grad_w, F));
-    pr.push_back(bgrad(d.R, w.dlr2, 2 * RP, 0, RP, w.ones, Ni, P.out_ctx.grad_b));
+    push_reduction(pr, wgrad(d.R, F, w.dlr2, 2 * RP, 0, RP, w.f2[1], 2 * F, 2 * F, 0, F, Ni, 1.f, P.out_ctx.grad_w, F), Ni, sc);
+    push_reduction(pr, bgrad(d.R, w.dlr2, 2 * RP, 0, RP, w.ones, Ni, P.out_ctx.grad_b), Ni, sc);
   }
   {
     lirec_gemm_problem g = mk_problem(Ni, hw, false, true);
@@ -419,9 +508,9 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
   if (d.gates) {
     pr.clear();
     for (int h = 0; h < 2; ++h)  // columns [0,F) multiply the context feature, [F,2F) the ints feature
-      pr.push_back(wgrad(Gd, F, w.dpreg2, 2 * Gd, 0, Gd, w.f2[h ? 0 : 1], 2 * F, 2 * F, 0, F, Ni, 1.f,
-                         P.gate.grad_w + h * F, 2 * F));
-    pr.push_back(bgrad(Gd, w.dpreg2, 2 * Gd, 0, Gd, w.ones, Ni, P.gate.grad_b));
+      push_reduction(pr, wgrad(Gd, F, w.dpreg2, 2 * Gd, 0, Gd, w.f2[h ? 0 : 1], 2 * F, 2 * F, 0, F, Ni, 1.f,
+                               P.gate.grad_w + h * F, 2 * F), Ni, sc);
+    push_reduction(pr, bgrad(Gd, w.dpreg2, 2 * Gd, 0, Gd, w.ones, Ni, P.gate.grad_b), Ni, sc);
     const lirec_operand dg_k = op(w.dpreg2, Ni, 2 * Gd, 2 * Gd);
     const lirec_operand wg = op(P.gate.w_bf16, Gd, 2 * F, 2 * F);
     for (int h = 0; h < 2; ++h) {
@@ -449,10 +538,10 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
     const lirec_encoder& enc = br ? P.enc_ctx : P.enc_ints;
     const lirec_operand dz_k = op(w.dz2[br], Ni, 2 * F, 2 * F);
     for (int s = 0; s < 4; ++s) {
-      pr.push_back(wgrad(d.outw[s], J, w.dz2[br], 2 * F, d.cs[s], F + d.cs[s], w.a2[br], 8 * J, 8 * J,
-                         s * 2 * J, s * 2 * J + J, Ni, keep_scale, enc.l2[s].grad_w, J));
-      pr.push_back(bgrad(d.outw[s], w.dz2[br], 2 * F, d.cs[s], F + d.cs[s], br ? w.flag_bf16 : w.ones, Ni,
-                         enc.l2[s].grad_b));
+      push_reduction(pr, wgrad(d.outw[s], J, w.dz2[br], 2 * F, d.cs[s], F + d.cs[s], w.a2[br], 8 * J, 8 * J,
+                               s * 2 * J, s * 2 * J + J, Ni, keep_scale, enc.l2[s].grad_w, J), Ni, sc);
+      push_reduction(pr, bgrad(d.outw[s], w.dz2[br], 2 * F, d.cs[s], F + d.cs[s], br ? w.flag_bf16 : w.ones, Ni,
+                               enc.l2[s].grad_b), Ni, sc);
       lirec_gemm_problem g = mk_problem(Ni, J, false, true);
       const lirec_operand w2 = op(enc.l2[s].w_bf16, d.outw[s], J, J);
       add_pass(g, mk_pass(dz_k, 0, d.cs[s], w2, 0, 0, d.outw[s]));
@@ -505,12 +594,23 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
       if (s == 0) { x = static_cast<const bf16*>(B.clip_bank); x_ld = B.clip_ld; }
       else if (s == 1) { x = static_cast<const bf16*>(B.clip_bank) + d.inw[0]; x_ld = B.clip_ld; }
       else { x = static_cast<const bf16*>(B.track_bank); x_ld = B.track_ld; }
-      pr.push_back(wgrad(J, d.inw[s], w.dz1[br][s], 2 * J, 0, J, x, d.inw[s], x_ld, 0, -1, nu, 1.f,
-                         enc.l1[s].grad_w, d.inw[s]));
-      pr.push_back(bgrad(J, w.dz1[br][s], 2 * J, 0, J, w.ones, nu, enc.l1[s].grad_b));
+      push_reduction(pr, wgrad(J, d.inw[s], w.dz1[br][s], 2 * J, 0, J, x, d.inw[s], x_ld, 0, -1, nu, 1.f,
+                               enc.l1[s].grad_w, d.inw[s]), nu, sc);
+      push_reduction(pr, bgrad(J, w.dz1[br][s], 2 * J, 0, J, w.ones, nu, enc.l1[s].grad_b), nu, sc);
     }
   }
-  return gemm::run_grouped(pr.data(), (int)pr.size(), stream);
+  if ((rc = gemm::run_grouped(pr.data(), (int)pr.size(), stream)) != LIREC_OK) return rc;
+
+  // ---- sum the split-K partials into the flat gradient buffer (fixed order) -----------------------
+  if (sc.jobs.n > 0) {
+    int64_t biggest = 0;
+    for (int i = 0; i < sc.jobs.n; ++i) biggest = std::max<int64_t>(biggest, (int64_t)sc.jobs.job[i].M * sc.jobs.job[i].N);
+    dim3 grid((unsigned)std::min<int64_t>((biggest + 255) / 256, 296), sc.jobs.n);
+    reduce_partials_kernel<<<grid, 256, 0, stream>>>(sc.jobs);
+    LIREC_CUDA_OK(cudaGetLastError());
+    note_launch();
+  }
+  return LIREC_OK;
 }
 
 }  // namespace model

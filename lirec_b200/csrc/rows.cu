@@ -97,6 +97,7 @@ expand_fwd_kernel(const ExpandFwdJobs jobs) {
   int beg = o, end = o + 1;
   if (jb.seg_off) { beg = jb.seg_off[o]; end = jb.seg_off[o + 1]; }
   const int n = end - beg;
+  const uint32_t thr = drop_threshold(jb.drop.p);
   for (int j = threadIdx.x * 4; j < J; j += blockDim.x * 4) {
     float4 acc[4];
 #pragma unroll
@@ -109,11 +110,12 @@ expand_fwd_kernel(const ExpandFwdJobs jobs) {
       for (int s = 0; s < 4; ++s) {
         float4 v = ld4(src[s] + static_cast<int64_t>(u[s]) * J + j);
         if (jb.drop.p > 0.f) {
-          const uint32_t c = static_cast<uint32_t>(jb.drop.col_off + s * J + j);
-          if (!drop_keep(rkey, c, jb.drop.p)) v.x = 0.f;
-          if (!drop_keep(rkey, c + 1, jb.drop.p)) v.y = 0.f;
-          if (!drop_keep(rkey, c + 2, jb.drop.p)) v.z = 0.f;
-          if (!drop_keep(rkey, c + 3, jb.drop.p)) v.w = 0.f;
+          const uint32_t c = static_cast<uint32_t>(jb.drop.col_off + s * J + j);   // multiple of 4
+          const uint32_t w0 = drop_word(rkey, c >> 1), w1 = drop_word(rkey, (c >> 1) + 1);
+          if ((w0 & 0xFFFFu) < thr) v.x = 0.f;
+          if ((w0 >> 16) < thr) v.y = 0.f;
+          if ((w1 & 0xFFFFu) < thr) v.z = 0.f;
+          if ((w1 >> 16) < thr) v.w = 0.f;
         }
         acc[s].x += v.x; acc[s].y += v.y; acc[s].z += v.z; acc[s].w += v.w;
       }
@@ -165,11 +167,13 @@ expand_bwd_kernel(const ExpandBwdJobs jobs) {
       float4 g = ld4(jb.d_in + static_cast<int64_t>(o) * jb.d_ld + j);
       if (jb.drop.p > 0.f) {
         const uint32_t rkey = drop_row_key(jb.drop.seed, jb.drop.stream_id, static_cast<uint32_t>(i));
-        const uint32_t c = static_cast<uint32_t>(jb.drop.col_off + jb.slot * J + j);
-        if (!drop_keep(rkey, c, jb.drop.p)) g.x = 0.f;
-        if (!drop_keep(rkey, c + 1, jb.drop.p)) g.y = 0.f;
-        if (!drop_keep(rkey, c + 2, jb.drop.p)) g.z = 0.f;
-        if (!drop_keep(rkey, c + 3, jb.drop.p)) g.w = 0.f;
+        const uint32_t c = static_cast<uint32_t>(jb.drop.col_off + jb.slot * J + j);   // multiple of 4
+        const uint32_t thr = drop_threshold(jb.drop.p);
+        const uint32_t w0 = drop_word(rkey, c >> 1), w1 = drop_word(rkey, (c >> 1) + 1);
+        if ((w0 & 0xFFFFu) < thr) g.x = 0.f;
+        if ((w0 >> 16) < thr) g.y = 0.f;
+        if ((w1 & 0xFFFFu) < thr) g.z = 0.f;
+        if ((w1 >> 16) < thr) g.w = 0.f;
       }
       acc.x += w * g.x; acc.y += w * g.y; acc.z += w * g.z; acc.w += w * g.w;
     }

@@ -24,7 +24,7 @@ def dropout_desc(p=0.0, seed=0, stream_id=0, col_off=0):
 def gemm_problem(M, N, passes, a_mn_major=False, b_mn_major=False, alpha=1.0, bias=None, row_flag=None,
                  act=ACT_NONE, post=POST_NONE, post_scale=1.0, drop=None, aux=None, aux_col_off=0,
                  aux_lo_off=0, out=None, out_kind=OUT_F32, out_ld_m=None, out_ld_n=1, out_col_off=0,
-                 out_lo_off=0, accumulate=False):
+                 out_lo_off=0, accumulate=False, split_k=0, split_stride=0):
     """passes: list of (a_operand, a_mn_off, a_k_off, b_operand, b_mn_off, b_k_off, k_len)."""
     g = _ext.GemmProblem()
     g.M, g.N = int(M), int(N)
@@ -50,6 +50,7 @@ def gemm_problem(M, N, passes, a_mn_major=False, b_mn_major=False, alpha=1.0, bi
     e.out_ld_n = int(out_ld_n)
     e.out_col_off, e.out_lo_off = int(out_col_off), int(out_lo_off)
     e.accumulate = int(accumulate)
+    g.split_k, g.split_stride = int(split_k), int(split_stride)
     return g
 
 

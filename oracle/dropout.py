@@ -29,16 +29,19 @@ def row_key(seed, stream_id, rows):
 
 
 def keep_mask(seed, stream_id, rows, cols, p):
-    """Boolean [len(rows), len(cols)] mask: True where element (row, col) is kept."""
+    """Boolean [len(rows), len(cols)] mask: True where element (row, col) is kept.  One 32-bit hash
+    word covers two adjacent columns (16 bits each); an element is dropped iff its lane < p * 65536."""
     rows = np.asarray(rows, dtype=np.int64)
     cols = np.asarray(cols, dtype=np.int64)
     if p <= 0:
         return np.ones((rows.size, cols.size), dtype=bool)
     rk = row_key(seed, stream_id, rows)[:, None]
-    ck = ((_u32(cols) * np.uint64(0x9E3779B1)) + np.uint64(0x632BE5AB)) & _M32
-    h = fmix32(rk ^ ck[None, :])
-    u = (h >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
-    return u >= np.float32(p)
+    pair = _u32(cols >> 1)
+    ck = ((pair * np.uint64(0x9E3779B1)) + np.uint64(0x632BE5AB)) & _M32
+    word = fmix32(rk ^ ck[None, :])
+    lane = (word >> (np.uint64(16) * _u32(cols & 1))[None, :]) & np.uint64(0xFFFF)
+    thr = np.uint64(int(np.float32(p) * np.float32(65536.0) + np.float32(0.5)))
+    return lane >= thr
 
 
 # dropout sites of lirec_model_forward (csrc/model.cu: DS_*)

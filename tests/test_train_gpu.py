@@ -42,25 +42,27 @@ def test_int_rel_ch_train_eval_checkpoint(tmp_path, opt_preset, monkeypatch):
 
 
 def test_torch_adam_and_fused_adam_agree(opt_preset):
-    """Drop-in optimizer (torch.optim.Adam on the flat-buffer parameters) and the fused flat Adam give the
-    same weights after a few steps with identical dropout seeds."""
+    """Drop-in optimizer (torch.optim.Adam on the flat-buffer parameters) and the fused flat Adam take the
+    same step from the same state (the kernels are deterministic, so the gradients are bit-identical)."""
     from lirec_b200.mixed_utils import synthetic
-    import lirec_b200.mlp.model as M
     from helpers import make_model
     pb = synthetic.make_batch(8, seed=4).to_device("cuda")
-    finals = []
+    finals, grads = [], []
     for fused in (0, 1):
         opt_preset("int_rel_ch", fused_adam=fused, lr=1e-3)
         model, loss, optimizer = make_model(seed=3)
         model.train()
-        for step in range(3):
-            lv = loss(model(pb, seed=50 + step), {})
-            optimizer.zero_grad()
-            lv.backward()
-            optimizer.step()
+        lv = loss(model(pb, seed=50), {})
+        optimizer.zero_grad()
+        lv.backward()
+        grads.append({k: p.grad.clone() for k, p in model.named_parameters()})
+        optimizer.step()
         finals.append({k: v.clone() for k, v in model.state_dict().items()})
-    # Adam normalises by sqrt(v): rounding-level gradient differences on near-zero gradients move single
-    # weights by a fraction of one lr-sized step, so compare against the step size (lr = 1e-3, 3 steps)
+        # the bf16 shadow the next forward reads is fresh either way
+        out1 = model(pb, seed=51).ragged_inters.clone()
+        finals[-1]["__next_logits"] = out1
+    for k in grads[0]:
+        assert torch.equal(grads[0][k], grads[1][k]), k
     for k in finals[0]:
-        assert float((finals[0][k] - finals[1][k]).abs().max()) < 1e-4, k
-        assert float((finals[0][k] - finals[1][k]).abs().mean()) < 1e-6, k
+        tol = 1e-4 if k == "__next_logits" else 2e-6      # logits see the bf16 re-rounding of the weights
+        assert float((finals[0][k] - finals[1][k]).abs().max()) < tol, k

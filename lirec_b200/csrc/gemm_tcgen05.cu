@@ -23,6 +23,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -78,6 +79,7 @@ struct DevEpi {
 
 struct DevProblem {
   int32_t M, N;
+  int32_t bn;                  // tile width of this problem (pair kernel: 128 or 256 per CTA pair)
   int32_t tiles_n, tiles_mn;   // tiles per row of tiles / per split slice
   int32_t split_chunk;         // k-blocks per split-K slice (INT_MAX: no split)
   int64_t split_stride;        // elements between the partial outputs of consecutive slices
@@ -209,6 +211,55 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
         "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
+      : "memory");
+}
+
+// ---- CTA-pair (cta_group::2) variants ---------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+// TMA load issued by either CTA of a pair: data lands in the issuing CTA's smem, the byte count is
+// signalled on an mbarrier that may live in the peer (leader) CTA.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map,
+                                                 uint32_t bar_cluster, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+// commit of the leader's outstanding MMAs, arriving on the barrier at this smem offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -580,6 +631,214 @@ lirec_gemm_tcgen05_kernel(const __grid_constant__ GemmParams P) {
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// CTA-pair kernel (cta_group::2): the two SMs of a TPC run ONE 256 x bn tile (bn = 128 or 256 per
+// problem).  Each CTA stages its own 128 rows of A and bn/2 rows of B, so a k-block costs each SM
+// 32 KB of shared-memory fill and 8 KB of operand reads per 256x256x16 MMA — half of what two
+// independent 128x128 tiles need, which is what lets the tensor pipe run near its rate (a 1-CTA
+// 128x128 SS-mode mainloop is bound by the 128 B/clk shared-memory port).
+//   * both CTAs' producers issue their TMA loads; every load signals the LEADER's full barrier;
+//   * the leader's MMA thread issues tcgen05.mma.cta_group::2 and commits (multicast) to the
+//     stage-empty and accumulator-full barriers of both CTAs;
+//   * each CTA's eight epilogue warps drain their own 128 accumulator lanes (rows m0 + 128*rank ..)
+//     and arrive on the leader's accumulator-empty barrier.
+// ---------------------------------------------------------------------------
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+lirec_gemm_tcgen05_pair_kernel(const __grid_constant__ GemmParams P) {
+  constexpr uint32_t A_BYTES = BM * BK * 2;        // 16 KB: this CTA's 128 rows of A
+  constexpr uint32_t B_BYTES_MAX = 128 * BK * 2;   // 16 KB: this CTA's half of a 256-wide B tile
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES_MAX;
+  constexpr uint32_t ACC_COLS = 256;               // accumulator buffer stride in TMEM columns
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                       // used in the leader only
+  uint64_t* empty_bar = bars + STAGES;             // per CTA
+  uint64_t* tfull_bar = bars + 2 * STAGES;         // per CTA
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;    // used in the leader only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == PRODUCER_WARP && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tfull_bar[s]), 1);
+      mbar_init(smem_u32(&tempty_bar[s]), 2 * NUM_EPI_WARPS);  // the epilogue warps of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == PRODUCER_WARP) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int slot = cluster_id; slot < P.num_slots; slot += num_clusters) {
+        const int t = P.use_order ? static_cast<int>(P.tile_order[slot]) : slot;
+        if (t == NO_TILE) continue;
+        int p = 0;
+        while (t >= P.tile_start[p + 1]) ++p;
+        const DevProblem& pr = P.probs[p];
+        const int local = t - P.tile_start[p];
+        const int slice = local / pr.tiles_mn, rem = local - slice * pr.tiles_mn;
+        const int bhalf = pr.bn >> 1;
+        const int m0 = (rem / pr.tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int n0 = (rem % pr.tiles_n) * pr.bn + static_cast<int>(rank) * bhalf;
+        const uint32_t cta_bytes = A_BYTES + static_cast<uint32_t>(bhalf) * (BK * 2);
+        for (int ps = 0; ps < pr.num_passes; ++ps) {
+          const DevPass& pa = pr.pass[ps];
+          const CUtensorMap* amap = &P.maps[pa.a_map];
+          const CUtensorMap* bmap = &P.maps[pa.b_map];
+          const int kb_end = min(pa.k_blocks, (slice + 1) * pr.split_chunk);
+          for (int kb = slice * pr.split_chunk; kb < kb_end; ++kb) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            const uint32_t fb_local = smem_u32(&full_bar[stage]);
+            if (rank == 0) mbar_expect_tx(fb_local, 2 * cta_bytes);   // both CTAs' bytes land here
+            const uint32_t fb = mapa_rank(fb_local, 0);
+            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+            const uint32_t sb = sa + A_BYTES;
+            if (!pr.a_mn_major) {
+              tma_load_2d_pair(sa, amap, fb, pa.a_k_off + kb * BK, pa.a_mn_off + m0);
+            } else {
+#pragma unroll
+              for (int h = 0; h < BM / 64; ++h)
+                tma_load_2d_pair(sa + h * (BK * 128), amap, fb, pa.a_mn_off + m0 + h * 64,
+                                 pa.a_k_off + kb * BK);
+            }
+            if (!pr.b_mn_major) {
+              tma_load_2d_pair(sb, bmap, fb, pa.b_k_off + kb * BK, pa.b_mn_off + n0);
+            } else {
+              for (int h = 0; h < bhalf / 64; ++h)
+                tma_load_2d_pair(sb + h * (BK * 128), bmap, fb, pa.b_mn_off + n0 + h * 64,
+                                 pa.b_k_off + kb * BK);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int slot = cluster_id; slot < P.num_slots; slot += num_clusters) {
+        const int t = P.use_order ? static_cast<int>(P.tile_order[slot]) : slot;
+        if (t == NO_TILE) continue;
+        int p = 0;
+        while (t >= P.tile_start[p + 1]) ++p;
+        const DevProblem& pr = P.probs[p];
+        // instruction descriptor: D=f32, A=B=bf16, majorness, N>>3, M>>4 with M = 256 over the pair
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                               (static_cast<uint32_t>(pr.a_mn_major) << 15) |
+                               (static_cast<uint32_t>(pr.b_mn_major) << 16) |
+                               (static_cast<uint32_t>(pr.bn >> 3) << 17) |
+                               (static_cast<uint32_t>((2 * BM) >> 4) << 24);
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc) * ACC_COLS;
+        uint32_t accumulate = 0;
+        const int slice = (t - P.tile_start[p]) / pr.tiles_mn;
+        for (int ps = 0; ps < pr.num_passes; ++ps) {
+          const int kb_end = min(pr.pass[ps].k_blocks, (slice + 1) * pr.split_chunk);
+          for (int kb = slice * pr.split_chunk; kb < kb_end; ++kb) {
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+            const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adesc = pr.a_mn_major
+                                         ? make_smem_desc(sa + k * (UMMA_K * 128), BK * 128, 1024)
+                                         : make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+              const uint64_t bdesc = pr.b_mn_major
+                                         ? make_smem_desc(sb + k * (UMMA_K * 128), BK * 128, 1024)
+                                         : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+              tc_mma_bf16_pair(tmem_d, adesc, bdesc, idesc, accumulate);
+              accumulate = 1;
+            }
+            tc_commit_pair(smem_u32(&empty_bar[stage]));  // frees the slot in both CTAs
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        tc_commit_pair(smem_u32(&tfull_bar[acc]));  // accumulator complete -> both epilogues
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (0..7), both CTAs =====================
+    const int quarter = warp & 3;
+    const int half = warp >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int slot = cluster_id; slot < P.num_slots; slot += num_clusters) {
+      const int t = P.use_order ? static_cast<int>(P.tile_order[slot]) : slot;
+      if (t == NO_TILE) continue;
+      int p = 0;
+      while (t >= P.tile_start[p + 1]) ++p;
+      const DevProblem& pr = P.probs[p];
+      const int local = t - P.tile_start[p];
+      const int slice = local / pr.tiles_mn, rem = local - slice * pr.tiles_mn;
+      const int m0 = (rem / pr.tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
+      const int n0 = (rem % pr.tiles_n) * pr.bn;
+      const int chunks = pr.bn >> 5;
+      mbar_wait_sleepy(smem_u32(&tfull_bar[acc]), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = half; c < chunks; c += NUM_EPI_WARPS / 4) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               static_cast<uint32_t>(acc) * ACC_COLS + static_cast<uint32_t>(c * 32);
+        tmem_ld_32x32(taddr, r);
+        epilogue_chunk(pr.epi, pr.M, pr.N, m0 + quarter * 32 + lane, n0 + c * 32, r,
+                       static_cast<int64_t>(slice) * pr.split_stride);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[acc]), 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  // neither CTA may leave (or free TMEM) while the pair still reads its smem / signals its barriers
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Host side: tensor maps, problem table, launch
 // ---------------------------------------------------------------------------
@@ -645,7 +904,7 @@ static int g_pending_problems = 0;
 
 // Longest-processing-time-first assignment of tiles to the `grid` persistent CTAs.
 // cost(tile) = k-blocks of its problem + a constant for the epilogue (in k-block units).
-static void schedule_tiles(GemmParams& P, int grid, int bn) {
+static void schedule_tiles(GemmParams& P, int grid) {
   P.use_order = 0;
   P.num_slots = P.total_tiles;
   if (P.total_tiles > MAX_ORDERED_TILES || P.total_tiles >= NO_TILE || grid <= 0) return;
@@ -660,7 +919,7 @@ static void schedule_tiles(GemmParams& P, int grid, int bn) {
       kb += std::min(P.probs[p].pass[ps].k_blocks, P.probs[p].split_chunk);
     const DevEpi& e = P.probs[p].epi;
     const int epi = (e.act == LIREC_ACT_TANH || e.post != LIREC_POST_NONE) ? 10 : (e.out_kind == LIREC_OUT_F32 ? 4 : 6);
-    const int cost = kb + epi * bn / 128;
+    const int cost = kb + epi * P.probs[p].bn / 128;
     if (first_cost < 0) first_cost = cost;
     uniform = uniform && (cost == first_cost);
     for (int t = P.tile_start[p]; t < P.tile_start[p + 1]; ++t) tiles.push_back(T{cost, t});
@@ -691,6 +950,24 @@ static void schedule_tiles(GemmParams& P, int grid, int bn) {
   P.use_order = 1;
 }
 
+static int record_begin(ProfRec& rec, const GemmParams& P, cudaStream_t stream) {
+  if (!g_prof_on) return LIREC_OK;
+  if (!g_prof_pool.empty()) { rec = g_prof_pool.back(); g_prof_pool.pop_back(); }
+  else {
+    LIREC_CUDA_OK(cudaEventCreate(&rec.e0));
+    LIREC_CUDA_OK(cudaEventCreate(&rec.e1));
+  }
+  rec.flops = g_pending_flops; rec.tiles = P.total_tiles; rec.problems = g_pending_problems;
+  LIREC_CUDA_OK(cudaEventRecord(rec.e0, stream));
+  return LIREC_OK;
+}
+static int record_end(ProfRec& rec, cudaStream_t stream) {
+  if (!g_prof_on) return LIREC_OK;
+  LIREC_CUDA_OK(cudaEventRecord(rec.e1, stream));
+  g_prof.push_back(rec);
+  return LIREC_OK;
+}
+
 template <int BN, int STAGES>
 static int launch(const GemmParams& P, cudaStream_t stream) {
   constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/;
@@ -706,31 +983,71 @@ static int launch(const GemmParams& P, cudaStream_t stream) {
     configured = true;
   }
   const int grid = std::min(P.total_tiles, num_sms);
-  schedule_tiles(const_cast<GemmParams&>(P), grid, BN);
+  schedule_tiles(const_cast<GemmParams&>(P), grid);
   ProfRec rec{};
-  if (g_prof_on) {
-    if (!g_prof_pool.empty()) { rec = g_prof_pool.back(); g_prof_pool.pop_back(); }
-    else {
-      LIREC_CUDA_OK(cudaEventCreate(&rec.e0));
-      LIREC_CUDA_OK(cudaEventCreate(&rec.e1));
-    }
-    rec.flops = g_pending_flops; rec.tiles = P.total_tiles; rec.problems = g_pending_problems;
-    LIREC_CUDA_OK(cudaEventRecord(rec.e0, stream));
-  }
+  int rc = record_begin(rec, P, stream);
+  if (rc != LIREC_OK) return rc;
   lirec_gemm_tcgen05_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, stream>>>(P);
   LIREC_CUDA_OK(cudaGetLastError());
-  if (g_prof_on) {
-    LIREC_CUDA_OK(cudaEventRecord(rec.e1, stream));
-    g_prof.push_back(rec);
-  }
+  if ((rc = record_end(rec, stream)) != LIREC_OK) return rc;
   note_launch();
   return LIREC_OK;
+}
+
+// CTA-pair launch: one cluster of two CTAs per TPC, persistent over the pair tiles.
+template <int STAGES>
+static int launch_pair(const GemmParams& P, cudaStream_t stream) {
+  constexpr size_t smem = STAGES * (BM * BK * 2 + 128 * BK * 2) + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(smem <= 232448, "shared memory budget");
+  static bool configured = false;
+  static int max_clusters = 0;
+  if (!configured) {
+    LIREC_CUDA_OK(cudaFuncSetAttribute(lirec_gemm_tcgen05_pair_kernel<STAGES>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, num_sms = 0;
+    LIREC_CUDA_OK(cudaGetDevice(&dev));
+    LIREC_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    max_clusters = num_sms / 2;
+    // the hardware may not be able to co-schedule a pair on every TPC (e.g. a GPC with an odd SM count)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms / 2 * 2);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    int active = 0;
+    if (cudaOccupancyMaxActiveClusters(&active, lirec_gemm_tcgen05_pair_kernel<STAGES>, &cfg) == cudaSuccess &&
+        active > 0)
+      max_clusters = std::min(max_clusters, active);
+    else
+      (void)cudaGetLastError();
+    configured = true;
+  }
+  const int clusters = std::min(P.total_tiles, max_clusters);
+  schedule_tiles(const_cast<GemmParams&>(P), clusters);
+  ProfRec rec{};
+  int rc = record_begin(rec, P, stream);
+  if (rc != LIREC_OK) return rc;
+  lirec_gemm_tcgen05_pair_kernel<STAGES><<<2 * clusters, NUM_THREADS, smem, stream>>>(P);
+  LIREC_CUDA_OK(cudaGetLastError());
+  if ((rc = record_end(rec, stream)) != LIREC_OK) return rc;
+  note_launch();
+  return LIREC_OK;
+}
+
+// LIREC_GEMM_PAIR=0 selects the single-CTA 128x128 kernel (kept for A/B measurements).
+static bool use_pair_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LIREC_GEMM_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 int run_grouped(const lirec_gemm_problem* probs, int nprobs, cudaStream_t stream) {
   LIREC_REQUIRE(nprobs >= 0 && nprobs <= MAX_PROBLEMS, "too many GEMM problems (%d > %d)", nprobs,
                 MAX_PROBLEMS);
-  constexpr int BN = 128;
+  const bool pair = use_pair_kernel();
+  const int tile_m = pair ? 2 * BM : BM;
   static thread_local GemmParams P;  // 16 KB: keep it off the stack
   std::vector<MapKey> keys;
   keys.reserve(MAX_MAPS);
@@ -763,8 +1080,11 @@ int run_grouped(const lirec_gemm_problem* probs, int nprobs, cudaStream_t stream
     DevProblem& d = P.probs[np];
     d.M = g.M;
     d.N = g.N;
-    const int tiles_m = (g.M + BM - 1) / BM;
-    d.tiles_n = (g.N + BN - 1) / BN;
+    // pair kernel: 256 x 256 tiles, 256 x 128 for narrow outputs (heads, bias gradients)
+    d.bn = pair ? (g.N > 128 ? 256 : 128) : 128;
+    const int b_box = pair ? d.bn / 2 : d.bn;       // B rows one CTA stages per k-block
+    const int tiles_m = (g.M + tile_m - 1) / tile_m;
+    d.tiles_n = (g.N + d.bn - 1) / d.bn;
     d.tiles_mn = tiles_m * d.tiles_n;
     int max_kb = 0;
     for (int ps = 0; ps < g.num_passes; ++ps) max_kb = std::max(max_kb, (g.pass[ps].k_len + BK - 1) / BK);
@@ -780,7 +1100,7 @@ int run_grouped(const lirec_gemm_problem* probs, int nprobs, cudaStream_t stream
       const lirec_gemm_pass& s = g.pass[ps];
       LIREC_REQUIRE(s.k_len > 0, "problem %d pass %d: k_len=%d", idx, ps, s.k_len);
       const int ia = map_index(s.a, d.a_mn_major, BM);
-      const int ib = map_index(s.b, d.b_mn_major, BN);
+      const int ib = map_index(s.b, d.b_mn_major, b_box);
       if (ia < 0 || ib < 0) return fail(LIREC_ERR_LIMIT, "more than %d tensor maps in one launch", MAX_MAPS);
       d.pass[ps] = DevPass{(int16_t)ia, (int16_t)ib, s.a_mn_off, s.a_k_off, s.b_mn_off, s.b_k_off,
                            (s.k_len + BK - 1) / BK};
@@ -845,7 +1165,7 @@ int run_grouped(const lirec_gemm_problem* probs, int nprobs, cudaStream_t stream
     int rc = encode_map(&P.maps[i], keys[i]);
     if (rc != LIREC_OK) return rc;
   }
-  return launch<BN, 6>(P, stream);
+  return pair ? launch_pair<6>(P, stream) : launch<128, 6>(P, stream);
 }
 
 }  // namespace gemm

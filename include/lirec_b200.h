@@ -95,7 +95,11 @@ enum lirec_post {
   LIREC_POST_DRELU = 2,   /* v *= post_scale * [aux_hi(m,n) > 0]             */
   LIREC_POST_DTANH = 3    /* v *= keep(m,n)/(1-p) * (1 - ((aux_hi+aux_lo)*(1-p))^2) */
 };
-enum lirec_out { LIREC_OUT_F32 = 0, LIREC_OUT_SPLIT_BF16 = 1 };
+enum lirec_out {
+  LIREC_OUT_F32 = 0,
+  LIREC_OUT_SPLIT_BF16 = 1,   /* hi at out[m*ld_m + col_off + n], lo at + lo_off                     */
+  LIREC_OUT_SPLIT_BF16_T = 2  /* transposed: hi at out[(col_off + n)*ld_m + m], lo at row + lo_off   */
+};
 
 typedef struct lirec_epilogue {
   float alpha;
@@ -110,7 +114,7 @@ typedef struct lirec_epilogue {
   int32_t aux_col_off, aux_lo_off;
   int32_t out_kind;         /* lirec_out                                     */
   void* out;
-  int64_t out_ld_m, out_ld_n; /* F32: &out[m*ld_m + n*ld_n]; SPLIT: ld_m only */
+  int64_t out_ld_m, out_ld_n; /* F32: &out[m*ld_m + n*ld_n]; SPLIT / SPLIT_T: ld_m only (row pitch) */
   int32_t out_col_off;      /* SPLIT: hi at col_off+n, lo at col_off+lo_off+n */
   int32_t out_lo_off;
   int32_t accumulate;       /* F32 only: out += v                            */
@@ -181,11 +185,14 @@ int lirec_rows_expand_fwd(const float* r1_txt, const float* r1_vis, const float*
  * owner : NULL (ints) or [n_rows] candidate index of each context row;
  * seg_off: NULL or [n_out+1] (context) to derive 1/n.
  * slot : 0 txt, 1 vis, 2 tr1, 3 tr2 (selects the dropout columns).
- * Writes dZ1 = [r1 > 0] * sum(...) as a hi/lo split [n_unique, 2*J].          */
+ * Writes dZ1 = [r1 > 0] * sum(...) as a hi/lo split [n_unique, 2*J] (out_t_pitch == 0),
+ * or TRANSPOSED as [2*J, out_t_pitch] (hi rows [0,J), lo rows [J,2J); out_t_pitch >=
+ * n_unique, a multiple of 8) — the K-major operand of the first-layer wgrad GEMM.   */
 int lirec_rows_expand_bwd(const float* d_in, int64_t d_ld, const float* r1, int32_t J,
                           int32_t slot, const int32_t* inv_off, const int32_t* inv_idx,
                           int32_t n_unique, const int32_t* owner, const int32_t* seg_off,
-                          lirec_dropout drop, void* out_split, int64_t out_ld, void* stream);
+                          lirec_dropout drop, void* out_split, int64_t out_ld,
+                          int64_t out_t_pitch, void* stream);
 
 /* fp32 [rows, cols] -> hi/lo bf16 split [rows, 2*pad_cols] (zero padded). */
 int lirec_split_f32(const float* x, int64_t ld, int32_t rows, int32_t cols, void* out_split,

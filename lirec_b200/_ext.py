@@ -17,7 +17,7 @@ MAX_PROBLEMS = 32
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 POST_NONE, POST_DROPOUT, POST_DRELU, POST_DTANH = 0, 1, 2, 3
-OUT_F32, OUT_SPLIT = 0, 1
+OUT_F32, OUT_SPLIT, OUT_SPLIT_T = 0, 1, 2
 
 
 class Dropout(C.Structure):
@@ -123,7 +123,7 @@ def lib():
                                                            C.c_void_p, C.c_void_p]
     L.lirec_rows_expand_bwd.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
                                         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
-                                        Dropout, C.c_void_p, C.c_int64, C.c_void_p]
+                                        Dropout, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     L.lirec_split_f32.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
                                   C.c_int32, C.c_void_p]
     L.lirec_cast_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]

@@ -404,6 +404,21 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpi& e, int M, int N, in
         }
       }
     }
+  } else if (e.out_kind == LIREC_OUT_SPLIT_BF16_T) {
+    // transposed hi/lo split: element (m, n) -> out[(col_off + n) * ld + m].  The 32 lanes of a warp
+    // hold 32 consecutive m, so every store instruction writes 64 contiguous bytes.
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) +
+                       static_cast<int64_t>(e.out_col_off + n0) * e.out_ld_m + m;
+    const int64_t lo_off = static_cast<int64_t>(e.out_lo_off) * e.out_ld_m;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < nvalid) {
+        __nv_bfloat16 h, l;
+        split_bf16(v[j], h, l);
+        o[static_cast<int64_t>(j) * e.out_ld_m] = h;
+        o[static_cast<int64_t>(j) * e.out_ld_m + lo_off] = l;
+      }
+    }
   } else {  // hi/lo bf16 split
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) +
                        static_cast<int64_t>(m) * e.out_ld_m + e.out_col_off + n0;
@@ -1090,6 +1105,9 @@ int run_grouped(const lirec_gemm_problem* probs, int nprobs, cudaStream_t stream
     for (int ps = 0; ps < g.num_passes; ++ps) max_kb = std::max(max_kb, (g.pass[ps].k_len + BK - 1) / BK);
     int split = std::max(1, std::min(g.split_k, max_kb));
     LIREC_REQUIRE(split == 1 || g.epi.out_kind == LIREC_OUT_F32, "problem %d: split-K needs an fp32 output", idx);
+    LIREC_REQUIRE(g.epi.out_kind == LIREC_OUT_F32 || g.epi.out_kind == LIREC_OUT_SPLIT_BF16 ||
+                      g.epi.out_kind == LIREC_OUT_SPLIT_BF16_T,
+                  "problem %d: out_kind=%d", idx, g.epi.out_kind);
     d.split_chunk = (split > 1) ? (max_kb + split - 1) / split : 0x3fffffff;
     if (split > 1) split = (max_kb + d.split_chunk - 1) / d.split_chunk;   // every slice non-empty
     d.split_stride = g.split_stride;
@@ -1134,6 +1152,8 @@ int run_grouped(const lirec_gemm_problem* probs, int nprobs, cudaStream_t stream
     const uintptr_t ob = reinterpret_cast<uintptr_t>(e.out);
     if (e.out_kind == LIREC_OUT_F32)
       de.vec_ok = (e.out_ld_n == 1 && (ob & 15) == 0 && (e.out_ld_m % 4) == 0) ? 1 : 0;
+    else if (e.out_kind == LIREC_OUT_SPLIT_BF16_T)
+      de.vec_ok = 0;
     else
       de.vec_ok = ((ob & 15) == 0 && (e.out_ld_m % 8) == 0 && (e.out_col_off % 8) == 0 &&
                    (e.out_lo_off % 8) == 0)

@@ -39,6 +39,7 @@ struct Dims {
   int Ni, Nx, nc, nci, nt, nti;
   int cs[4], outw[4], inw[4];
   int ones_rows;
+  int NiP, ncP[2], ntP[2], onesP;   // row pitches of the transposed gradient buffers (multiples of 64)
   bool ctx, gates;
 };
 
@@ -63,6 +64,10 @@ static Dims make_dims(const lirec_model_cfg& c, const lirec_batch& b) {
   d.ctx = c.ctx != 0;
   d.gates = c.gates != 0;
   d.ones_rows = std::max(std::max(d.Ni, d.nc), d.nt);
+  d.NiP = (int)round_up(d.Ni, 64);
+  d.ncP[0] = (int)round_up(d.nci, 64); d.ncP[1] = (int)round_up(d.nc, 64);
+  d.ntP[0] = (int)round_up(d.nti, 64); d.ntP[1] = (int)round_up(d.nt, 64);
+  d.onesP = (int)round_up(d.ones_rows, 64);
   return d;
 }
 
@@ -70,17 +75,25 @@ struct Workspace {
   float* r1[2][4];    // relu(L1) of the unique rows, per branch and slot
   bf16* a2[2];        // expanded / pooled layer-2 inputs  [Ni, 8J]
   int32_t* flag_c;    // [Ni] context segment non-empty
-  bf16* flag_bf16;    // [Ni, 64]
-  bf16* ones;         // [ones_rows, 64]
+  bf16* flagT;        // [1, NiP] the same flag as the K-major operand of the bias-gradient GEMMs
+  bf16* onesT;        // [1, onesP] ones
   bf16* f2[2];        // dropout(tanh(concat)) hi|lo       [Ni, 6J]
   bf16* g2;           // gate output hi|lo                  [Ni, 2Gd]
-  // backward temporaries
-  bf16* dli2;         // [Ni, 2CP]
-  bf16* dlr2;         // [Ni, 2RP]
-  bf16* dpreg2;       // [Ni, 2Gd]
-  bf16* dz2[2];       // [Ni, 6J]
+  // Backward temporaries.  Every activation gradient is kept TRANSPOSED ([feature, row], hi rows then
+  // lo rows, row pitch NiP / nuP): it is the K-major B operand of the weight-gradient GEMM that reduces
+  // over the batch rows and the MN-major A operand of the next data-gradient GEMM — the two operand
+  // forms the CTA-pair tcgen05 kernel runs at full rate (an MN-major B operand does not).
+  bf16* dliT;         // [2CP, NiP]
+  bf16* dlrT;         // [2RP, NiP]
+  bf16* dpregT;       // [2Gd, NiP]
+  bf16* dz2T[2];      // [6J, NiP]
   float* da2[2];      // [Ni, 4J]
-  bf16* dz1[2][4];    // [n_unique, 2J]
+  bf16* dz1T[2][4];   // [2J, nuP]
+  // [in, out] copies of the weights the data-gradient GEMMs multiply by (K-major B operands)
+  bf16* out_intsT;    // [Gd or 3J, CP]
+  bf16* out_ctxT;     // [3J, RP]
+  bf16* gateT;        // [6J, Gd]
+  bf16* l2T[2][4];    // [J, outw]
   float* pool;        // split-K partial gradients
   size_t pool_floats;
   size_t bytes;
@@ -92,17 +105,19 @@ struct Workspace {
 // problem is cut into S row ranges that write partial results into a pool; one small kernel sums
 // the partials into the flat gradient buffer at the end of backward, in a fixed order
 // (deterministic, no atomics).
-static int split_factor(int M, int N, int passes, int rows) {
-  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+static int split_factor(int out_f, int in_f, int passes, int rows) {
+  // tiles of the (M = in_f, N = out_f) pair-kernel problem: 256 x (256 | 128)
+  const int bn = out_f > 128 ? 256 : 128;
+  const int tiles = ((in_f + 255) / 256) * ((out_f + bn - 1) / bn);
   const int kb = passes * ((rows + 63) / 64);
-  if (tiles > 32 || kb < 128) return 1;
-  return std::max(1, std::min(8, kb / 64));
+  if (tiles >= 64 || kb < 128) return 1;
+  return std::max(1, std::min(std::min(8, kb / 64), (148 + tiles - 1) / tiles));
 }
 static size_t split_pool_floats(const Dims& d) {
   size_t n = 0;
-  auto add = [&](int M, int N, int passes, int rows) {
-    const int S = split_factor(M, N, passes, rows);
-    if (S > 1) n += (size_t)S * M * N;
+  auto add = [&](int out_f, int in_f, int passes, int rows) {
+    const int S = split_factor(out_f, in_f, passes, rows);
+    if (S > 1) n += (size_t)S * out_f * in_f;
   };
   const int hw = d.gates ? d.Gd : d.F;
   add(d.C, hw, 3, d.Ni); add(d.C, 1, 2, d.Ni);
@@ -131,29 +146,35 @@ static Workspace carve(const Dims& d, void* base) {
   for (int br = 0; br < 2; ++br)
     for (int s = 0; s < 4; ++s) {
       w.r1[br][s] = nullptr;
-      w.dz1[br][s] = nullptr;
+      w.dz1T[br][s] = nullptr;
+      w.l2T[br][s] = nullptr;
     }
-  w.a2[1] = w.f2[1] = w.dz2[1] = nullptr;
+  w.a2[1] = w.f2[1] = w.dz2T[1] = nullptr;
   w.da2[1] = nullptr;
   for (int br = 0; br < nbr; ++br) {
     const int ncl = br ? d.nc : d.nci, ntr = br ? d.nt : d.nti;
     for (int s = 0; s < 4; ++s) {
       const int nu = (s < 2) ? ncl : ntr;
+      const int nuP = (s < 2) ? d.ncP[br] : d.ntP[br];
       w.r1[br][s] = static_cast<float*>(take((size_t)nu * d.J * 4));
-      w.dz1[br][s] = static_cast<bf16*>(take((size_t)nu * 2 * d.J * 2));
+      w.dz1T[br][s] = static_cast<bf16*>(take((size_t)2 * d.J * nuP * 2));
+      w.l2T[br][s] = static_cast<bf16*>(take((size_t)d.J * d.outw[s] * 2));
     }
     w.a2[br] = static_cast<bf16*>(take((size_t)d.Ni * 8 * d.J * 2));
     w.f2[br] = static_cast<bf16*>(take((size_t)d.Ni * 2 * d.F * 2));
-    w.dz2[br] = static_cast<bf16*>(take((size_t)d.Ni * 2 * d.F * 2));
+    w.dz2T[br] = static_cast<bf16*>(take((size_t)2 * d.F * d.NiP * 2));
     w.da2[br] = static_cast<float*>(take((size_t)d.Ni * 4 * d.J * 4));
   }
   w.flag_c = static_cast<int32_t*>(take((size_t)d.Ni * 4));
-  w.flag_bf16 = static_cast<bf16*>(take((size_t)d.Ni * 64 * 2));
-  w.ones = static_cast<bf16*>(take((size_t)d.ones_rows * 64 * 2));
+  w.flagT = static_cast<bf16*>(take((size_t)d.NiP * 2));
+  w.onesT = static_cast<bf16*>(take((size_t)d.onesP * 2));
   w.g2 = static_cast<bf16*>(take((size_t)d.Ni * 2 * d.Gd * 2));
-  w.dpreg2 = static_cast<bf16*>(take((size_t)d.Ni * 2 * d.Gd * 2));
-  w.dli2 = static_cast<bf16*>(take((size_t)d.Ni * 2 * d.CP * 2));
-  w.dlr2 = static_cast<bf16*>(take((size_t)d.Ni * 2 * d.RP * 2));
+  w.dpregT = static_cast<bf16*>(take((size_t)2 * d.Gd * d.NiP * 2));
+  w.dliT = static_cast<bf16*>(take((size_t)2 * d.CP * d.NiP * 2));
+  w.dlrT = static_cast<bf16*>(take((size_t)2 * d.RP * d.NiP * 2));
+  w.out_intsT = static_cast<bf16*>(take((size_t)(d.gates ? d.Gd : d.F) * d.CP * 2));
+  w.out_ctxT = static_cast<bf16*>(take((size_t)d.F * d.RP * 2));
+  w.gateT = static_cast<bf16*>(take((size_t)2 * d.F * d.Gd * 2));
   w.pool_floats = split_pool_floats(d);
   w.pool = static_cast<float*>(take(w.pool_floats * 4));
   w.bytes = off;
@@ -271,8 +292,8 @@ int forward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lirec
   int rc;
 
   {  // ones column for the bias-gradient GEMMs
-    const int64_t n = (int64_t)d.ones_rows * 64;
-    fill_bf16_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, stream>>>(w.ones, n, 1.0f);
+    const int64_t n = d.onesP;
+    fill_bf16_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, stream>>>(w.onesT, n, 1.0f);
     LIREC_CUDA_OK(cudaGetLastError());
     note_launch();
   }
@@ -315,7 +336,7 @@ int forward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lirec
       j.out = w.a2[br];
       j.out_ld = 8 * J;
       j.row_flag_out = br ? w.flag_c : nullptr;
-      j.flag_bf16_out = br ? w.flag_bf16 : nullptr;
+      j.flag_bf16_out = br ? w.flagT : nullptr;
     }
     if ((rc = rows::expand_fwd(jobs, stream)) != LIREC_OK) return rc;
   }
@@ -390,50 +411,74 @@ int forward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lirec
 }
 
 // ---------------------------------------------------------------------------
-// wgrad helper: dW[M=out, N=in] = alpha * dY^T X with dY, X hi/lo split tensors read
-// MN-major (rows = reduction).  x_lo_off < 0: X is exact bf16 (no lo part).
-static lirec_gemm_problem wgrad(int out_f, int in_f, const bf16* dy, int64_t dy_cols, int dy_hi, int dy_lo,
-                                const bf16* x, int64_t x_cols, int64_t x_ld, int x_hi, int x_lo, int rows,
-                                float alpha, float* grad, int64_t grad_ld) {
-  lirec_gemm_problem g = mk_problem(out_f, in_f, true, true);
-  const lirec_operand a = op(dy, rows, dy_cols, dy_cols);
-  const lirec_operand b = op(x, rows, x_cols, x_ld);
-  add_pass(g, mk_pass(a, dy_hi, 0, b, x_hi, 0, rows));
-  if (x_lo >= 0) add_pass(g, mk_pass(a, dy_hi, 0, b, x_lo, 0, rows));
-  add_pass(g, mk_pass(a, dy_lo, 0, b, x_hi, 0, rows));
+// Backward GEMM builders.  TGrad = a transposed hi/lo gradient tensor: rows [hi, hi + n) hold the hi
+// parts of n features, rows [lo, lo + n) the lo parts, every row is `rows` batch rows long.
+struct TGrad {
+  const bf16* ptr;
+  int buf_rows;      // rows of the whole buffer (for the tensor map)
+  int64_t pitch;
+  int hi, lo;
+};
+
+// Weight gradient dW[out_f, in_f] = alpha * dY^T X, run as D'[in_f, out_f] = X^T dY:
+//   A = X  [rows, x_cols] natural, read MN-major (x_lo < 0: exact bf16, no lo part)
+//   B = dY^T (TGrad) K-major
+// and stored transposed into dW (lanes run along in_f, so the fp32 stores stay coalesced).
+static lirec_gemm_problem wgrad_t(int out_f, int in_f, const TGrad& dy, const bf16* x, int64_t x_cols, int64_t x_ld,
+                                  int x_hi, int x_lo, int rows, float alpha, float* grad, int64_t grad_ld) {
+  lirec_gemm_problem g = mk_problem(in_f, out_f, true, false);
+  const lirec_operand a = op(x, rows, x_cols, x_ld);
+  const lirec_operand b = op(dy.ptr, dy.buf_rows, rows, dy.pitch);
+  add_pass(g, mk_pass(a, x_hi, 0, b, dy.hi, 0, rows));
+  if (x_lo >= 0) add_pass(g, mk_pass(a, x_lo, 0, b, dy.hi, 0, rows));
+  add_pass(g, mk_pass(a, x_hi, 0, b, dy.lo, 0, rows));
   g.epi.alpha = alpha;
-  out_f32(g, grad, grad_ld);
+  out_f32(g, grad, 1, grad_ld);
   return g;
 }
-// bias gradient: db[M=out] = dY^T v, v = ones or a 0/1 row-flag column
-static lirec_gemm_problem bgrad(int out_f, const bf16* dy, int64_t dy_cols, int dy_hi, int dy_lo,
-                                const bf16* v, int rows, float* grad) {
-  lirec_gemm_problem g = mk_problem(out_f, 1, true, true);
-  const lirec_operand a = op(dy, rows, dy_cols, dy_cols);
-  const lirec_operand b = op(v, rows, 64, 64);
-  add_pass(g, mk_pass(a, dy_hi, 0, b, 0, 0, rows));
-  add_pass(g, mk_pass(a, dy_lo, 0, b, 0, 0, rows));
+// bias gradient db[out_f] = dY^T v with v = ones or the 0/1 row flags, both [1, rows] K-major
+static lirec_gemm_problem bgrad_t(int out_f, const TGrad& dy, const bf16* v, int rows, float* grad) {
+  lirec_gemm_problem g = mk_problem(out_f, 1, false, false);
+  const lirec_operand a = op(dy.ptr, dy.buf_rows, rows, dy.pitch);
+  const lirec_operand b = op(v, 1, rows, round_up(rows, 64));
+  add_pass(g, mk_pass(a, dy.hi, 0, b, 0, 0, rows));
+  add_pass(g, mk_pass(a, dy.lo, 0, b, 0, 0, rows));
   out_f32(g, grad, 1);
   return g;
 }
+// data-gradient passes dX[rows, in_f] += dY W: A = dY^T (TGrad) read MN-major, B = W^T [in_f.., out_p] K-major
+static void add_dgrad_passes(lirec_gemm_problem& g, const TGrad& dy, int rows, const bf16* wT, int wT_rows,
+                             int out_p, int w_row_off, int k_len) {
+  const lirec_operand a = op(dy.ptr, dy.buf_rows, rows, dy.pitch);
+  const lirec_operand b = op(wT, wT_rows, out_p, out_p);
+  add_pass(g, mk_pass(a, 0, dy.hi, b, w_row_off, 0, k_len));
+  add_pass(g, mk_pass(a, 0, dy.lo, b, w_row_off, 0, k_len));
+}
+static void out_split_t(lirec_gemm_problem& g, bf16* out, int64_t pitch, int row_off, int lo_off) {
+  g.epi.out_kind = LIREC_OUT_SPLIT_BF16_T;
+  g.epi.out = out; g.epi.out_ld_m = pitch; g.epi.out_col_off = row_off; g.epi.out_lo_off = lo_off;
+}
 
-// Push a reduction-over-rows problem (all passes have k_len == rows), split-K if that helps.
-static void push_reduction(std::vector<lirec_gemm_problem>& pr, lirec_gemm_problem g, int rows, SplitCtx& sc) {
-  const int S = split_factor(g.M, g.N, g.num_passes, rows);
-  const size_t need = (size_t)S * g.M * g.N;
+// Push a reduction-over-rows problem producing a [out_f, in_f] parameter gradient, split-K if that helps.
+// The problem stores element (o, i) at out[o * ld + i] through (out_ld_m, out_ld_n); the pool slices use
+// the same indexing with ld = in_f.
+static void push_reduction(std::vector<lirec_gemm_problem>& pr, lirec_gemm_problem g, int out_f, int in_f, int rows,
+                           bool transposed, SplitCtx& sc) {
+  const int S = split_factor(out_f, in_f, g.num_passes, rows);
+  const size_t need = (size_t)S * out_f * in_f;
   if (S > 1 && sc.used + need <= sc.pool_floats && sc.jobs.n < MAX_REDUCE_JOBS) {
     ReduceJob& j = sc.jobs.job[sc.jobs.n++];
     j.dst = static_cast<float*>(g.epi.out);
-    j.dst_ld = g.epi.out_ld_m;
+    j.dst_ld = transposed ? g.epi.out_ld_n : g.epi.out_ld_m;
     j.src = sc.pool + sc.used;
-    j.M = g.M; j.N = g.N;
+    j.M = out_f; j.N = in_f;
     const int kb = (rows + 63) / 64, chunk = (kb + S - 1) / S;
     j.S = (kb + chunk - 1) / chunk;                       // the slice count the GEMM will actually use
     g.split_k = S;
-    g.split_stride = (int64_t)g.M * g.N;
+    g.split_stride = (int64_t)out_f * in_f;
     g.epi.out = sc.pool + sc.used;
-    g.epi.out_ld_m = g.N;
-    g.epi.out_ld_n = 1;
+    if (transposed) { g.epi.out_ld_m = 1; g.epi.out_ld_n = in_f; }
+    else { g.epi.out_ld_m = in_f; g.epi.out_ld_n = 1; }
     sc.used += need;
   }
   pr.push_back(g);
@@ -446,7 +491,7 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
   const float p = (B.training && cfg.dropout_p > 0.f) ? cfg.dropout_p : 0.f;
   const float keep_scale = 1.0f / (1.0f - p);
   const int nbr = d.ctx ? 2 : 1;
-  const int J = d.J, F = d.F, Ni = d.Ni, Gd = d.Gd, CP = d.CP, RP = d.RP;
+  const int J = d.J, F = d.F, Ni = d.Ni, Gd = d.Gd, CP = d.CP, RP = d.RP, NiP = d.NiP;
   int rc;
   LIREC_REQUIRE(d_ints != nullptr && (!d.ctx || d_rels != nullptr), "model backward: null logit gradient");
   for (int s = 0; s < 3; ++s) {
@@ -454,52 +499,68 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
     LIREC_REQUIRE(!d.ctx || (B.inv_ctx_off[s] && (d.Nx == 0 || B.inv_ctx_idx[s])),
                   "model backward: inverse context tables missing");
   }
+  const int hw = d.gates ? Gd : F;                 // width of the interaction head's input
+  const bf16* hx = d.gates ? w.g2 : w.f2[0];
+
+  // ---- [in, out] copies of the weights the data gradients multiply by ---------------------------
+  {
+    rows::TransposeJobs tj;
+    tj.n = 0;
+    auto add = [&](const void* src, int out_f, int in_f, bf16* dst, int out_p) {
+      rows::TransposeJob& j = tj.job[tj.n++];
+      j.src = static_cast<const bf16*>(src); j.src_ld = in_f; j.R = out_f; j.C = in_f;
+      j.dst = dst; j.dst_ld = out_p; j.Rp = out_p;
+    };
+    add(P.out_ints.w_bf16, d.C, hw, w.out_intsT, CP);
+    if (d.ctx) add(P.out_ctx.w_bf16, d.R, F, w.out_ctxT, RP);
+    if (d.gates) add(P.gate.w_bf16, Gd, 2 * F, w.gateT, Gd);
+    for (int br = 0; br < nbr; ++br)
+      for (int s = 0; s < 4; ++s)
+        add((br ? P.enc_ctx : P.enc_ints).l2[s].w_bf16, d.outw[s], J, w.l2T[br][s], d.outw[s]);
+    if ((rc = rows::transpose_bf16(tj, stream)) != LIREC_OK) return rc;
+  }
 
   SplitCtx sc;
   sc.pool = w.pool; sc.pool_floats = w.pool_floats; sc.used = 0; sc.jobs.n = 0;
-  if ((rc = rows::split_f32(d_ints, d.C, Ni, d.C, w.dli2, 2 * CP, CP, stream)) != LIREC_OK) return rc;
-  if (d.ctx && (rc = rows::split_f32(d_rels, d.R, Ni, d.R, w.dlr2, 2 * RP, RP, stream)) != LIREC_OK) return rc;
-
-  const int hw = d.gates ? Gd : F;                 // width of the interaction head's input
-  const bf16* hx = d.gates ? w.g2 : w.f2[0];
-  const lirec_operand dli_k = op(w.dli2, Ni, 2 * CP, 2 * CP);
-  const lirec_operand dlr_k = op(w.dlr2, Ni, 2 * RP, 2 * RP);
+  if ((rc = rows::split_f32_t(d_ints, d.C, Ni, d.C, w.dliT, NiP, CP, stream)) != LIREC_OK) return rc;
+  if (d.ctx && (rc = rows::split_f32_t(d_rels, d.R, Ni, d.R, w.dlrT, NiP, RP, stream)) != LIREC_OK) return rc;
+  const TGrad dli{w.dliT, 2 * CP, NiP, 0, CP};
+  const TGrad dlr{w.dlrT, 2 * RP, NiP, 0, RP};
+  const TGrad dpg{w.dpregT, 2 * Gd, NiP, 0, Gd};
 
   // ---- stage H: head wgrad/bgrad + dgrad through the head --------------------
   std::vector<lirec_gemm_problem> pr;
-  push_reduction(pr, wgrad(d.C, hw, w.dli2, 2 * CP, 0, CP, hx, 2 * hw, 2 * hw, 0, hw, Ni, 1.f, P.out_ints.grad_w, hw), Ni, sc);
-  push_reduction(pr, bgrad(d.C, w.dli2, 2 * CP, 0, CP, w.ones, Ni, P.out_ints.grad_b), Ni, sc);
+  push_reduction(pr, wgrad_t(d.C, hw, dli, hx, 2 * hw, 2 * hw, 0, hw, Ni, 1.f, P.out_ints.grad_w, hw), d.C, hw, Ni,
+                 true, sc);
+  push_reduction(pr, bgrad_t(d.C, dli, w.onesT, Ni, P.out_ints.grad_b), d.C, 1, Ni, false, sc);
   if (d.ctx) {
-    push_reduction(pr, wgrad(d.R, F, w.dlr2, 2 * RP, 0, RP, w.f2[1], 2 * F, 2 * F, 0, F, Ni, 1.f, P.out_ctx.grad_w, F), Ni, sc);
-    push_reduction(pr, bgrad(d.R, w.dlr2, 2 * RP, 0, RP, w.ones, Ni, P.out_ctx.grad_b), Ni, sc);
+    push_reduction(pr, wgrad_t(d.R, F, dlr, w.f2[1], 2 * F, 2 * F, 0, F, Ni, 1.f, P.out_ctx.grad_w, F), d.R, F, Ni,
+                   true, sc);
+    push_reduction(pr, bgrad_t(d.R, dlr, w.onesT, Ni, P.out_ctx.grad_b), d.R, 1, Ni, false, sc);
   }
   {
-    lirec_gemm_problem g = mk_problem(Ni, hw, false, true);
-    const lirec_operand wo = op(P.out_ints.w_bf16, d.C, hw, hw);
-    add_pass(g, mk_pass(dli_k, 0, 0, wo, 0, 0, CP));
-    add_pass(g, mk_pass(dli_k, 0, CP, wo, 0, 0, CP));
+    lirec_gemm_problem g = mk_problem(Ni, hw, true, false);
+    add_dgrad_passes(g, dli, Ni, w.out_intsT, hw, CP, 0, CP);
     if (d.gates) {
       g.epi.post = LIREC_POST_DRELU;  // through dropout(relu(.)) of the gate: model.py:353
       g.epi.post_scale = keep_scale;
       g.epi.aux = w.g2; g.epi.aux_ld = 2 * Gd; g.epi.aux_col_off = 0; g.epi.aux_lo_off = Gd;
-      out_split(g, w.dpreg2, 2 * Gd, 0, Gd);
+      out_split_t(g, w.dpregT, NiP, 0, Gd);
     } else {
       g.epi.post = LIREC_POST_DTANH;  // through dropout(tanh(.)): model.py:297
       g.epi.drop = mk_drop(p, B.seed, DS_CAT_INTS, 0);
       g.epi.aux = w.f2[0]; g.epi.aux_ld = 2 * F; g.epi.aux_col_off = 0; g.epi.aux_lo_off = F;
-      out_split(g, w.dz2[0], 2 * F, 0, F);
+      out_split_t(g, w.dz2T[0], NiP, 0, F);
     }
     pr.push_back(g);
   }
   if (d.ctx && !d.gates) {
-    lirec_gemm_problem g = mk_problem(Ni, F, false, true);
-    const lirec_operand wo = op(P.out_ctx.w_bf16, d.R, F, F);
-    add_pass(g, mk_pass(dlr_k, 0, 0, wo, 0, 0, RP));
-    add_pass(g, mk_pass(dlr_k, 0, RP, wo, 0, 0, RP));
+    lirec_gemm_problem g = mk_problem(Ni, F, true, false);
+    add_dgrad_passes(g, dlr, Ni, w.out_ctxT, F, RP, 0, RP);
     g.epi.post = LIREC_POST_DTANH;
     g.epi.drop = mk_drop(p, B.seed, DS_CAT_CTX, 0);
     g.epi.aux = w.f2[1]; g.epi.aux_ld = 2 * F; g.epi.aux_col_off = 0; g.epi.aux_lo_off = F;
-    out_split(g, w.dz2[1], 2 * F, 0, F);
+    out_split_t(g, w.dz2T[1], NiP, 0, F);
     pr.push_back(g);
   }
   if ((rc = gemm::run_grouped(pr.data(), (int)pr.size(), stream)) != LIREC_OK) return rc;
@@ -508,25 +569,19 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
   if (d.gates) {
     pr.clear();
     for (int h = 0; h < 2; ++h)  // columns [0,F) multiply the context feature, [F,2F) the ints feature
-      push_reduction(pr, wgrad(Gd, F, w.dpreg2, 2 * Gd, 0, Gd, w.f2[h ? 0 : 1], 2 * F, 2 * F, 0, F, Ni, 1.f,
-                               P.gate.grad_w + h * F, 2 * F), Ni, sc);
-    push_reduction(pr, bgrad(Gd, w.dpreg2, 2 * Gd, 0, Gd, w.ones, Ni, P.gate.grad_b), Ni, sc);
-    const lirec_operand dg_k = op(w.dpreg2, Ni, 2 * Gd, 2 * Gd);
-    const lirec_operand wg = op(P.gate.w_bf16, Gd, 2 * F, 2 * F);
+      push_reduction(pr, wgrad_t(Gd, F, dpg, w.f2[h ? 0 : 1], 2 * F, 2 * F, 0, F, Ni, 1.f, P.gate.grad_w + h * F,
+                                 2 * F), Gd, F, Ni, true, sc);
+    push_reduction(pr, bgrad_t(Gd, dpg, w.onesT, Ni, P.gate.grad_b), Gd, 1, Ni, false, sc);
     for (int h = 0; h < 2; ++h) {
       const int br = h ? 0 : 1;
-      lirec_gemm_problem g = mk_problem(Ni, F, false, true);
-      add_pass(g, mk_pass(dg_k, 0, 0, wg, h * F, 0, Gd));
-      add_pass(g, mk_pass(dg_k, 0, Gd, wg, h * F, 0, Gd));
-      if (br == 1) {  // the context feature also feeds the relationship head
-        const lirec_operand wo = op(P.out_ctx.w_bf16, d.R, F, F);
-        add_pass(g, mk_pass(dlr_k, 0, 0, wo, 0, 0, RP));
-        add_pass(g, mk_pass(dlr_k, 0, RP, wo, 0, 0, RP));
-      }
+      lirec_gemm_problem g = mk_problem(Ni, F, true, false);
+      add_dgrad_passes(g, dpg, Ni, w.gateT, 2 * F, Gd, h * F, Gd);
+      if (br == 1)  // the context feature also feeds the relationship head
+        add_dgrad_passes(g, dlr, Ni, w.out_ctxT, F, RP, 0, RP);
       g.epi.post = LIREC_POST_DTANH;
       g.epi.drop = mk_drop(p, B.seed, br ? DS_CAT_CTX : DS_CAT_INTS, 0);
       g.epi.aux = w.f2[br]; g.epi.aux_ld = 2 * F; g.epi.aux_col_off = 0; g.epi.aux_lo_off = F;
-      out_split(g, w.dz2[br], 2 * F, 0, F);
+      out_split_t(g, w.dz2T[br], NiP, 0, F);
       pr.push_back(g);
     }
     if ((rc = gemm::run_grouped(pr.data(), (int)pr.size(), stream)) != LIREC_OK) return rc;
@@ -536,16 +591,14 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
   pr.clear();
   for (int br = 0; br < nbr; ++br) {
     const lirec_encoder& enc = br ? P.enc_ctx : P.enc_ints;
-    const lirec_operand dz_k = op(w.dz2[br], Ni, 2 * F, 2 * F);
     for (int s = 0; s < 4; ++s) {
-      push_reduction(pr, wgrad(d.outw[s], J, w.dz2[br], 2 * F, d.cs[s], F + d.cs[s], w.a2[br], 8 * J, 8 * J,
-                               s * 2 * J, s * 2 * J + J, Ni, keep_scale, enc.l2[s].grad_w, J), Ni, sc);
-      push_reduction(pr, bgrad(d.outw[s], w.dz2[br], 2 * F, d.cs[s], F + d.cs[s], br ? w.flag_bf16 : w.ones, Ni,
-                               enc.l2[s].grad_b), Ni, sc);
-      lirec_gemm_problem g = mk_problem(Ni, J, false, true);
-      const lirec_operand w2 = op(enc.l2[s].w_bf16, d.outw[s], J, J);
-      add_pass(g, mk_pass(dz_k, 0, d.cs[s], w2, 0, 0, d.outw[s]));
-      add_pass(g, mk_pass(dz_k, 0, F + d.cs[s], w2, 0, 0, d.outw[s]));
+      const TGrad dz{w.dz2T[br], 2 * F, NiP, d.cs[s], F + d.cs[s]};
+      push_reduction(pr, wgrad_t(d.outw[s], J, dz, w.a2[br], 8 * J, 8 * J, s * 2 * J, s * 2 * J + J, Ni, keep_scale,
+                                 enc.l2[s].grad_w, J), d.outw[s], J, Ni, true, sc);
+      push_reduction(pr, bgrad_t(d.outw[s], dz, br ? w.flagT : w.onesT, Ni, enc.l2[s].grad_b), d.outw[s], 1, Ni,
+                     false, sc);
+      lirec_gemm_problem g = mk_problem(Ni, J, true, false);
+      add_dgrad_passes(g, dz, Ni, w.l2T[br][s], J, d.outw[s], 0, d.outw[s]);
       g.epi.alpha = keep_scale;
       out_f32(g, w.da2[br] + s * J, 4 * J);
       pr.push_back(g);
@@ -574,8 +627,9 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
         j.owner = br ? B.ctx_owner : nullptr;
         j.seg_off = br ? B.ctx_off : nullptr;
         j.drop = mk_drop(p, B.seed, br ? DS_L1_CTX : DS_L1_INTS, 0);
-        j.out = w.dz1[br][s];
-        j.out_ld = 2 * J;
+        j.out = w.dz1T[br][s];
+        j.out_ld = 0;
+        j.out_t_pitch = (s < 2) ? d.ncP[br] : d.ntP[br];
       }
     }
     jobs.n = n;
@@ -589,14 +643,16 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
     const int ncl = br ? d.nc : d.nci, ntr = br ? d.nt : d.nti;
     for (int s = 0; s < 4; ++s) {
       const int nu = (s < 2) ? ncl : ntr;
+      const int nuP = (s < 2) ? d.ncP[br] : d.ntP[br];
       const bf16* x;
       int64_t x_ld;
       if (s == 0) { x = static_cast<const bf16*>(B.clip_bank); x_ld = B.clip_ld; }
       else if (s == 1) { x = static_cast<const bf16*>(B.clip_bank) + d.inw[0]; x_ld = B.clip_ld; }
       else { x = static_cast<const bf16*>(B.track_bank); x_ld = B.track_ld; }
-      push_reduction(pr, wgrad(J, d.inw[s], w.dz1[br][s], 2 * J, 0, J, x, d.inw[s], x_ld, 0, -1, nu, 1.f,
-                               enc.l1[s].grad_w, d.inw[s]), nu, sc);
-      push_reduction(pr, bgrad(J, w.dz1[br][s], 2 * J, 0, J, w.ones, nu, enc.l1[s].grad_b), nu, sc);
+      const TGrad dz{w.dz1T[br][s], 2 * J, nuP, 0, J};
+      push_reduction(pr, wgrad_t(J, d.inw[s], dz, x, d.inw[s], x_ld, 0, -1, nu, 1.f, enc.l1[s].grad_w, d.inw[s]), J,
+                     d.inw[s], nu, true, sc);
+      push_reduction(pr, bgrad_t(J, dz, w.onesT, nu, enc.l1[s].grad_b), J, 1, nu, false, sc);
     }
   }
   if ((rc = gemm::run_grouped(pr.data(), (int)pr.size(), stream)) != LIREC_OK) return rc;
@@ -625,7 +681,7 @@ extern "C" size_t lirec_model_workspace_bytes(const lirec_model_cfg* cfg, const 
 }
 
 // Debug / white-box test aid: byte offsets of the workspace buffers, in the order
-// r1[2][4], dz1[2][4], a2[2], f2[2], dz2[2], da2[2], flag_c, flag_bf16, ones, g2, dpreg2, dli2, dlr2
+// r1[2][4], dz1T[2][4], a2[2], f2[2], dz2T[2], da2[2], flag_c, flagT, onesT, g2, dpregT, dliT, dlrT
 // (-1 for buffers the configuration does not use).  Returns the number of entries written.
 extern "C" int lirec_model_workspace_layout(const lirec_model_cfg* cfg, const lirec_batch* batch_host,
                                             int64_t* offsets, int max_entries) {
@@ -636,12 +692,12 @@ extern "C" int lirec_model_workspace_layout(const lirec_model_cfg* cfg, const li
   int n = 0;
   auto put = [&](const void* p) { offsets[n++] = p ? (reinterpret_cast<const char*>(p) - base) : -1; };
   for (int br = 0; br < 2; ++br) for (int s = 0; s < 4; ++s) put(w.r1[br][s]);
-  for (int br = 0; br < 2; ++br) for (int s = 0; s < 4; ++s) put(w.dz1[br][s]);
+  for (int br = 0; br < 2; ++br) for (int s = 0; s < 4; ++s) put(w.dz1T[br][s]);
   for (int br = 0; br < 2; ++br) put(w.a2[br]);
   for (int br = 0; br < 2; ++br) put(w.f2[br]);
-  for (int br = 0; br < 2; ++br) put(w.dz2[br]);
+  for (int br = 0; br < 2; ++br) put(w.dz2T[br]);
   for (int br = 0; br < 2; ++br) put(w.da2[br]);
-  put(w.flag_c); put(w.flag_bf16); put(w.ones); put(w.g2); put(w.dpreg2); put(w.dli2); put(w.dlr2);
+  put(w.flag_c); put(w.flagT); put(w.onesT); put(w.g2); put(w.dpregT); put(w.dliT); put(w.dlrT);
   return n;
 }
 

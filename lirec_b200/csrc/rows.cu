@@ -139,8 +139,7 @@ expand_fwd_kernel(const ExpandFwdJobs jobs) {
     for (int s = 0; s < 4; ++s) store_split4(orow + s * 2 * J + j, orow + s * 2 * J + J + j, acc[s]);
   }
   if (jb.row_flag_out && threadIdx.x == 0) jb.row_flag_out[o] = (n > 0) ? 1 : 0;
-  if (jb.flag_bf16_out && threadIdx.x < 64)
-    jb.flag_bf16_out[static_cast<int64_t>(o) * 64 + threadIdx.x] = __float2bfloat16_rn(n > 0 ? 1.f : 0.f);
+  if (jb.flag_bf16_out && threadIdx.x == 0) jb.flag_bf16_out[o] = __float2bfloat16_rn(n > 0 ? 1.f : 0.f);
 }
 
 // ---------------------------------------------------------------------------
@@ -184,6 +183,143 @@ expand_bwd_kernel(const ExpandBwdJobs jobs) {
     if (!(r.w > 0.f)) acc.w = 0.f;
     __nv_bfloat16* orow = jb.out + static_cast<int64_t>(u) * jb.out_ld;
     store_split4(orow + j, orow + J + j, acc);
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// Same reduction, TRANSPOSED output: out[(j) * pitch + u] (hi rows [0, J), lo rows [J, 2J)), the
+// K-major B operand of the first-layer weight-gradient GEMM.  One CTA owns 64 consecutive unique rows
+// and walks the J columns in chunks of 64: thread t reduces 16 columns of row t/4, the chunk is
+// transposed through shared memory, and every output row segment is 64 rows x 2 B = one 128-byte line.
+// ---------------------------------------------------------------------------
+constexpr int EBT_ROWS = 64;
+constexpr int EBT_COLS = 64;
+__global__ void __launch_bounds__(256)
+expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
+  const ExpandBwdJob& jb = jobs.job[blockIdx.y];
+  const int u0 = blockIdx.x * EBT_ROWS;
+  if (u0 >= jb.n_unique) return;
+  __shared__ __align__(16) __nv_bfloat16 tile[2][EBT_COLS][EBT_ROWS + 8];   // [hi|lo][col][row], padded
+  const int J = jb.J;
+  const int lr = threadIdx.x >> 2;            // local unique row
+  const int cq = (threadIdx.x & 3) * 16;      // first of this thread's 16 columns inside the chunk
+  const int u = u0 + lr;
+  const bool live = u < jb.n_unique;
+  int beg = 0, end = 0;
+  if (live) { beg = jb.inv_off[u]; end = jb.inv_off[u + 1]; }
+  const uint32_t thr = drop_threshold(jb.drop.p);
+  for (int c0 = 0; c0 < J; c0 += EBT_COLS) {
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+    const int j = c0 + cq;
+    for (int q = beg; q < end; ++q) {
+      const int i = jb.inv_idx[q];
+      int o = i;
+      float w = 1.0f;
+      if (jb.owner) {
+        o = jb.owner[i];
+        w = 1.0f / static_cast<float>(jb.seg_off[o + 1] - jb.seg_off[o]);
+      }
+      const float* gp = jb.d_in + static_cast<int64_t>(o) * jb.d_ld + j;
+      float4 g[4] = {ld4(gp), ld4(gp + 4), ld4(gp + 8), ld4(gp + 12)};
+      if (jb.drop.p > 0.f) {
+        const uint32_t rkey = drop_row_key(jb.drop.seed, jb.drop.stream_id, static_cast<uint32_t>(i));
+        const uint32_t cp = static_cast<uint32_t>(jb.drop.col_off + jb.slot * J + j) >> 1;   // j % 16 == 0
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t w0 = drop_word(rkey, cp + 2 * k), w1 = drop_word(rkey, cp + 2 * k + 1);
+          if ((w0 & 0xFFFFu) < thr) g[k].x = 0.f;
+          if ((w0 >> 16) < thr) g[k].y = 0.f;
+          if ((w1 & 0xFFFFu) < thr) g[k].z = 0.f;
+          if ((w1 >> 16) < thr) g[k].w = 0.f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[4 * k] += w * g[k].x; acc[4 * k + 1] += w * g[k].y;
+        acc[4 * k + 2] += w * g[k].z; acc[4 * k + 3] += w * g[k].w;
+      }
+    }
+    if (live) {
+      const float* rp = jb.r1 + static_cast<int64_t>(u) * J + j;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 r = ld4(rp + 4 * k);
+        if (!(r.x > 0.f)) acc[4 * k] = 0.f;
+        if (!(r.y > 0.f)) acc[4 * k + 1] = 0.f;
+        if (!(r.z > 0.f)) acc[4 * k + 2] = 0.f;
+        if (!(r.w > 0.f)) acc[4 * k + 3] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      __nv_bfloat16 h, l;
+      split_bf16(acc[k], h, l);
+      tile[0][cq + k][lr] = h;
+      tile[1][cq + k][lr] = l;
+    }
+    __syncthreads();
+    // write-out: thread t -> column t/4, 16 rows (32 bytes) of hi and of lo
+    {
+      const int col = threadIdx.x >> 2, r0 = (threadIdx.x & 3) * 16;
+      const int nrow = min(EBT_ROWS, jb.n_unique - u0);
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        __nv_bfloat16* dst = jb.out + (static_cast<int64_t>(part) * J + c0 + col) * jb.out_t_pitch + u0 + r0;
+        const __nv_bfloat16* src = &tile[part][col][r0];
+        if (r0 + 16 <= nrow) {
+          reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(src)[0];
+          reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(src)[1];
+        } else {
+          for (int k = 0; r0 + k < nrow; ++k) dst[k] = src[k];
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// fp32 [rows, cols] -> TRANSPOSED hi/lo bf16 split: out[c * pitch + r] (hi, c < pad) and
+// out[(pad + c) * pitch + r] (lo); rows c in [cols, pad) are zero.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+split_t_kernel(const float* __restrict__ x, int64_t ld, int rows, int cols, __nv_bfloat16* __restrict__ out,
+               int64_t pitch, int pad) {
+  const int c = blockIdx.y;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+    const float v = (c < cols) ? x[static_cast<int64_t>(r) * ld + c] : 0.f;
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    out[static_cast<int64_t>(c) * pitch + r] = h;
+    out[static_cast<int64_t>(pad + c) * pitch + r] = l;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Batched bf16 transposes with zero padding: dst[c, r] = src[r, c] for r < R, 0 for R <= r < Rp.
+// Gives backward the [in, out] (K-major) copy of every weight its data-gradient GEMMs multiply by.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const TransposeJobs jobs) {
+  const TransposeJob& jb = jobs.job[blockIdx.y];
+  const int tiles_c = (jb.C + 63) / 64, tiles_r = (jb.Rp + 63) / 64;
+  __shared__ __nv_bfloat16 tile[64][64 + 2];
+  for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+    const int r0 = (t / tiles_c) * 64, c0 = (t % tiles_c) * 64;
+    for (int k = threadIdx.x; k < 64 * 64; k += blockDim.x) {
+      const int r = r0 + k / 64, c = c0 + k % 64;
+      tile[k / 64][k % 64] = (r < jb.R && c < jb.C) ? jb.src[static_cast<int64_t>(r) * jb.src_ld + c]
+                                                   : __float2bfloat16_rn(0.f);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 64 * 64; k += blockDim.x) {
+      const int c = c0 + k / 64, r = r0 + k % 64;
+      if (c < jb.C && r < jb.Rp) jb.dst[static_cast<int64_t>(c) * jb.dst_ld + r] = tile[k % 64][k / 64];
+    }
+    __syncthreads();
   }
 }
 
@@ -269,8 +405,50 @@ int expand_bwd(const ExpandBwdJobs& jobs, cudaStream_t stream) {
     max_u = std::max(max_u, j.n_unique);
   }
   if (max_u == 0 || jobs.n == 0) return LIREC_OK;
-  dim3 grid(max_u, jobs.n);
-  expand_bwd_kernel<<<grid, 128, 0, stream>>>(jobs);
+  int n_t = 0;
+  for (int i = 0; i < jobs.n; ++i) n_t += jobs.job[i].out_t_pitch > 0 ? 1 : 0;
+  LIREC_REQUIRE(n_t == 0 || n_t == jobs.n, "expand_bwd: natural and transposed outputs cannot be mixed");
+  if (n_t) {
+    for (int i = 0; i < jobs.n; ++i) {
+      const ExpandBwdJob& j = jobs.job[i];
+      LIREC_REQUIRE(j.J % EBT_COLS == 0 && j.out_t_pitch % 8 == 0 && j.out_t_pitch >= j.n_unique &&
+                        (reinterpret_cast<uintptr_t>(j.out) & 15) == 0,
+                    "expand_bwd: transposed output needs J %% 64 == 0 and a 16-byte aligned pitch");
+    }
+    dim3 grid((max_u + EBT_ROWS - 1) / EBT_ROWS, jobs.n);
+    expand_bwd_t_kernel<<<grid, 256, 0, stream>>>(jobs);
+  } else {
+    dim3 grid(max_u, jobs.n);
+    expand_bwd_kernel<<<grid, 128, 0, stream>>>(jobs);
+  }
+  LIREC_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return LIREC_OK;
+}
+
+int split_f32_t(const float* x, int64_t ld, int rows, int cols, void* out, int64_t pitch, int pad,
+                cudaStream_t stream) {
+  LIREC_REQUIRE(pad >= cols && pitch >= rows, "split_f32_t: pad=%d cols=%d pitch=%lld rows=%d", pad, cols,
+                (long long)pitch, rows);
+  if (rows <= 0) return LIREC_OK;
+  dim3 grid(std::min((rows + 255) / 256, 64), pad);
+  split_t_kernel<<<grid, 256, 0, stream>>>(x, ld, rows, cols, reinterpret_cast<__nv_bfloat16*>(out), pitch, pad);
+  LIREC_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return LIREC_OK;
+}
+
+int transpose_bf16(const TransposeJobs& jobs, cudaStream_t stream) {
+  if (jobs.n == 0) return LIREC_OK;
+  int max_tiles = 0;
+  for (int i = 0; i < jobs.n; ++i) {
+    const TransposeJob& j = jobs.job[i];
+    LIREC_REQUIRE(j.src && j.dst && j.R > 0 && j.C > 0 && j.Rp >= j.R && j.dst_ld >= j.Rp,
+                  "transpose_bf16: bad job %d", i);
+    max_tiles = std::max(max_tiles, ((j.C + 63) / 64) * ((j.Rp + 63) / 64));
+  }
+  dim3 grid(std::min(max_tiles, 148 * 4), jobs.n);
+  transpose_bf16_kernel<<<grid, 256, 0, stream>>>(jobs);
   LIREC_CUDA_OK(cudaGetLastError());
   note_launch();
   return LIREC_OK;
@@ -343,7 +521,8 @@ extern "C" int lirec_rows_expand_fwd(const float* r1_txt, const float* r1_vis, c
 extern "C" int lirec_rows_expand_bwd(const float* d_in, int64_t d_ld, const float* r1, int32_t J,
                                      int32_t slot, const int32_t* inv_off, const int32_t* inv_idx,
                                      int32_t n_unique, const int32_t* owner, const int32_t* seg_off,
-                                     lirec_dropout drop, void* out_split, int64_t out_ld, void* stream) {
+                                     lirec_dropout drop, void* out_split, int64_t out_ld,
+                                     int64_t out_t_pitch, void* stream) {
   LIREC_ENTER();
   LIREC_REQUIRE((owner == nullptr) == (seg_off == nullptr), "expand_bwd: owner and seg_off go together");
   rows::ExpandBwdJobs jobs;
@@ -354,6 +533,7 @@ extern "C" int lirec_rows_expand_bwd(const float* d_in, int64_t d_ld, const floa
   j.owner = owner; j.seg_off = seg_off; j.drop = drop;
   j.out = reinterpret_cast<__nv_bfloat16*>(out_split);
   j.out_ld = out_ld;
+  j.out_t_pitch = out_t_pitch;
   return rows::expand_bwd(jobs, static_cast<cudaStream_t>(stream));
 }
 

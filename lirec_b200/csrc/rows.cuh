@@ -21,7 +21,7 @@ struct ExpandFwdJob {
   __nv_bfloat16* out;       // [n_out, out_ld], slot s at columns [s*2J, (s+1)*2J) as hi|lo
   int64_t out_ld;
   int32_t* row_flag_out;    // [n_out] or NULL: 1 where the segment is non-empty
-  __nv_bfloat16* flag_bf16_out;  // [n_out, 64] or NULL: the same flag as a bf16 GEMM operand
+  __nv_bfloat16* flag_bf16_out;  // [n_out] or NULL: the same flag as a bf16 row ([1, n_out] K-major GEMM operand)
 };
 struct ExpandFwdJobs {
   ExpandFwdJob job[MAX_JOBS];
@@ -40,11 +40,27 @@ struct ExpandBwdJob {
   const int32_t* owner;     // NULL (ints) or [n_rows] candidate of each context row
   const int32_t* seg_off;   // NULL or [n_out + 1]
   lirec_dropout drop;
-  __nv_bfloat16* out;       // [n_unique, out_ld] hi|lo
+  __nv_bfloat16* out;       // [n_unique, out_ld] hi|lo, or transposed [2J, out_t_pitch] (hi rows, lo rows)
   int64_t out_ld;
+  int64_t out_t_pitch;      // > 0: transposed output with this row pitch (elements)
 };
 struct ExpandBwdJobs {
   ExpandBwdJob job[MAX_JOBS];
+  int32_t n;
+};
+
+// dst[c, r] = src[r, c] (bf16), zero for R <= r < Rp
+struct TransposeJob {
+  const __nv_bfloat16* src;
+  int64_t src_ld;
+  int32_t R, C;
+  __nv_bfloat16* dst;
+  int64_t dst_ld;
+  int32_t Rp;
+};
+constexpr int MAX_TRANSPOSE_JOBS = 16;
+struct TransposeJobs {
+  TransposeJob job[MAX_TRANSPOSE_JOBS];
   int32_t n;
 };
 
@@ -55,6 +71,9 @@ int expand_bwd(const ExpandBwdJobs& jobs, cudaStream_t stream);
 int split_f32(const float* x, int64_t ld, int rows, int cols, void* out, int64_t out_ld, int pad_cols,
               cudaStream_t stream);
 int cast_bf16(const float* x, void* out, int64_t n, cudaStream_t stream);
+int split_f32_t(const float* x, int64_t ld, int rows, int cols, void* out, int64_t pitch, int pad,
+                cudaStream_t stream);
+int transpose_bf16(const TransposeJobs& jobs, cudaStream_t stream);
 
 }  // namespace rows
 }  // namespace lirec

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _ext
-from ._ext import (ACT_NONE, ACT_RELU, ACT_TANH, OUT_F32, OUT_SPLIT, POST_DRELU, POST_DROPOUT, POST_DTANH,
+from ._ext import (ACT_NONE, ACT_RELU, ACT_TANH, OUT_F32, OUT_SPLIT, OUT_SPLIT_T, POST_DRELU, POST_DROPOUT, POST_DTANH,
                    POST_NONE)
 
 __all__ = ["gemm_problem", "gemm_grouped", "seg_reduce", "rows_expand_fwd", "rows_expand_bwd", "split_f32",
@@ -79,12 +79,13 @@ def rows_expand_fwd(r1, J, rows, seg_off, n_out, guard_zero, drop, out_split, ro
 
 
 def rows_expand_bwd(d_in, d_ld, r1, J, slot, inv_off, inv_idx, n_unique, owner, seg_off, drop, out_split,
-                    d_in_col_off=0):
+                    d_in_col_off=0, transposed=False):
+    """transposed=False: out_split [n_unique, 2J]; True: out_split [2J, pitch] with pitch = out_split.stride(0)."""
     L = _ext.lib()
     _ext.check(L.lirec_rows_expand_bwd(
         d_in.data_ptr() + 4 * d_in_col_off, d_ld, _ext.ptr(r1), J, slot, _ext.ptr(inv_off), _ext.ptr(inv_idx),
         n_unique, _ext.ptr(owner), _ext.ptr(seg_off), drop, _ext.ptr(out_split), out_split.stride(0),
-        _ext.stream_ptr()))
+        out_split.stride(0) if transposed else 0, _ext.stream_ptr()))
 
 
 def split_f32(x, out_split, pad_cols):

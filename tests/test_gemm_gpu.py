@@ -143,3 +143,48 @@ def test_argument_errors_are_reported():
     out = torch.empty(64, 64, device="cuda")
     with pytest.raises(RuntimeError, match="16-byte"):
         ops.gemm_grouped([ops.gemm_problem(64, 64, [(_ext.operand(a), 0, 0, _ext.operand(b), 0, 0, 100)], out=out)])
+
+
+def test_transposed_gradient_forms():
+    """The three operand forms of backward (all with a K-major B, the CTA-pair kernel's fast path):
+    dgrad  dX = dY W      : A = dY^T [feat, rows] read MN-major, B = W^T [in, out], transposed split store;
+    wgrad  dW = dY^T X    : computed as X^T dY with A = X natural (MN-major), B = dY^T, transposed fp32 store;
+    bgrad  db = dY^T 1    : A = dY^T K-major, B = a single row of ones (rows past it are TMA zero fill)."""
+    from lirec_b200 import _ext, ops
+    rows, out_f, in_f = 1000, 200, 328
+    pitch = 1024
+    dy = torch.randn(rows, out_f, device="cuda")
+    dyT = torch.full((2 * 256, pitch), float("nan"), device="cuda", dtype=torch.bfloat16)   # hi rows 0.., lo rows 256..
+    dyT[:256, :rows] = 0
+    dyT[256:, :rows] = 0
+    hi = dy.to(torch.bfloat16)
+    dyT[:out_f, :rows] = hi.t()
+    dyT[256:256 + out_f, :rows] = (dy - hi.float()).to(torch.bfloat16).t()
+    w = _rnd(out_f, in_f)
+    wT = torch.zeros(in_f, 256, device="cuda", dtype=torch.bfloat16)
+    wT[:, :out_f] = w.t()
+    o_dyT = _ext.operand(dyT[:, :rows])                       # view: cols = rows, ld = pitch
+    # dgrad, transposed split output [2 * in_p, pitch]
+    in_p = 384
+    dxT = torch.zeros(2 * in_p, pitch, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_grouped([ops.gemm_problem(rows, in_f, [(o_dyT, 0, 0, _ext.operand(wT), 0, 0, 256),
+                                                    (o_dyT, 0, 256, _ext.operand(wT), 0, 0, 256)],
+                                       a_mn_major=True, out=dxT, out_kind=ops.OUT_SPLIT_T, out_ld_m=pitch,
+                                       out_lo_off=in_p)])
+    got = (dxT[:in_f, :rows].double() + dxT[in_p:in_p + in_f, :rows].double()).t()
+    assert _rel(got, dy.double() @ w.double()) < 2e-5
+    assert (dxT[:, rows:] == 0).all() and (dxT[in_f:in_p] == 0).all()         # nothing outside the valid block
+    # wgrad, transposed fp32 store into dW[out_f, in_f]
+    x = _rnd(rows, in_f)
+    dW = torch.full((out_f, in_f), float("nan"), device="cuda")
+    ops.gemm_grouped([ops.gemm_problem(in_f, out_f, [(_ext.operand(x), 0, 0, o_dyT, 0, 0, rows),
+                                                     (_ext.operand(x), 0, 0, o_dyT, 256, 0, rows)],
+                                       a_mn_major=True, out=dW, out_ld_m=1, out_ld_n=in_f)])
+    assert _rel(dW, dy.double().t() @ x.double()) < 2e-5
+    # bgrad against one row of ones
+    ones = torch.ones(1, pitch, device="cuda", dtype=torch.bfloat16)
+    db = torch.full((out_f,), float("nan"), device="cuda")
+    ops.gemm_grouped([ops.gemm_problem(out_f, 1, [(o_dyT, 0, 0, _ext.operand(ones[:, :rows]), 0, 0, rows),
+                                                  (o_dyT, 256, 0, _ext.operand(ones[:, :rows]), 0, 0, rows)],
+                                       out=db, out_ld_m=1)])
+    assert _rel(db, dy.double().sum(0)) < 2e-5

@@ -118,6 +118,13 @@ def test_expand_forward_and_backward(p):
         ref *= (r1[slot] > 0)
         got = (out[:, :J].double() + out[:, J:].double()).cpu().numpy()
         np.testing.assert_allclose(got, ref, rtol=0, atol=2e-5 * np.abs(ref).max())
+        # transposed output (the K-major operand of the first-layer wgrad GEMM): same values, bit for bit
+        pitch = (n_u + 63) // 64 * 64
+        out_t = torch.zeros(2 * J, pitch, device="cuda", dtype=torch.bfloat16)
+        ops.rows_expand_bwd(dd, 4 * J, r1d[slot], J, slot, torch.from_numpy(off).cuda(), torch.from_numpy(idx).cuda(),
+                            n_u, torch.from_numpy(owner).cuda(), segd, drop, out_t, d_in_col_off=slot * J,
+                            transposed=True)
+        assert torch.equal(out_t[:, :n_u].t().contiguous(), out)
 
 
 def test_split_and_cast():

@@ -20,6 +20,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
     "--shared",
 ]
+# A/B knobs for kernel experiments (defaults are what ships): LIREC_NVCC_DEFINES="-DLIREC_EPI_WARPS=16 ..."
+NVCC_FLAGS += [f for f in os.environ.get("LIREC_NVCC_DEFINES", "").split() if f.startswith("-D")]
 
 
 def _nvcc():

@@ -230,8 +230,10 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n"
                "barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Relaxed: the arrive only has to be ordered after this warp's TMEM reads, which the preceding
+// tcgen05.fence::before_thread_sync does; a release here would also wait for the epilogue's global stores.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
                : "memory");
 }
 // TMA load issued by either CTA of a pair: data lands in the issuing CTA's smem, the byte count is

@@ -111,7 +111,7 @@ static int split_factor(int out_f, int in_f, int passes, int rows) {
   const int tiles = ((in_f + 255) / 256) * ((out_f + bn - 1) / bn);
   const int kb = passes * ((rows + 63) / 64);
   if (tiles >= 64 || kb < 128) return 1;
-  return std::max(1, std::min(std::min(8, kb / 64), (148 + tiles - 1) / tiles));
+  return std::max(1, std::min(std::min(8, kb / 64), (74 + tiles - 1) / tiles));
 }
 static size_t split_pool_floats(const Dims& d) {
   size_t n = 0;

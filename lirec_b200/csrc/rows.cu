@@ -195,17 +195,36 @@ expand_bwd_kernel(const ExpandBwdJobs jobs) {
 // ---------------------------------------------------------------------------
 constexpr int EBT_ROWS = 64;
 constexpr int EBT_COLS = 64;
+constexpr int EBT_REFS = 1536;   // references cached in shared memory per CTA (the rest is read in place)
 __global__ void __launch_bounds__(256)
 expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
   const ExpandBwdJob& jb = jobs.job[blockIdx.y];
   const int u0 = blockIdx.x * EBT_ROWS;
   if (u0 >= jb.n_unique) return;
   __shared__ __align__(16) __nv_bfloat16 tile[2][EBT_COLS][EBT_ROWS + 8];   // [hi|lo][col][row], padded
+  __shared__ int32_t ref_row[EBT_REFS];     // table row i (dropout key)
+  __shared__ int32_t ref_out[EBT_REFS];     // expanded row o whose gradient is read
+  __shared__ float ref_w[EBT_REFS];         // 1 / segment length (1 for the ints branch)
   const int J = jb.J;
   const int lr = threadIdx.x >> 2;            // local unique row
   const int cq = (threadIdx.x & 3) * 16;      // first of this thread's 16 columns inside the chunk
   const int u = u0 + lr;
   const bool live = u < jb.n_unique;
+  // The references of 64 consecutive unique rows are one contiguous span of the CSR: resolve
+  // idx -> owner -> 1/len ONCE per CTA, one reference per thread (three dependent loads, all in flight
+  // together), instead of once per thread per column chunk.
+  const int q0 = jb.inv_off[u0], q1 = jb.inv_off[min(u0 + EBT_ROWS, jb.n_unique)];
+  for (int q = q0 + threadIdx.x; q < min(q1, q0 + EBT_REFS); q += blockDim.x) {
+    const int i = jb.inv_idx[q];
+    int o = i;
+    float w = 1.0f;
+    if (jb.owner) {
+      o = jb.owner[i];
+      w = 1.0f / static_cast<float>(jb.seg_off[o + 1] - jb.seg_off[o]);
+    }
+    ref_row[q - q0] = i; ref_out[q - q0] = o; ref_w[q - q0] = w;
+  }
+  __syncthreads();
   int beg = 0, end = 0;
   if (live) { beg = jb.inv_off[u]; end = jb.inv_off[u + 1]; }
   const uint32_t thr = drop_threshold(jb.drop.p);
@@ -215,12 +234,16 @@ expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
     for (int k = 0; k < 16; ++k) acc[k] = 0.f;
     const int j = c0 + cq;
     for (int q = beg; q < end; ++q) {
-      const int i = jb.inv_idx[q];
-      int o = i;
-      float w = 1.0f;
-      if (jb.owner) {
-        o = jb.owner[i];
-        w = 1.0f / static_cast<float>(jb.seg_off[o + 1] - jb.seg_off[o]);
+      int i, o;
+      float w;
+      if (q - q0 < EBT_REFS) {
+        i = ref_row[q - q0]; o = ref_out[q - q0]; w = ref_w[q - q0];
+      } else {
+        i = jb.inv_idx[q]; o = i; w = 1.0f;
+        if (jb.owner) {
+          o = jb.owner[i];
+          w = 1.0f / static_cast<float>(jb.seg_off[o + 1] - jb.seg_off[o]);
+        }
       }
       const float* gp = jb.d_in + static_cast<int64_t>(o) * jb.d_ld + j;
       float4 g[4] = {ld4(gp), ld4(gp + 4), ld4(gp + 8), ld4(gp + 12)};
@@ -307,17 +330,37 @@ transpose_bf16_kernel(const TransposeJobs jobs) {
   const TransposeJob& jb = jobs.job[blockIdx.y];
   const int tiles_c = (jb.C + 63) / 64, tiles_r = (jb.Rp + 63) / 64;
   __shared__ __nv_bfloat16 tile[64][64 + 2];
+  const bool vec = (jb.C % 2 == 0) && (jb.src_ld % 2 == 0) && (jb.Rp % 2 == 0) && (jb.dst_ld % 2 == 0) &&
+                   (reinterpret_cast<uintptr_t>(jb.src) % 4 == 0) && (reinterpret_cast<uintptr_t>(jb.dst) % 4 == 0);
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
   for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
     const int r0 = (t / tiles_c) * 64, c0 = (t % tiles_c) * 64;
-    for (int k = threadIdx.x; k < 64 * 64; k += blockDim.x) {
-      const int r = r0 + k / 64, c = c0 + k % 64;
-      tile[k / 64][k % 64] = (r < jb.R && c < jb.C) ? jb.src[static_cast<int64_t>(r) * jb.src_ld + c]
-                                                   : __float2bfloat16_rn(0.f);
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < 64 * 64; k += blockDim.x) {
-      const int c = c0 + k / 64, r = r0 + k % 64;
-      if (c < jb.C && r < jb.Rp) jb.dst[static_cast<int64_t>(c) * jb.dst_ld + r] = tile[k % 64][k / 64];
+    if (vec) {
+      // load: 32 column pairs x 64 rows, one 4-byte load per element pair (128 B per row per warp)
+      for (int k = threadIdx.x; k < 64 * 32; k += blockDim.x) {
+        const int r = r0 + k / 32, c = c0 + 2 * (k % 32);
+        __nv_bfloat162 v = __halves2bfloat162(zero, zero);
+        if (r < jb.R && c < jb.C) v = *reinterpret_cast<const __nv_bfloat162*>(jb.src + static_cast<int64_t>(r) * jb.src_ld + c);
+        tile[k / 32][2 * (k % 32)] = v.x;
+        tile[k / 32][2 * (k % 32) + 1] = v.y;
+      }
+      __syncthreads();
+      for (int k = threadIdx.x; k < 64 * 32; k += blockDim.x) {
+        const int c = c0 + k / 32, r = r0 + 2 * (k % 32);
+        if (c < jb.C && r < jb.Rp)
+          *reinterpret_cast<__nv_bfloat162*>(jb.dst + static_cast<int64_t>(c) * jb.dst_ld + r) =
+              __halves2bfloat162(tile[2 * (k % 32)][k / 32], tile[2 * (k % 32) + 1][k / 32]);
+      }
+    } else {
+      for (int k = threadIdx.x; k < 64 * 64; k += blockDim.x) {
+        const int r = r0 + k / 64, c = c0 + k % 64;
+        tile[k / 64][k % 64] = (r < jb.R && c < jb.C) ? jb.src[static_cast<int64_t>(r) * jb.src_ld + c] : zero;
+      }
+      __syncthreads();
+      for (int k = threadIdx.x; k < 64 * 64; k += blockDim.x) {
+        const int c = c0 + k / 64, r = r0 + k % 64;
+        if (c < jb.C && r < jb.Rp) jb.dst[static_cast<int64_t>(c) * jb.dst_ld + r] = tile[k % 64][k / 64];
+      }
     }
     __syncthreads();
   }

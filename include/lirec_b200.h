@@ -194,6 +194,14 @@ int lirec_rows_expand_bwd(const float* d_in, int64_t d_ld, const float* r1, int3
                           lirec_dropout drop, void* out_split, int64_t out_ld,
                           int64_t out_t_pitch, void* stream);
 
+/* Row gather out[i, :] = bank[idx[i], :] over bf16 rows (dim, bank_ld, out_ld in elements,
+ * multiples of 8; idx outside [0, n_bank) gives a zero row).  Replaces the host-side
+ * np.hstack / np.tile assembly of cached vectors into batch rows (reference
+ * mixed_utils/mixed_features.py:115-125, classification_dataloader.py:329-334, 393-416):
+ * the split's pooled feature banks stay resident in HBM and a batch ships only indices.  */
+int lirec_gather_rows(const void* bank, int64_t bank_ld, int32_t n_bank, const int32_t* idx,
+                      int32_t n, int32_t dim, void* out, int64_t out_ld, void* stream);
+
 /* fp32 [rows, cols] -> hi/lo bf16 split [rows, 2*pad_cols] (zero padded). */
 int lirec_split_f32(const float* x, int64_t ld, int32_t rows, int32_t cols, void* out_split,
                     int64_t out_ld, int32_t pad_cols, void* stream);

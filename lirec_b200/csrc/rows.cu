@@ -401,8 +401,45 @@ cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, i
 }
 
 // ---------------------------------------------------------------------------
+// Row gather: out[i, :] = bank[idx[i], :] (bf16 rows, 16-byte column groups).  Builds the per-batch
+// feature banks from dataset banks that stay resident in HBM; one warp-wide 128-bit load and store
+// per 512 bytes of row, grid-strided over (row, column-group) pairs so short rows still fill the SMs.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const uint4* __restrict__ bank, int64_t bank_ld16, int n_bank, const int32_t* __restrict__ idx,
+                   int n, int cols16, uint4* __restrict__ out, int64_t out_ld16) {
+  const int64_t total = static_cast<int64_t>(n) * cols16;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / cols16), c = static_cast<int>(i - static_cast<int64_t>(r) * cols16);
+    const int src = idx[r];
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (src >= 0 && src < n_bank) v = bank[static_cast<int64_t>(src) * bank_ld16 + c];   // out of range -> zero row
+    out[static_cast<int64_t>(r) * out_ld16 + c] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
+int gather_rows(const void* bank, int64_t bank_ld, int n_bank, const int32_t* idx, int n, int dim, void* out,
+                int64_t out_ld, cudaStream_t stream) {
+  LIREC_REQUIRE(dim > 0 && dim % 8 == 0 && bank_ld % 8 == 0 && out_ld % 8 == 0,
+                "gather_rows: dim=%d and the row pitches must be multiples of 8 bf16 elements", dim);
+  LIREC_REQUIRE((reinterpret_cast<uintptr_t>(bank) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "gather_rows: bank / out not 16-byte aligned");
+  LIREC_REQUIRE(bank && idx && out && n_bank > 0, "gather_rows: null argument");
+  if (n <= 0) return LIREC_OK;
+  const int cols16 = dim / 8;
+  const int64_t total = static_cast<int64_t>(n) * cols16;
+  const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16));
+  gather_rows_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(bank), bank_ld / 8, n_bank, idx, n, cols16,
+                                               static_cast<uint4*>(out), out_ld / 8);
+  LIREC_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return LIREC_OK;
+}
+
 int seg_reduce(const float* x, const int32_t* seg_off, int nseg, int dim, int mode, float* out_f32,
                int64_t out_f32_ld, void* out_bf16, int64_t out_bf16_ld, cudaStream_t stream) {
   LIREC_REQUIRE(dim > 0 && dim % 4 == 0, "seg_reduce: dim=%d must be a positive multiple of 4", dim);
@@ -578,6 +615,12 @@ extern "C" int lirec_rows_expand_bwd(const float* d_in, int64_t d_ld, const floa
   j.out_ld = out_ld;
   j.out_t_pitch = out_t_pitch;
   return rows::expand_bwd(jobs, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lirec_gather_rows(const void* bank, int64_t bank_ld, int32_t n_bank, const int32_t* idx, int32_t n,
+                                 int32_t dim, void* out, int64_t out_ld, void* stream) {
+  LIREC_ENTER();
+  return rows::gather_rows(bank, bank_ld, n_bank, idx, n, dim, out, out_ld, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int lirec_split_f32(const float* x, int64_t ld, int32_t rows_n, int32_t cols, void* out_split,

@@ -10,6 +10,13 @@ i+1 to the GPU on a side stream while batch i computes.
 The MovieGraphs annotations / feature dump (~80 GB) are not available offline, and their parsing
 (utils/util_functions.py, moviegraphs/py3loader) is outside the hot path:
 without `opt.synthetic` the dataset refuses to construct instead of pretending.
+
+  --synthetic 1   independent synthetic clips (mixed_utils/synthetic.py; the bench workload)
+  --synthetic 2   a synthetic ANNOTATION world (mixed_utils/synthetic_world.py) run through the index-only
+                  port of the reference dataset logic (mixed_utils/indexed_dataset.py: relationship
+                  timelines, shared context clips, the reference's slot order and RNG use), the path real
+                  MovieGraphs annotations would take; `--resident_banks 1` keeps the split's pooled feature
+                  banks in HBM so a batch ships only index tables.
 """
 import torch
 from torch.utils.data import Dataset
@@ -26,7 +33,18 @@ def preset_from_opt():
     return "int_rels"
 
 
-class MixedFeaturesDataset(Dataset):
+def MixedFeaturesDataset(mode="train", size=None):
+    """Reference constructor signature (classification_dataloader.py:30); dispatches on opt.synthetic."""
+    if int(getattr(opt, "synthetic", 0)) == 2:
+        from lirec_b200.mixed_utils import indexed_dataset, synthetic_world
+        world = synthetic_world.build_world(int(opt.seed), n_movies=int(getattr(opt, "world_movies", 6)),
+                                            n_scenes=int(getattr(opt, "world_scenes", 40)), n_inter_names=324,
+                                            n_merged=synthetic.N_CLASSES)
+        return indexed_dataset.IndexedMixedFeaturesDataset(synthetic_world.subset(world, mode), world, mode=mode)
+    return SyntheticClipsDataset(mode, size)
+
+
+class SyntheticClipsDataset(Dataset):
     """Same constructor and attributes the loops use (`n_classes`, `n_rels`, `rels_list`, `cache()`,
     `init_relships()`, `epoch`), backed by the synthetic MovieGraphs-shaped generator."""
     SIZES = {"train": 4096, "val": 512, "test": 512}
@@ -65,6 +83,9 @@ class MixedFeaturesDataset(Dataset):
         return synthetic.make_clip(self._base + int(idx), preset=self.preset, max_n_tripl=self._max_n_tripl,
                                    rels_n_clips=self.rels_n_clips)
 
+    def collate(self, records):
+        return collate_packed(records)
+
 
 def collate_packed(records):
     """records -> pinned host PackedBatch (runs in the dataloader worker / main process)."""
@@ -94,9 +115,15 @@ def packed_loader(dataset, batch_size, shuffle, num_workers=0, device="cuda", ra
                                          num_workers=int(num_workers), collate_fn=None)
     copy_stream = torch.cuda.Stream(device=device)
     pending = None
+    banks = None
+    if int(getattr(opt, "resident_banks", 0)) and hasattr(dataset, "clip_bank"):
+        from lirec_b200.mixed_utils.indexed_dataset import ResidentBanks
+        banks = getattr(dataset, "_resident", None) or ResidentBanks(dataset, device)
+        dataset._resident = banks
+        copy_stream.wait_stream(torch.cuda.current_stream())
     for host_pb in loader:
         with torch.cuda.stream(copy_stream):
-            dev_pb = host_pb.pin().to_device(device, non_blocking=True)
+            dev_pb = banks.stage(host_pb) if banks is not None else host_pb.pin().to_device(device, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         if pending is not None:
@@ -121,7 +148,7 @@ class _IndexView(Dataset):
 
     def __getitem__(self, i):
         idx, global_size = self.batches[i]
-        pb = collate_packed([self.dataset[j] for j in idx])
+        pb = self.dataset.collate([self.dataset[j] for j in idx])
         pb.global_clips = global_size
         return pb
 

@@ -12,7 +12,7 @@ from ._ext import (ACT_NONE, ACT_RELU, ACT_TANH, OUT_F32, OUT_SPLIT, OUT_SPLIT_T
                    POST_NONE)
 
 __all__ = ["gemm_problem", "gemm_grouped", "seg_reduce", "rows_expand_fwd", "rows_expand_bwd", "split_f32",
-           "cast_bf16", "loss_track", "loss_rowmargin", "predict_tracks", "adam_flat", "dropout_desc"]
+           "cast_bf16", "gather_rows", "loss_track", "loss_rowmargin", "predict_tracks", "adam_flat", "dropout_desc"]
 
 
 def dropout_desc(p=0.0, seed=0, stream_id=0, col_off=0):
@@ -97,6 +97,16 @@ def split_f32(x, out_split, pad_cols):
 def cast_bf16(x, out):
     L = _ext.lib()
     _ext.check(L.lirec_cast_bf16(_ext.ptr(x), _ext.ptr(out), x.numel(), _ext.stream_ptr()))
+
+
+def gather_rows(bank, idx, out=None):
+    """out[i] = bank[idx[i]] over bf16 rows on the device (lirec_gather_rows)."""
+    assert bank.dtype == torch.bfloat16 and bank.dim() == 2 and bank.stride(1) == 1 and idx.dtype == torch.int32
+    if out is None:
+        out = torch.empty(idx.numel(), bank.shape[1], dtype=torch.bfloat16, device=bank.device)
+    _ext.check(_ext.lib().lirec_gather_rows(_ext.ptr(bank), bank.stride(0), bank.shape[0], _ext.ptr(idx), idx.numel(),
+                                            bank.shape[1], _ext.ptr(out), out.stride(0), _ext.stream_ptr()))
+    return out
 
 
 def loss_track(ints, rels, cand_off, labels, rels_label, gt_tracks, multilab, margin, lymbda, n_rels,

@@ -156,8 +156,10 @@ class PackedBatch:
         self.multilab = self.multilab.pin_memory()
         return self
 
-    def to_device(self, device="cuda", non_blocking=True):
-        """Copy to the GPU: 4 async copies (int arena, clip bank, track bank, multilab)."""
+    def to_device(self, device="cuda", non_blocking=True, banks=True):
+        """Copy to the GPU: 4 async copies (int arena, clip bank, track bank, multilab).  With
+        banks=False the two feature banks are left for the caller to provide on the device
+        (mixed_utils/indexed_dataset.py:ResidentBanks gathers them from HBM-resident dataset banks)."""
         if not hasattr(self, "_arena"):
             self.pin()
         d = PackedBatch()
@@ -165,8 +167,9 @@ class PackedBatch:
             setattr(d, k, getattr(self, k))
         d.device = torch.device(device)
         arena = self._arena.to(device, non_blocking=non_blocking)
-        d.clip_bank = self.clip_bank.to(device, non_blocking=non_blocking)
-        d.track_bank = self.track_bank.to(device, non_blocking=non_blocking)
+        if banks:
+            d.clip_bank = self.clip_bank.to(device, non_blocking=non_blocking)
+            d.track_bank = self.track_bank.to(device, non_blocking=non_blocking)
         d.multilab = self.multilab.to(device, non_blocking=non_blocking)
         for k, (off, n, shape) in self._layout.items():
             d.tables[k] = arena[off:off + n].view(*shape)
@@ -177,7 +180,7 @@ class PackedBatch:
     def record_stream(self, stream):
         """Tell the caching allocator that `stream` uses this batch's device tensors (they may have been
         allocated on a copy stream)."""
-        for t in (self._arena_dev, self.clip_bank, self.track_bank, self.multilab):
+        for t in (self._arena_dev, self.clip_bank, self.track_bank, self.multilab) + tuple(getattr(self, "_bank_idx", ())):
             t.record_stream(stream)
         return self
 
@@ -194,6 +197,7 @@ class PackedBatch:
             return np.hstack((clip[tbl[:, 0]], track[tbl[:, 1]], track[tbl[:, 2]]))
 
         cand = rows_of(t["cand_rows"])
+        ROW_DIM = cand.shape[1]
         b_idx, s_idx = t["cand_clip"], t["cand_slot"]
         out = {}
         mem_mask = np.zeros((B, T), dtype=np.float64)

@@ -103,7 +103,11 @@ _FLAGS = [
     ("--dp", dict(default=0, type=int, help="1: data-parallel over clips, NCCL gradient allreduce")),
     ("--fused_adam", dict(default=0, type=int, help="1: flat fused Adam kernel instead of torch.optim.Adam")),
     ("--max_n_tripl", dict(default=20, type=int, help="candidate slots per clip (reference hard-codes 20)")),
-    ("--synthetic", dict(default=0, type=int, help="1: synthetic MovieGraphs-shaped dataset")),
+    ("--synthetic", dict(default=0, type=int, help="1: independent synthetic MovieGraphs-shaped clips; 2: synthetic "
+                                                   "annotation world through the index-only dataset")),
+    ("--resident_banks", dict(default=0, type=int, help="1: pooled feature banks stay in HBM, batches ship indices")),
+    ("--world_movies", dict(default=6, type=int)),
+    ("--world_scenes", dict(default=40, type=int)),
 ]
 
 

@@ -117,3 +117,88 @@ def run_loss(loss, output, batch):
     """Call a reference loss under torch-1.1 mask semantics."""
     with torch11_masks():
         return loss(output, batch)
+
+
+def load_dataloader():
+    """The reference's mixed_utils.classification_dataloader module (unmodified), imported next to
+    mlp.model under the same shims.  Returns (opt, module)."""
+    if _state.get("dataloader") is not None:
+        return _state["opt"], _state["dataloader"]
+    opt, _ = load()
+    prefixes = ("utils", "mlp", "mixed_utils", "text_utils", "visual_utils", "resume", "moviegraphs")
+    saved_argv, saved_path = sys.argv, list(sys.path)
+    shadow = {k: sys.modules.pop(k) for k in list(sys.modules) if k.split(".")[0] in prefixes}
+    sys.modules.update(_state["modules"])
+    sys.argv = ["oracle"]
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        import mixed_utils.classification_dataloader as ref_dl  # noqa
+        import mixed_utils.mixed_features as ref_mf  # noqa
+        import utils.util_functions as ref_uf  # noqa
+        _state["dataloader"], _state["mixed_features"], _state["util_functions"] = ref_dl, ref_mf, ref_uf
+        _state["modules"] = {k: v for k, v in sys.modules.items() if k.split(".")[0] in prefixes}
+    finally:
+        sys.argv, sys.path[:] = saved_argv, saved_path
+        for k in list(sys.modules):
+            if k.split(".")[0] in prefixes:
+                del sys.modules[k]
+        sys.modules.update(shadow)
+    return opt, ref_dl
+
+
+def reference_dataset(world_split, world, mode, preset, **overrides):
+    """Run the reference's UNMODIFIED MixedFeaturesDataset.__init__ / cache() / init_relships() on a
+    synthetic annotation world (lirec_b200/mixed_utils/synthetic_world.py): only the file loaders the
+    constructor calls are replaced by functions that hand over the world, and the per-scene feature
+    holders are the reference's own MixedFeatures objects with their caches pre-filled (so no .npy
+    file is read or written)."""
+    import contextlib as _cl
+    import io
+    opt, dl = load_dataloader()
+    mf, uf = _state["mixed_features"], _state["util_functions"]
+    set_preset(preset, **overrides)
+    opt.text_dim, opt.visual_dim, opt.track_dim = world.text_dim, world.visual_dim, world.track_dim
+    opt.mlp_dim = world.text_dim + world.visual_dim + 2 * world.track_dim
+    opt.inter_class, opt.merged, opt.feature_type = "all", True, "m"
+    opt.multilab_weights = True
+    opt.rels = False
+    holders = {}
+
+    def make_holder(video_idx, scene_idx, fname):
+        h = mf.MixedFeatures.__new__(mf.MixedFeatures)
+        h.video_idx, h.scene_idx, h.fname = video_idx, scene_idx, fname
+        h.visual = h.textual = None
+        h.f_text = h.f_visual = None
+        h.cached, h.cached_tracks = {}, {}
+        for it in world_split["interactions"]:
+            if it.video_descr["movie"] == video_idx and it.video_descr["scene"][0] == scene_idx:
+                h.cached[it.id] = world_split["clip_vec"][it.id]
+                for p in it.id2names.values():
+                    h.cached_tracks[(it.id, p)] = world_split["track_vec"][(it.id, p)]
+        holders[(video_idx, scene_idx)] = h
+        return h
+
+    patches = dict(
+        load_interaction_names=lambda: (world.interaction_names, world.inter2idx),
+        load_merged_interactions=lambda: (world.inter2mgd, world.mgd2idx),
+        load_set=lambda mode=None: world_split["movie_idxs"],
+        load_annotated_inter=lambda movie_idxs=None, inter_class=None: (
+            (world_split["interactions"], world_split["rels"], world_split["rels_list"], world_split["rels_opp"])
+            if (opt.rels or opt.rels_multitask) else world_split["interactions"]),
+        load_iou2_clips=lambda: world.iou2_clips,
+        MixedFeatures=make_holder,
+        tqdm=lambda x, *a, **k: x,
+    )
+    saved = {k: getattr(dl, k) for k in patches}
+    for k, v in patches.items():
+        setattr(dl, k, v)
+    try:
+        with _cl.redirect_stdout(io.StringIO()):
+            ds = dl.MixedFeaturesDataset(mode=mode)
+            ds.cache()
+            if opt.rels or opt.rels_multitask:
+                ds.init_relships()
+    finally:
+        for k, v in saved.items():
+            setattr(dl, k, v)
+    return ds

@@ -14,7 +14,7 @@ def test_int_rel_ch_train_eval_checkpoint(tmp_path, opt_preset, monkeypatch):
                      save_model=True, save_model_often=False, store_root=str(tmp_path), resume=False,
                      resume_train=False, fused_adam=1, dp=0, lr=1e-3, tr_sum_max=False, rels_multi_clip=True)
     from lirec_b200.mixed_utils import classification_dataloader as cd
-    monkeypatch.setattr(cd.MixedFeaturesDataset, "SIZES", {"train": 48, "val": 24, "test": 24})
+    monkeypatch.setattr(cd.SyntheticClipsDataset, "SIZES", {"train": 48, "val": 24, "test": 24})
     import lirec_b200.mlp.model as M
     import lirec_b200.mlp.test as T
     import lirec_b200.mlp.train as TR

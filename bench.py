@@ -260,6 +260,74 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = clips_total / (float(t.item()) / 1e3)
 
+    # ---------------- end-to-end with HBM-resident dataset banks (index-only batches) ----------------
+    # Same loop, but the pooled feature vectors of the whole (synthetic) dataset — here the union of the
+    # rotating batches — were uploaded once, like the reference's dataset.cache(); every step copies only
+    # the packed integer tables, multi-label bits and two row-index lists, and gathers its banks on the
+    # device (lirec_gather_rows).  Reported next to `e2e`, which streams all features every step.
+    from lirec_b200.mixed_utils.indexed_dataset import ResidentBanks
+    banks = ResidentBanks(device=dev, clip=torch.cat([h.clip_bank for h in host]),
+                          track=torch.cat([h.track_bank for h in host]))
+    idx_host, c0, t0 = [], 0, 0
+    for h in host:
+        idx_host.append(h.without_banks(np.arange(c0, c0 + h.n_clip), np.arange(t0, t0 + h.n_track)).pin())
+        c0, t0 = c0 + h.n_clip, t0 + h.n_track
+    res_bytes = sum(ResidentBanks.h2d_bytes(h) for h in idx_host) / len(idx_host)
+
+    def prefetch_res(i):
+        with torch.cuda.stream(copy_stream):
+            pb = banks.stage(idx_host[i % len(idx_host)])
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return pb, ev
+
+    copy_stream.wait_stream(main)
+    for i in range(2):                                  # warm the gather kernel / allocator on the copy stream
+        pb, ev = prefetch_res(i)
+        main.wait_event(ev)
+        pb.record_stream(main)
+        step(pb)
+    barrier()
+    e0.record()
+    nxt = prefetch_res(0)
+    for i in range(args.steps):
+        pb, ev = nxt
+        main.wait_event(ev)
+        pb.record_stream(main)
+        if i + 1 < args.steps:
+            nxt = prefetch_res(i + 1)
+        lv = step(pb)
+        loss_host[i:i + 1].copy_(lv.detach().reshape(1), non_blocking=True)
+    e1.record()
+    barrier()
+    assert bool(torch.isfinite(loss_host).all()), "e2e (resident banks): non-finite loss read back"
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_res_value = clips_total / (float(t.item()) / 1e3)
+
+    # ---------------- inference: forward + device-side prediction arg-maxes (no_grad) ----------------
+    from lirec_b200 import ops
+    model.eval()
+    with torch.no_grad():
+        def infer(pb):
+            out = model(pb)
+            return ops.predict_tracks(out.ragged_inters, out.ragged_rels, pb["cand_off"], pb["labels"], pb["rels_label"],
+                                      pb["gt_tracks"], 15)
+        for i in range(3):
+            infer(resident[i % len(resident)])
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            infer(resident[i % len(resident)])
+        e1.record()
+        barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    infer_value = clips_total / (float(t.item()) / 1e3)
+    model.train()
+
     if rank != 0:
         return
     # ---------------- roofline of the dominant kernel (the tcgen05 GEMM) ----------------
@@ -308,6 +376,13 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(in_bytes),
                     "d2h_bytes_per_step": 4},
+            "e2e_resident_banks": {"value": e2e_res_value, "unit": "clips/s", "h2d_bytes_per_step": int(res_bytes),
+                                   "d2h_bytes_per_step": 4,
+                                   "note": "dataset feature banks uploaded once and kept in HBM; per step only index "
+                                           "tables cross PCIe and the batch banks are gathered on the device"},
+            "inference": {"value": infer_value, "unit": "clips/s",
+                          "what": "forward (eval, no_grad) + device-side track/class/relationship arg-maxes, inputs "
+                                  "resident in HBM"},
             "gpu_launches": int(launches),
             "roofline": roofline}
     if cpu is not None:

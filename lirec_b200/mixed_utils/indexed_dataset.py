@@ -498,12 +498,14 @@ class ResidentBanks:
     < 1 GB).  A step's host->device traffic is then the packed batch's integer tables plus two row-index
     lists; the per-batch banks the kernels read are gathered on the device (`lirec_gather_rows`)."""
 
-    def __init__(self, dataset, device="cuda"):
+    def __init__(self, dataset=None, device="cuda", clip=None, track=None):
         from lirec_b200 import _ext
         _ext.require_device(torch.device(device))
         self.device = torch.device(device)
-        self.clip = torch.from_numpy(dataset.clip_bank).to(torch.bfloat16).to(self.device)
-        self.track = torch.from_numpy(dataset.track_bank).to(torch.bfloat16).to(self.device)
+        if dataset is not None:
+            clip, track = torch.from_numpy(dataset.clip_bank), torch.from_numpy(dataset.track_bank)
+        self.clip = clip.to(torch.bfloat16).to(self.device)
+        self.track = track.to(torch.bfloat16).to(self.device)
 
     def stage(self, pb, non_blocking=True):
         """Host PackedBatch from `collate_indexed` -> device PackedBatch whose banks were gathered on the GPU."""

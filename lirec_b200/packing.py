@@ -177,6 +177,22 @@ class PackedBatch:
         d.host = self
         return d
 
+    def without_banks(self, clip_rows, track_rows):
+        """Host copy that shares the integer tables but carries no feature banks: `clip_rows` /
+        `track_rows` name the rows of HBM-resident dataset banks to gather on the device instead
+        (mixed_utils/indexed_dataset.py:ResidentBanks.stage)."""
+        assert self.device is None
+        d = PackedBatch()
+        for k in ("B", "n_slots", "n_ctx_slots", "n_classes", "has_ctx", "n_clip_ints", "n_track_ints", "multilab",
+                  "tables"):
+            setattr(d, k, getattr(self, k))
+        d.extras = dict(self.extras)
+        d.clip_bank = torch.empty((self.n_clip, 0), dtype=torch.bfloat16)
+        d.track_bank = torch.empty((self.n_track, 0), dtype=torch.bfloat16)
+        d.extras["bank_rows"] = (np.ascontiguousarray(clip_rows, dtype=np.int32),
+                                 np.ascontiguousarray(track_rows, dtype=np.int32))
+        return d
+
     def record_stream(self, stream):
         """Tell the caching allocator that `stream` uses this batch's device tensors (they may have been
         allocated on a copy stream)."""

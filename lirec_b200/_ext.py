@@ -126,6 +126,9 @@ def lib():
                                         Dropout, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     L.lirec_split_f32.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
                                   C.c_int32, C.c_void_p]
+    L.lirec_roi_max_pool_f32.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                         C.c_void_p]
     L.lirec_gather_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_void_p, C.c_int64, C.c_void_p]
     L.lirec_cast_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
@@ -156,7 +159,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "lirec_abi_version", "lirec_last_error", "lirec_device_check", "lirec_dropout_keep_host", "lirec_last_launch_count",
     "lirec_gemm_grouped", "lirec_profile_begin", "lirec_profile_end", "lirec_seg_reduce_f32", "lirec_rows_expand_fwd", "lirec_rows_expand_bwd",
-    "lirec_split_f32", "lirec_cast_bf16", "lirec_gather_rows", "lirec_loss_track_fwd_bwd", "lirec_loss_rowmargin_fwd_bwd", "lirec_predict_tracks",
+    "lirec_split_f32", "lirec_cast_bf16", "lirec_gather_rows", "lirec_roi_max_pool_f32", "lirec_loss_track_fwd_bwd", "lirec_loss_rowmargin_fwd_bwd", "lirec_predict_tracks",
     "lirec_model_workspace_bytes", "lirec_model_workspace_layout", "lirec_model_forward", "lirec_model_backward", "lirec_adam_flat",
 ]
 

@@ -401,6 +401,60 @@ cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, i
 }
 
 // ---------------------------------------------------------------------------
+// Spatial / ROI mean of I3D feature maps fused with the temporal max over a segment of elements:
+//   out[s, c] = max_{e in seg s} mean_{y0<=y<y1, x0<=x<x1} maps[frame_e, c, y, x]
+// Reference: clip visual = np.max over frames of the H x W mean (visual_features.py:67-69,
+// mixed_features.py:54); person track = np.max over track elements of the mean over the person box
+// derived from the face box (visual_features.py:105-135, mixed_features.py:104-105).  The reference
+// quirks are kept: an element with frame < 0 (frame index == T, :130-131) is an all-zero row that
+// still takes part in the max; an empty box averages nothing and gives NaN, which np.max propagates;
+// an empty segment gives zeros (mixed_features.py:89-93).
+// One warp owns one (segment, channel): lanes stride over the flattened box of one H x W plane (a
+// contiguous <= 2 KB region), a shuffle tree sums the lanes, and the running max lives in lane 0.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+roi_max_pool_kernel(const float* __restrict__ maps, int C, int HW, int W, const int32_t* __restrict__ elem,
+                    const int32_t* __restrict__ seg_off, float* __restrict__ out_f32, int64_t out_f32_ld,
+                    __nv_bfloat16* __restrict__ out_bf16, int64_t out_bf16_ld) {
+  const int seg = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.y * (blockDim.x >> 5) + warp;
+  if (c >= C) return;
+  const int beg = seg_off[seg], end = seg_off[seg + 1];
+  float best = 0.f;
+  bool first = true;
+  for (int e = beg; e < end; ++e) {
+    const int32_t* el = elem + 5 * static_cast<int64_t>(e);
+    const int frame = el[0], y0 = el[1], y1 = el[2], x0 = el[3], x1 = el[4];
+    float v = 0.f;
+    if (frame >= 0) {
+      const int w = x1 - x0, h = y1 - y0;
+      const int n = (w > 0 && h > 0) ? w * h : 0;
+      const float* plane = maps + (static_cast<int64_t>(frame) * C + c) * HW;
+      float acc = 0.f;
+      if (w == W) {                                   // full-width box: one contiguous run
+        const float* p = plane + y0 * W;
+        for (int i = lane; i < n; i += 32) acc += p[i];
+      } else {
+        for (int i = lane; i < n; i += 32) {
+          const int yy = i / w, xx = i - yy * w;
+          acc += plane[(y0 + yy) * W + x0 + xx];
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      v = (n > 0) ? acc / static_cast<float>(n) : __int_as_float(0x7fc00000);
+    }
+    if (first || v > best || v != v) best = (best != best) ? best : v;   // NaN sticks, like np.max
+    first = false;
+  }
+  if (lane == 0) {
+    if (out_f32) out_f32[static_cast<int64_t>(seg) * out_f32_ld + c] = best;
+    if (out_bf16) out_bf16[static_cast<int64_t>(seg) * out_bf16_ld + c] = __float2bfloat16_rn(best);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Row gather: out[i, :] = bank[idx[i], :] (bf16 rows, 16-byte column groups).  Builds the per-batch
 // feature banks from dataset banks that stay resident in HBM; one warp-wide 128-bit load and store
 // per 512 bytes of row, grid-strided over (row, column-group) pairs so short rows still fill the SMs.
@@ -422,6 +476,20 @@ gather_rows_kernel(const uint4* __restrict__ bank, int64_t bank_ld16, int n_bank
 // ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
+int roi_max_pool(const float* maps, int T, int C, int H, int W, const int32_t* elem, const int32_t* seg_off, int nseg,
+                 float* out_f32, int64_t out_f32_ld, void* out_bf16, int64_t out_bf16_ld, cudaStream_t stream) {
+  LIREC_REQUIRE(maps && elem && seg_off, "roi_max_pool: null argument");
+  LIREC_REQUIRE(T > 0 && C > 0 && H > 0 && W > 0, "roi_max_pool: maps [%d, %d, %d, %d]", T, C, H, W);
+  LIREC_REQUIRE(out_f32 || out_bf16, "roi_max_pool: no output");
+  if (nseg <= 0) return LIREC_OK;
+  dim3 grid(nseg, (C + 7) / 8);
+  roi_max_pool_kernel<<<grid, 256, 0, stream>>>(maps, C, H * W, W, elem, seg_off, out_f32, out_f32_ld,
+                                                reinterpret_cast<__nv_bfloat16*>(out_bf16), out_bf16_ld);
+  LIREC_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return LIREC_OK;
+}
+
 int gather_rows(const void* bank, int64_t bank_ld, int n_bank, const int32_t* idx, int n, int dim, void* out,
                 int64_t out_ld, cudaStream_t stream) {
   LIREC_REQUIRE(dim > 0 && dim % 8 == 0 && bank_ld % 8 == 0 && out_ld % 8 == 0,
@@ -615,6 +683,14 @@ extern "C" int lirec_rows_expand_bwd(const float* d_in, int64_t d_ld, const floa
   j.out_ld = out_ld;
   j.out_t_pitch = out_t_pitch;
   return rows::expand_bwd(jobs, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lirec_roi_max_pool_f32(const float* maps, int32_t T, int32_t C, int32_t H, int32_t W,
+                                      const int32_t* elem, const int32_t* seg_off, int32_t nseg, float* out_f32,
+                                      int64_t out_f32_ld, void* out_bf16, int64_t out_bf16_ld, void* stream) {
+  LIREC_ENTER();
+  return rows::roi_max_pool(maps, T, C, H, W, elem, seg_off, nseg, out_f32, out_f32_ld, out_bf16, out_bf16_ld,
+                            static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int lirec_gather_rows(const void* bank, int64_t bank_ld, int32_t n_bank, const int32_t* idx, int32_t n,

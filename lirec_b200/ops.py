@@ -12,7 +12,7 @@ from ._ext import (ACT_NONE, ACT_RELU, ACT_TANH, OUT_F32, OUT_SPLIT, OUT_SPLIT_T
                    POST_NONE)
 
 __all__ = ["gemm_problem", "gemm_grouped", "seg_reduce", "rows_expand_fwd", "rows_expand_bwd", "split_f32",
-           "cast_bf16", "gather_rows", "loss_track", "loss_rowmargin", "predict_tracks", "adam_flat", "dropout_desc"]
+           "cast_bf16", "gather_rows", "roi_max_pool", "loss_track", "loss_rowmargin", "predict_tracks", "adam_flat", "dropout_desc"]
 
 
 def dropout_desc(p=0.0, seed=0, stream_id=0, col_off=0):
@@ -97,6 +97,22 @@ def split_f32(x, out_split, pad_cols):
 def cast_bf16(x, out):
     L = _ext.lib()
     _ext.check(L.lirec_cast_bf16(_ext.ptr(x), _ext.ptr(out), x.numel(), _ext.stream_ptr()))
+
+
+def roi_max_pool(maps, elem, seg_off, out_f32=None, out_bf16=None):
+    """out[s, c] = max_{e in segment s} mean(maps[frame_e, c, y0:y1, x0:x1]) (lirec_roi_max_pool_f32).
+    maps fp32 [T, C, H, W]; elem int32 [n, 5]; seg_off int32 [nseg + 1]."""
+    assert maps.dtype == torch.float32 and maps.dim() == 4 and maps.is_contiguous()
+    assert elem.dtype == torch.int32 and seg_off.dtype == torch.int32 and elem.is_contiguous()
+    T, Cc, H, W = maps.shape
+    nseg = seg_off.numel() - 1
+    if out_f32 is None and out_bf16 is None:
+        out_f32 = torch.empty(nseg, Cc, dtype=torch.float32, device=maps.device)
+    _ext.check(_ext.lib().lirec_roi_max_pool_f32(
+        _ext.ptr(maps), T, Cc, H, W, _ext.ptr(elem), _ext.ptr(seg_off), nseg,
+        _ext.ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
+        _ext.ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, _ext.stream_ptr()))
+    return out_f32 if out_f32 is not None else out_bf16
 
 
 def gather_rows(bank, idx, out=None):

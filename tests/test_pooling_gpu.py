@@ -1,0 +1,73 @@
+"""Fused spatial / person-box mean + temporal max on the GPU (lirec_roi_max_pool_f32) against the rows
+the reference's unmodified VisualFeatures produced (tests/golden/pooling_visual.npz): the means within
+2e-6 relative (a different float32 summation order than numpy's pairwise sum), the max an exact
+selection of them, NaN / zero-row / empty-track quirks identical."""
+import numpy as np
+import pytest
+import torch
+
+from test_pooling_cpu import load_world, numpy_rows
+
+pytestmark = pytest.mark.gpu
+RTOL = 2e-6
+
+
+def test_visual_pooling_matches_the_reference(opt_preset):
+    from lirec_b200.utils.arg_pars import opt
+    from lirec_b200.visual_utils.visual_features import VisualFeatures
+    opt.sampling_fr = 0.0625
+    g, meta, feats, frame2time, dims = load_world()
+    v = VisualFeatures(feats, frame2time, dims, device="cuda")
+    for i, tn in enumerate(meta["time_nodes"]):
+        rows = v.get_features_by_time(tn).cpu().numpy()
+        np.testing.assert_allclose(rows, g["time_rows_%d" % i], rtol=RTOL, atol=0)
+    for i, tr in enumerate(meta["tracks"]):
+        if not tr:
+            continue
+        rows = v.get_features_by_track(tr).cpu().numpy()
+        ref = g["track_rows_%d" % i]
+        assert np.array_equal(np.isnan(rows), np.isnan(ref))
+        np.testing.assert_allclose(rows, ref, rtol=RTOL, atol=0)
+    # one launch for every clip and track of the scene; bf16 bank rows
+    pooled = v.pool(meta["time_nodes"], meta["tracks"]).cpu().numpy()
+    nt = len(meta["time_nodes"])
+    for i in range(nt):
+        np.testing.assert_allclose(pooled[i:i + 1], g["time_max_%d" % i], rtol=RTOL, atol=0)
+    for i in range(len(meta["tracks"])):
+        ref = g["track_max_%d" % i]
+        got = pooled[nt + i:nt + i + 1]
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), i
+        np.testing.assert_allclose(got, ref, rtol=RTOL, atol=0)
+    assert not pooled[nt + len(meta["tracks"]) - 1].any()          # the empty track
+    bank = torch.empty(pooled.shape[0], pooled.shape[1], dtype=torch.bfloat16, device="cuda")
+    v.pool(meta["time_nodes"], meta["tracks"], out_bf16=bank)
+    ref16 = torch.from_numpy(pooled).to(torch.bfloat16)
+    assert torch.equal(torch.nan_to_num(bank.cpu().float(), nan=-1.0), torch.nan_to_num(ref16.float(), nan=-1.0))
+
+
+def test_roi_pool_full_size_maps_against_numpy():
+    """I3D-sized maps [T, 2048, 13, 30]: random boxes, ragged segments, max is an exact selection."""
+    from lirec_b200 import ops
+    rng = np.random.RandomState(0)
+    T, C, H, W = 6, 2048, 13, 30
+    feats = np.abs(rng.standard_normal((T, C, H, W))).astype(np.float32)
+    n = 40
+    el = np.zeros((n, 5), dtype=np.int32)
+    el[:, 0] = rng.randint(0, T, n)
+    el[:, 1] = rng.randint(0, H - 1, n)
+    el[:, 2] = el[:, 1] + 1 + rng.randint(0, H, n)
+    el[:, 2] = np.minimum(el[:, 2], H)
+    el[:, 3] = rng.randint(0, W - 1, n)
+    el[:, 4] = np.minimum(el[:, 3] + 1 + rng.randint(0, W, n), W)
+    el[5] = (2, 0, H, 0, W)
+    el[9, 0] = -1
+    seg = np.array([0, 1, 1, 7, 20, 40], dtype=np.int32)
+    rows = numpy_rows(feats, el)
+    ref = np.stack([rows[a:b].max(axis=0) if b > a else np.zeros(C) for a, b in zip(seg[:-1], seg[1:])])
+    maps = torch.from_numpy(feats).cuda()
+    out = ops.roi_max_pool(maps, torch.from_numpy(el).cuda(), torch.from_numpy(seg).cuda()).cpu().numpy()
+    np.testing.assert_allclose(out, ref, rtol=RTOL, atol=0)
+    per = ops.roi_max_pool(maps, torch.from_numpy(el).cuda(),
+                           torch.arange(n + 1, dtype=torch.int32).cuda()).cpu().numpy()
+    sel = np.stack([per[a:b].max(axis=0) if b > a else np.zeros(C, dtype=np.float32) for a, b in zip(seg[:-1], seg[1:])])
+    assert np.array_equal(out, sel)                                   # max = exact selection of the means

@@ -392,10 +392,17 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE JSON line: library chatter written to fd 1 while the job runs (NCCL prints
+    # its version banner there) is routed to stderr, and the line is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
     try:
         import torch.distributed as dist
         if dist.is_initialized():

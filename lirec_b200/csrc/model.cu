@@ -198,14 +198,31 @@ struct ReduceJobs {
   ReduceJob job[MAX_REDUCE_JOBS];
   int32_t n;
 };
+// One thread sums one group of four consecutive elements over the S partial slices (S independent
+// 128-bit loads in flight), so the big first-layer jobs stream at HBM rate; blockIdx.y selects the job
+// and CTAs beyond a job's size exit at once.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceJobs jobs) {
   const ReduceJob& j = jobs.job[blockIdx.y];
   const int64_t total = (int64_t)j.M * j.N;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    float acc = 0.f;
-    for (int s = 0; s < j.S; ++s) acc += j.src[(int64_t)s * total + i];
+  const bool vec = (j.N % 4 == 0) && (j.dst_ld % 4 == 0) && (total % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(j.src) | reinterpret_cast<uintptr_t>(j.dst)) & 15) == 0;
+  if (vec) {
+    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
+    if (i >= total) return;
+    float4 acc = *reinterpret_cast<const float4*>(j.src + i);
+    for (int s = 1; s < j.S; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(j.src + (int64_t)s * total + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
     const int m = (int)(i / j.N), n = (int)(i - (int64_t)m * j.N);
-    j.dst[(int64_t)m * j.dst_ld + n] = acc;
+    *reinterpret_cast<float4*>(j.dst + (int64_t)m * j.dst_ld + n) = acc;
+  } else {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      float acc = 0.f;
+      for (int s = 0; s < j.S; ++s) acc += j.src[(int64_t)s * total + i];
+      const int m = (int)(i / j.N), n = (int)(i - (int64_t)m * j.N);
+      j.dst[(int64_t)m * j.dst_ld + n] = acc;
+    }
   }
 }
 
@@ -661,7 +678,7 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
   if (sc.jobs.n > 0) {
     int64_t biggest = 0;
     for (int i = 0; i < sc.jobs.n; ++i) biggest = std::max<int64_t>(biggest, (int64_t)sc.jobs.job[i].M * sc.jobs.job[i].N);
-    dim3 grid((unsigned)std::min<int64_t>((biggest + 255) / 256, 296), sc.jobs.n);
+    dim3 grid((unsigned)((biggest + 1023) / 1024), sc.jobs.n);
     reduce_partials_kernel<<<grid, 256, 0, stream>>>(sc.jobs);
     LIREC_CUDA_OK(cudaGetLastError());
     note_launch();

@@ -195,7 +195,11 @@ expand_bwd_kernel(const ExpandBwdJobs jobs) {
 // ---------------------------------------------------------------------------
 constexpr int EBT_ROWS = 64;
 constexpr int EBT_COLS = 64;
-constexpr int EBT_REFS = 1536;   // references cached in shared memory per CTA (the rest is read in place)
+constexpr int EBT_REFS = 1536;
+#ifndef LIREC_EBT_ZSPLIT
+#define LIREC_EBT_ZSPLIT 4
+#endif
+constexpr int EBT_ZSPLIT = LIREC_EBT_ZSPLIT;   // references cached in shared memory per CTA (the rest is read in place)
 __global__ void __launch_bounds__(256)
 expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
   const ExpandBwdJob& jb = jobs.job[blockIdx.y];
@@ -228,7 +232,11 @@ expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
   int beg = 0, end = 0;
   if (live) { beg = jb.inv_off[u]; end = jb.inv_off[u + 1]; }
   const uint32_t thr = drop_threshold(jb.drop.p);
-  for (int c0 = 0; c0 < J; c0 += EBT_COLS) {
+  // blockIdx.z takes a slice of the column chunks: more, shorter CTAs fill the last wave of the ragged
+  // job list (the ints-branch jobs have 10x fewer unique rows than the context-branch ones)
+  const int c_per = ((J / EBT_COLS + gridDim.z - 1) / gridDim.z) * EBT_COLS;
+  const int c_beg = blockIdx.z * c_per, c_end = min(J, c_beg + c_per);
+  for (int c0 = c_beg; c0 < c_end; c0 += EBT_COLS) {
     float acc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.f;
@@ -563,7 +571,9 @@ int expand_bwd(const ExpandBwdJobs& jobs, cudaStream_t stream) {
                         (reinterpret_cast<uintptr_t>(j.out) & 15) == 0,
                     "expand_bwd: transposed output needs J %% 64 == 0 and a 16-byte aligned pitch");
     }
-    dim3 grid((max_u + EBT_ROWS - 1) / EBT_ROWS, jobs.n);
+    int max_j = 0;
+    for (int i = 0; i < jobs.n; ++i) max_j = std::max(max_j, jobs.job[i].J);
+    dim3 grid((max_u + EBT_ROWS - 1) / EBT_ROWS, jobs.n, std::max(1, std::min(EBT_ZSPLIT, max_j / EBT_COLS)));
     expand_bwd_t_kernel<<<grid, 256, 0, stream>>>(jobs);
   } else {
     dim3 grid(max_u, jobs.n);

@@ -70,7 +70,7 @@ def encode(sd, branch, x, cfg, masks):
 
 
 def gating_unit(sd, feat_ints, feat_ctx, cfg, masks):
-    z = torch.cat((feat_ctx, feat_ints), dim=-1)               # (rels, inters) order: model.py:352
+    z = _tape(cfg, "gate_in", torch.cat((feat_ctx, feat_ints), dim=-1))   # (rels, inters) order: model.py:352
     z = torch.relu(_tape(cfg, "pre_gate", _lin(sd, "gates_ints.fc_out", z)))
     return _drop(z, masks, ("gate",), cfg.dropout)             # dropout(relu(.)): model.py:353
 

@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--cpu_clips", type=int, default=64, help="clips per CPU-baseline step (bounded sample)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--dump_profile", default="", help="write the per-launch GEMM event timings to this file")
+    ap.add_argument("--nccl_allreduce", action="store_true",
+                    help="N > 1: use ncclAllReduce + Adam instead of the fused in-switch reduce + Adam kernel")
     ap.add_argument("--ncu_window", action="store_true",
                     help="bracket the device-resident timed loop with cudaProfilerStart/Stop "
                          "(run under `ncu --profile-from-start off`; numbers printed under ncu are not bench values)")
@@ -172,6 +174,7 @@ def run_ours(args):
         model, loss_fn, optimizer = M.create_model(101, n_rels=15)
     model.train()
     dp.broadcast_params(model._flat)
+    fused = None if (world == 1 or args.nccl_allreduce) else dp.SwitchReduceAdam.attach(model, optimizer)
 
     # distinct synthetic batches per rank (seeded 1000*rank + i), pinned on the host
     host = [synthetic.make_batch(args.batch, seed=1000 * rank + i, preset=args.preset).pin()
@@ -185,8 +188,7 @@ def run_ours(args):
         lv = loss_fn(out, {})
         optimizer.zero_grad()
         lv.backward()
-        scale = dp.allreduce_flat_grad(model._flat_grad) if world > 1 else 1.0
-        optimizer.step(grad_scale=scale)
+        dp.reduce_and_step(model, optimizer, fused)
         return lv
 
     def barrier():
@@ -370,6 +372,9 @@ def run_ours(args):
                        "clips_per_gpu": args.batch, "global_batch": args.batch * world,
                        "candidate_rows_per_step": float(nc), "context_rows_per_step": float(nx),
                        "parallelism": "dp%d" % world, "optimizer": "fused flat Adam",
+                       "gradient_exchange": ("none (1 GPU)" if world == 1 else
+                                             "in-switch multimem reduce fused with Adam (lirec_dp_allreduce_adam)"
+                                             if fused is not None else "ncclAllReduce fp32 + Adam"),
                        "precision": "bf16 operands, hi/lo split activations, fp32 accumulate",
                        "l2": "inputs+workspace per step exceed L2 (%d distinct batches of %.0f MB rotate)" % (
                            len(host), in_bytes / 1e6)},

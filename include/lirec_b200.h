@@ -350,6 +350,23 @@ int lirec_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_
                     void* param_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int32_t step, float grad_scale, void* stream);
 
+/* ---- data parallel: gradient sum over ranks fused with the Adam step ------
+ * One launch per rank per step replaces ncclAllReduce(flat gradient) + lirec_adam_flat.  `grad` is this
+ * rank's flat fp32 gradient buffer in SYMMETRIC memory and `grad_multicast` the NVSwitch multicast
+ * address of the same buffer (lirec_b200/dp.py obtains both from torch.distributed._symmetric_memory).
+ * Each rank reduces its 1/world shard inside the switch (multimem.ld_reduce.add) and broadcasts the sum
+ * (multimem.st), so `grad` holds the SUM over ranks afterwards; then Adam runs with grad * grad_scale
+ * (1/world for equal shards).  flag_ptrs_dev: device array [world] of every rank's peer-mapped flag
+ * buffer (>= 2*world zero-initialised uint32); sync_ws: 3 zero-initialised local uint32; epoch = 1, 2, ...
+ * per call.  The reference has no counterpart (single process); optimizer semantics are
+ * torch.optim.Adam's (mlp/model.py:599-601).                                                   */
+int lirec_dp_grid_size(void);
+int lirec_dp_allreduce_adam(float* param, float* grad, void* grad_multicast, float* exp_avg,
+                            float* exp_avg_sq, void* param_bf16, int64_t n, float lr, float beta1,
+                            float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                            int32_t rank, int32_t world, const void* flag_ptrs_dev, void* sync_ws,
+                            uint32_t epoch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

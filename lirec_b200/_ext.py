@@ -142,6 +142,9 @@ def lib():
                                        C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     L.lirec_adam_flat.argtypes = [C.c_void_p] * 5 + [C.c_int64] + [C.c_float] * 5 + [C.c_int32, C.c_float,
                                                                                   C.c_void_p]
+    L.lirec_dp_grid_size.restype = C.c_int
+    L.lirec_dp_allreduce_adam.argtypes = [C.c_void_p] * 6 + [C.c_int64] + [C.c_float] * 5 + [
+        C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.lirec_model_workspace_bytes.argtypes = [C.c_void_p, C.c_void_p]
     L.lirec_model_workspace_bytes.restype = C.c_size_t
     L.lirec_profile_end.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -160,7 +163,7 @@ EXPORTED_SYMBOLS = [
     "lirec_abi_version", "lirec_last_error", "lirec_device_check", "lirec_dropout_keep_host", "lirec_last_launch_count",
     "lirec_gemm_grouped", "lirec_profile_begin", "lirec_profile_end", "lirec_seg_reduce_f32", "lirec_rows_expand_fwd", "lirec_rows_expand_bwd",
     "lirec_split_f32", "lirec_cast_bf16", "lirec_gather_rows", "lirec_roi_max_pool_f32", "lirec_loss_track_fwd_bwd", "lirec_loss_rowmargin_fwd_bwd", "lirec_predict_tracks",
-    "lirec_model_workspace_bytes", "lirec_model_workspace_layout", "lirec_model_forward", "lirec_model_backward", "lirec_adam_flat",
+    "lirec_model_workspace_bytes", "lirec_model_workspace_layout", "lirec_model_forward", "lirec_model_backward", "lirec_adam_flat", "lirec_dp_grid_size", "lirec_dp_allreduce_adam",
 ]
 
 # kernels launched through this binding since import (bench.py reports it as gpu_launches)

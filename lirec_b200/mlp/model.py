@@ -170,6 +170,17 @@ class _HotPath(nn.Module):
         self._versions = None
         self._build_structs()
 
+    def use_grad_buffer(self, buf):
+        """Adopt `buf` (flat fp32, same size) as the gradient buffer — e.g. symmetric memory for the
+        in-switch data-parallel reduction (lirec_b200/dp.py:SwitchReduceAdam)."""
+        self._sync_flat()
+        assert buf.dtype == torch.float32 and buf.numel() == self._flat.numel() and buf.device == self._flat.device
+        buf.copy_(self._flat_grad)
+        self._flat_grad = buf
+        for p in self._param_list:
+            p.grad = None
+        self._build_structs()
+
     def _grad_view(self, i):
         p, off = self._param_list[i], self._offsets[i]
         return self._flat_grad[off:off + p.numel()].view(p.shape)

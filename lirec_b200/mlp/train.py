@@ -21,22 +21,18 @@ from lirec_b200.utils.model_saver import ModelSaver
 from lirec_b200.utils.util_functions import Averaging, dir_check
 
 
-def train_step(model, loss, optimizer, pb, world=1):
-    """One optimisation step on a device PackedBatch; returns the (device) loss tensor."""
+def train_step(model, loss, optimizer, pb, world=1, fused=None):
+    """One optimisation step on a device PackedBatch; returns the (device) loss tensor.  `fused`: the
+    in-switch reduce+Adam of dp.SwitchReduceAdam.attach (None: NCCL all_reduce, then the optimizer)."""
     output = model(pb)
     loss_values = loss(output, {})
     optimizer.zero_grad()
     loss_values.backward()
-    scale = 1.0
+    local = global_clips = None
     if world > 1:
         local = pb.B
         global_clips = getattr(pb.host, "global_clips", None) if getattr(pb, "host", None) is not None else None
-        scale = dp.allreduce_flat_grad(model._flat_grad, local, global_clips,
-                                       average_in_place=not hasattr(optimizer, "model"))
-    if hasattr(optimizer, "model"):          # FlatAdam folds the 1/world average into the kernel
-        optimizer.step(grad_scale=scale)
-    else:
-        optimizer.step()
+    dp.reduce_and_step(model, optimizer, fused, local, global_clips)
     return loss_values
 
 
@@ -44,11 +40,13 @@ def training(train_dataset, **kwargs):
     train_start_time = datetime.now().strftime("%Y%m%d-%H%M%S")
     print("set parameters and model, train start time: %s" % train_start_time)
     model, loss, optimizer = kwargs["model"], kwargs["loss"], kwargs["optimizer"]
-    rank, world = 0, 1
+    rank, world, fused = 0, 1, None
     if getattr(opt, "dp", 0):
         rank, world, _ = dp.init_from_env()
         model._sync_flat()
         dp.broadcast_params(model._flat)
+        if int(getattr(opt, "dp_switch_reduce", 1)):
+            fused = dp.SwitchReduceAdam.attach(model, optimizer)     # None without NVSwitch multicast / FlatAdam
     batch_time, data_time, losses = Averaging(), Averaging(), Averaging()
     print("epochs: %s", opt.epochs)
     model_saver_val = ModelSaver(path=opt.store_root)
@@ -70,7 +68,7 @@ def training(train_dataset, **kwargs):
             data_time.update(time.time() - end)
             if getattr(pb.host, "global_clips", pb.B) == 1:
                 continue
-            loss_values = train_step(model, loss, optimizer, pb, world)
+            loss_values = train_step(model, loss, optimizer, pb, world, fused)
             counter += pb.B
             if i % 10 == 0:
                 losses.update(loss_values.item(), pb.B)      # device->host sync only here

@@ -12,7 +12,7 @@ from ._ext import (ACT_NONE, ACT_RELU, ACT_TANH, OUT_F32, OUT_SPLIT, OUT_SPLIT_T
                    POST_NONE)
 
 __all__ = ["gemm_problem", "gemm_grouped", "seg_reduce", "rows_expand_fwd", "rows_expand_bwd", "split_f32",
-           "cast_bf16", "gather_rows", "roi_max_pool", "loss_track", "loss_rowmargin", "predict_tracks", "adam_flat", "dropout_desc"]
+           "cast_bf16", "gather_rows", "roi_max_pool", "loss_track", "loss_rowmargin", "predict_tracks", "adam_flat", "dp_allreduce_adam", "dropout_desc"]
 
 
 def dropout_desc(p=0.0, seed=0, stream_id=0, col_off=0):
@@ -176,3 +176,14 @@ def adam_flat(param, grad, exp_avg, exp_avg_sq, param_bf16, lr, beta1, beta2, ep
                                  _ext.ptr(param_bf16), param.numel(), float(lr), float(beta1), float(beta2),
                                  float(eps), float(weight_decay), int(step), float(grad_scale),
                                  _ext.stream_ptr()))
+
+
+def dp_allreduce_adam(param, grad, grad_multicast_ptr, exp_avg, exp_avg_sq, param_bf16, lr, beta1, beta2, eps,
+                      weight_decay, step, grad_scale, rank, world, flag_ptrs_dev, sync_ws, epoch):
+    """In-switch gradient sum over ranks + Adam in one launch (lirec_dp_allreduce_adam)."""
+    L = _ext.lib()
+    _ext.check(L.lirec_dp_allreduce_adam(
+        _ext.ptr(param), _ext.ptr(grad), C.c_void_p(int(grad_multicast_ptr)), _ext.ptr(exp_avg), _ext.ptr(exp_avg_sq),
+        _ext.ptr(param_bf16), param.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
+        int(step), float(grad_scale), int(rank), int(world), C.c_void_p(int(flag_ptrs_dev)), _ext.ptr(sync_ws),
+        int(epoch), _ext.stream_ptr()))

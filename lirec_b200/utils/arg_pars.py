@@ -101,6 +101,8 @@ _FLAGS = [
     ("--sanity_check", dict(default=False)),
     # ---- B200: flags added by this implementation (defaults keep reference behaviour) ----
     ("--dp", dict(default=0, type=int, help="1: data-parallel over clips, NCCL gradient allreduce")),
+    ("--dp_switch_reduce", dict(default=1, type=int, help="1: with --dp and --fused_adam, reduce gradients inside the "
+                                                          "NVSwitch fused with Adam (falls back to NCCL without multicast)")),
     ("--fused_adam", dict(default=0, type=int, help="1: flat fused Adam kernel instead of torch.optim.Adam")),
     ("--max_n_tripl", dict(default=20, type=int, help="candidate slots per clip (reference hard-codes 20)")),
     ("--synthetic", dict(default=0, type=int, help="1: independent synthetic MovieGraphs-shaped clips; 2: synthetic "

@@ -233,6 +233,9 @@ typedef struct lirec_track_loss_cfg {
   int32_t tr_correct;  /* supervised assignment (t* = 0)                     */
   int32_t max_neg;     /* opt.tr_max_neg && opt.tr_sum_max_flag              */
   int32_t max_slots;   /* T: reference slot count, only used by max_neg      */
+  int32_t cat_distr;   /* opt.tr_cat_distr: sample t* from the softmax scores
+                          (model.py:468-471, 538-543) instead of the arg-max   */
+  uint32_t seed;       /* counter-hash seed of that draw (per step)           */
 } lirec_track_loss_cfg;
 
 /* MarginLoss (model.py:444-494) when n_rels == 0, MarginTrackRelsLoss
@@ -245,6 +248,13 @@ int lirec_loss_track_fwd_bwd(const float* ints, const float* rels, const int32_t
                              const int32_t* gt_tracks, const uint8_t* multilab,
                              lirec_track_loss_cfg cfg, float* loss_per_clip, int32_t* assign,
                              float* d_ints, float* d_rels, void* stream);
+
+/* Softmax cross-entropy rows, forward + gradient: either term of MultiTaskCrossEntropyLoss
+ * (model.py:357-378, F.cross_entropy with optional class weights).  rows with label < 0 are
+ * skipped; scale = 1 / (sum of class weights of the selected rows) gives the mean reduction.  */
+int lirec_loss_ce_fwd_bwd(const float* logits, int64_t ld, int32_t rows, int32_t C,
+                          const int32_t* labels, const float* class_weights, float scale,
+                          float* loss_per_row, float* d_logits, int64_t d_ld, void* stream);
 
 /* MaxMarginCrossEntropyLoss (model.py:422-441) and the two terms of
  * MultiTaskMaxMargin (model.py:381-419): a row-wise hinge

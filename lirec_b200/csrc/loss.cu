@@ -71,8 +71,47 @@ track_loss_kernel(const float* __restrict__ ints, const float* __restrict__ rels
     }
     s_score[t] = sc;
   }
+  // ---- tr_cat_distr: the assignment is SAMPLED from (softmax_t(ints[t,y]) + softmax_t(rels[t,r0])) / 2
+  // (model.py:468-471, 538-543; a relationship column that is -inf everywhere gives NaN -> 0 there).
+  // The uniform draw comes from the counter hash of (seed, clip), mirrored by oracle/dropout.py.
+  if (cfg.cat_distr && !cfg.tr_correct) {
+    __shared__ float s_p[MAX_SLOTS];
+    if (threadIdx.x == 0) {
+      float mx = -INFINITY, mxr = -INFINITY;
+      for (int t = 0; t < n; ++t) {
+        mx = fmaxf(mx, xi[static_cast<int64_t>(t) * C + y]);
+        if (has_rels && r0 < R && rels_label[beg + t] != R) mxr = fmaxf(mxr, xr[static_cast<int64_t>(t) * R + r0]);
+      }
+      float zi = 0.f, zr = 0.f;
+      for (int t = 0; t < n; ++t) {
+        zi += expf(xi[static_cast<int64_t>(t) * C + y] - mx);
+        if (has_rels && r0 < R && rels_label[beg + t] != R) zr += expf(xr[static_cast<int64_t>(t) * R + r0] - mxr);
+      }
+      float total = 0.f;
+      for (int t = 0; t < n; ++t) {
+        float pt = expf(xi[static_cast<int64_t>(t) * C + y] - mx) / zi;
+        if (has_rels) {
+          float pr = 0.f;
+          if (r0 < R && rels_label[beg + t] != R && zr > 0.f) pr = expf(xr[static_cast<int64_t>(t) * R + r0] - mxr) / zr;
+          pt = 0.5f * (pt + pr);
+        }
+        s_p[t] = pt;
+        total += pt;
+      }
+      const uint32_t h = fmix32(cfg.seed ^ fmix32(static_cast<uint32_t>(b) + 0x51ED270Bu));
+      const float u = static_cast<float>(h >> 8) * (1.0f / 16777216.0f) * total;
+      float acc = 0.f;
+      int pick = n - 1;
+      for (int t = 0; t < n; ++t) {
+        acc += s_p[t];
+        if (u < acc) { pick = t; break; }
+      }
+      s_tstar = pick;
+      assign[b] = pick;
+    }
+  }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && !(cfg.cat_distr && !cfg.tr_correct)) {
     int best = 0;
     if (!cfg.tr_correct) {
       float bv = s_score[0];
@@ -227,6 +266,40 @@ rowmargin_kernel(const float* __restrict__ logits, int64_t ld, int rows, int C,
 }
 
 
+// Row-wise softmax cross-entropy, forward + gradient: both terms of MultiTaskCrossEntropyLoss
+// (model.py:357-378; F.cross_entropy with optional class weights, mean reduction).  The caller passes
+// scale = 1 / sum_i w[y_i] over the selected rows; rows with label < 0 are skipped.
+//   loss_row = scale * w[y] * (logsumexp(x) - x[y]);  d/dx_c = scale * w[y] * (softmax_c - [c == y])
+__global__ void __launch_bounds__(128)
+ce_kernel(const float* __restrict__ logits, int64_t ld, int C, const int32_t* __restrict__ labels,
+          const float* __restrict__ class_w, float scale, float* __restrict__ loss_per_row,
+          float* __restrict__ d_logits, int64_t d_ld) {
+  __shared__ float s_red[8];
+  const int b = blockIdx.x;
+  const int y = labels[b];
+  float* g = d_logits + static_cast<int64_t>(b) * d_ld;
+  if (y < 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) g[c] = 0.f;
+    if (threadIdx.x == 0) loss_per_row[b] = 0.f;
+    return;
+  }
+  const float* x = logits + static_cast<int64_t>(b) * ld;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, x[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+  float z = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) z += expf(x[c] - mx);
+  z = block_sum(z, s_red);
+  const float w = (class_w ? class_w[y] : 1.0f) * scale;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) g[c] = w * (expf(x[c] - mx) / z - (c == y ? 1.f : 0.f));
+  if (threadIdx.x == 0) loss_per_row[b] = w * (logf(z) + mx - x[y]);
+}
+
 // Prediction arg-maxes of the evaluation loop (reference utils/evaluation.py:114-175, 179-271), one CTA
 // per clip over its valid candidate slots; empty slots are -inf there, i.e. never win.
 //   out[b] = { pr_track, joint_t, joint_c, joint_r, cls_at_gt0, cls_at_gt1, rel_at_gt0, rel_at_gt1 }
@@ -377,6 +450,19 @@ extern "C" int lirec_loss_rowmargin_fwd_bwd(const float* logits, int64_t ld, int
   if (rows <= 0) return LIREC_OK;
   loss::rowmargin_kernel<<<rows, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       logits, ld, rows, C, labels, weights, margin, scale, loss_per_row, d_logits, d_ld);
+  LIREC_CUDA_OK(cudaGetLastError());
+  note_launch();
+  return LIREC_OK;
+}
+
+extern "C" int lirec_loss_ce_fwd_bwd(const float* logits, int64_t ld, int32_t rows, int32_t C, const int32_t* labels,
+                                     const float* class_weights, float scale, float* loss_per_row,
+                                     float* d_logits, int64_t d_ld, void* stream) {
+  LIREC_ENTER();
+  LIREC_REQUIRE(logits && labels && loss_per_row && d_logits && C > 0, "ce loss: bad arguments");
+  if (rows <= 0) return LIREC_OK;
+  loss::ce_kernel<<<rows, 128, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, C, labels, class_weights, scale,
+                                                                      loss_per_row, d_logits, d_ld);
   LIREC_CUDA_OK(cudaGetLastError());
   note_launch();
   return LIREC_OK;

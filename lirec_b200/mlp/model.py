@@ -410,16 +410,16 @@ class MultiTaskMaxMargin(nn.Module):
 
 class _TrackLoss(nn.Module):
     def _run(self, x, args, n_rels, lymbda):
-        if opt.tr_cat_distr:
-            raise NotImplementedError("tr_cat_distr (multinomial track assignment, model.py:468-471) "
-                                      "is not implemented on the B200 path")
         assert opt.tr_maximize
+        assert not (opt.tr_cat_distr and opt.tr_correct)                 # model.py:469, 539
+        self._draws = getattr(self, "_draws", 0) + 1
         pb = _batch_of(x, args)
         li, lr = x.ragged_inters, x.ragged_rels if n_rels else None
         terms, assign, d_i, d_r = ops.loss_track(
             li, lr, pb["cand_off"], pb["labels"], pb["rels_label"] if n_rels else None, pb["gt_tracks"],
             pb.multilab, self.m, lymbda, n_rels, tr_correct=opt.tr_correct,
-            max_neg=bool(opt.tr_max_neg and opt.tr_sum_max_flag), max_slots=pb.n_slots)
+            max_neg=bool(opt.tr_max_neg and opt.tr_sum_max_flag), max_slots=pb.n_slots,
+            cat_distr=bool(opt.tr_cat_distr), seed=(int(opt.seed) * 0x9E3779B1 + self._draws * 0xC2B2AE35))
         self.last_assignment = assign
         if n_rels:
             return _LossFn.apply(terms, (d_i, d_r), li, lr)
@@ -450,8 +450,9 @@ class MarginTrackRelsLoss(_TrackLoss):
 
 
 class MultiTaskCrossEntropyLoss(nn.Module):
-    """Reference: mlp/model.py:357-378.  Never selected by create_model (model.py:586-597); kept
-    for surface completeness on top of torch's cross_entropy over the ragged logits."""
+    """Reference: mlp/model.py:357-378 (never selected by create_model, model.py:586-597): softmax
+    cross-entropy of the interaction logits (optionally class-weighted) plus that of the relationship
+    logits of the rows whose label is not None, both as fused forward+gradient kernels."""
 
     def __init__(self, n_classes, weights=None, n_rels=0):
         super().__init__()
@@ -459,15 +460,25 @@ class MultiTaskCrossEntropyLoss(nn.Module):
         self.weights = None if weights is None else torch.tensor(weights).float()
 
     def forward(self, x, args):
-        import torch.nn.functional as F
         pb = _batch_of(x, args)
-        w = None if self.weights is None else self.weights.to(x.ragged_inters.device)
-        loss = F.cross_entropy(x.ragged_inters, pb["labels"].long(), weight=w)
-        lab = pb["rels_label"].long()
-        sel = (lab != self.n_rels).nonzero().reshape(-1)
-        if sel.numel():
-            loss = loss + F.cross_entropy(x.ragged_rels[sel], lab[sel])
-        return loss
+        host = pb.host if pb.device is not None else pb
+        li = x.ragged_inters
+        lab_i = pb["labels"]
+        if li.shape[0] != lab_i.numel():
+            raise RuntimeError("MultiTaskCrossEntropyLoss expects one interaction row per clip")
+        w = None if self.weights is None else self.weights.to(li.device)
+        denom = float(self.weights[torch.as_tensor(host["labels"]).long()].sum()) if w is not None else li.shape[0]
+        t, d = ops.loss_ce(li, lab_i, w, 1.0 / denom)
+        terms, grads, logits = [t], [d], [li]
+        if x.ragged_rels is not None:
+            lab = host["rels_label"]
+            n_sel = int((lab != self.n_rels).sum())
+            if n_sel:
+                sel = pb["rels_label"].clone()
+                sel[sel == self.n_rels] = -1                     # rows labelled None are skipped (model.py:369)
+                t, d = ops.loss_ce(x.ragged_rels, sel, None, 1.0 / n_sel)
+                terms.append(t), grads.append(d), logits.append(x.ragged_rels)
+        return _LossFn.apply(torch.cat(terms), tuple(grads), *logits)
 
 
 # =================================================================================================

@@ -12,7 +12,7 @@ from ._ext import (ACT_NONE, ACT_RELU, ACT_TANH, OUT_F32, OUT_SPLIT, OUT_SPLIT_T
                    POST_NONE)
 
 __all__ = ["gemm_problem", "gemm_grouped", "seg_reduce", "rows_expand_fwd", "rows_expand_bwd", "split_f32",
-           "cast_bf16", "gather_rows", "roi_max_pool", "loss_track", "loss_rowmargin", "predict_tracks", "adam_flat", "dp_allreduce_adam", "dropout_desc"]
+           "cast_bf16", "gather_rows", "roi_max_pool", "loss_track", "loss_rowmargin", "loss_ce", "predict_tracks", "adam_flat", "dp_allreduce_adam", "dropout_desc"]
 
 
 def dropout_desc(p=0.0, seed=0, stream_id=0, col_off=0):
@@ -126,7 +126,7 @@ def gather_rows(bank, idx, out=None):
 
 
 def loss_track(ints, rels, cand_off, labels, rels_label, gt_tracks, multilab, margin, lymbda, n_rels,
-               tr_correct=False, max_neg=False, max_slots=20):
+               tr_correct=False, max_neg=False, max_slots=20, cat_distr=False, seed=0):
     """Fused MarginLoss / MarginTrackRelsLoss. Returns (loss_per_clip, assign, d_ints, d_rels)."""
     B = cand_off.numel() - 1
     Ni, Cc = ints.shape
@@ -134,6 +134,7 @@ def loss_track(ints, rels, cand_off, labels, rels_label, gt_tracks, multilab, ma
     cfg.margin, cfg.lymbda = float(margin), float(lymbda)
     cfg.n_classes, cfg.n_rels = int(Cc), int(n_rels)
     cfg.tr_correct, cfg.max_neg, cfg.max_slots = int(tr_correct), int(max_neg), int(max_slots)
+    cfg.cat_distr, cfg.seed = int(cat_distr), int(seed) & 0xFFFFFFFF
     loss = torch.empty(B, dtype=torch.float32, device=ints.device)
     assign = torch.empty(B, dtype=torch.int32, device=ints.device)
     d_ints = torch.empty_like(ints)
@@ -144,6 +145,17 @@ def loss_track(ints, rels, cand_off, labels, rels_label, gt_tracks, multilab, ma
         _ext.ptr(rels_label) if n_rels > 0 else None, _ext.ptr(gt_tracks), _ext.ptr(multilab), cfg,
         _ext.ptr(loss), _ext.ptr(assign), _ext.ptr(d_ints), _ext.ptr(d_rels), _ext.stream_ptr()))
     return loss, assign, d_ints, d_rels
+
+
+def loss_ce(logits, labels, class_weights, scale):
+    """Softmax cross-entropy rows, forward + gradient (lirec_loss_ce_fwd_bwd). labels < 0 are skipped."""
+    rows, Cc = logits.shape
+    loss = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    d = torch.empty_like(logits)
+    _ext.check(_ext.lib().lirec_loss_ce_fwd_bwd(_ext.ptr(logits), logits.stride(0), rows, Cc, _ext.ptr(labels),
+                                                _ext.ptr(class_weights), float(scale), _ext.ptr(loss), _ext.ptr(d),
+                                                d.stride(0), _ext.stream_ptr()))
+    return loss, d
 
 
 def loss_rowmargin(logits, labels, weights, margin, scale):

@@ -82,3 +82,12 @@ def dense_masks(pb, seed, p, J=512, gate_dim=3072, kind="maxtracks"):
         m[dense_row] = keep_mask(seed, DS_GATE, np.arange(Ni), np.arange(gate_dim), p)
         masks[("gate",)] = torch.from_numpy(m)
     return masks
+
+
+def cat_distr_uniform(seed, n_clips):
+    """The uniform draw in [0, 1) the track-loss kernel uses for clip b under opt.tr_cat_distr
+    (csrc/loss.cu: fmix32(seed ^ fmix32(b + 0x51ED270B)) >> 8, scaled by 2^-24)."""
+    b = np.arange(n_clips, dtype=np.uint64)
+    inner = fmix32((b + np.uint64(0x51ED270B)) & _M32)
+    h = fmix32((np.uint64(int(seed) & 0xFFFFFFFF) ^ inner) & _M32)
+    return (h >> np.uint64(8)).astype(np.float64) / 16777216.0

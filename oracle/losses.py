@@ -79,14 +79,28 @@ def _track_hinge(s, pos, neg, margin, max_neg):
     return (torch.relu((margin - pos).view(-1, 1) + flat) * nm.view(B, -1)).sum(1)
 
 
+def cat_distr_probs(x_masked, labels, r_masked=None, r0=None):
+    """Sampling distribution of opt.tr_cat_distr (model.py:468-471, 538-543): softmax over the slots of the
+    target-class logits, averaged with the softmax of the GT-relationship logits (NaN -> 0) if given."""
+    b = torch.arange(x_masked.shape[0])
+    p = torch.softmax(x_masked[b, :, labels], dim=1)
+    if r_masked is not None:
+        pr = torch.softmax(r_masked[b, :, r0], dim=1)
+        pr = torch.where(pr != pr, torch.zeros_like(pr), pr)
+        p = (p + pr) / 2
+    return p
+
+
 def margin_loss(inters, labels, mem_mask, multilab_weights, gt_tracks, margin, tr_correct=False,
-                max_neg=False):
-    """Returns (loss, assignment t*, masked logits)."""
+                max_neg=False, assign=None):
+    """Returns (loss, assignment t*, masked logits).  assign: forced t* (tr_cat_distr draws)."""
     B = inters.shape[0]
     x, neg = _track_ints_part(inters, labels, mem_mask, multilab_weights, gt_tracks, tr_correct)
     s = torch.sigmoid(x)
     b = torch.arange(B)
-    if tr_correct:
+    if assign is not None:
+        tstar = assign
+    elif tr_correct:
         tstar = torch.zeros(B, dtype=torch.long)
     else:
         tstar = torch.argmax(s[b, :, labels] * mem_mask.to(s.dtype), dim=1)   # model.py:479
@@ -95,7 +109,7 @@ def margin_loss(inters, labels, mem_mask, multilab_weights, gt_tracks, margin, t
 
 
 def margin_track_rels(inters, rels, labels, rels_label, mem_mask, multilab_weights, gt_tracks, margin,
-                      lymbda, n_rels, tr_correct=False, max_neg=False):
+                      lymbda, n_rels, tr_correct=False, max_neg=False, assign=None):
     """Returns (loss, assignment t*, masked inters, masked rels with the appended None column)."""
     B, T, R = rels.shape
     b = torch.arange(B)
@@ -116,7 +130,9 @@ def margin_track_rels(inters, rels, labels, rels_label, mem_mask, multilab_weigh
         neg_r[b, :, r0] = False                                 # model.py:536-537
         neg_r[b, :, r1] = False
     s_i, s_r = torch.sigmoid(x), torch.sigmoid(r)
-    if tr_correct:
+    if assign is not None:
+        tstar = assign
+    elif tr_correct:
         tstar = torch.zeros(B, dtype=torch.long)
     else:
         score = s_i[b, :, labels] + s_r[b, :, r0]

@@ -169,3 +169,95 @@ def test_prediction_argmaxes_are_bit_exact(with_rels):
     if not with_rels:
         ref[:, 3] = -1
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("with_rels", [True, False])
+def test_cat_distr_sampled_assignment(with_rels):
+    """opt.tr_cat_distr (model.py:468-471, 538-543): t* is drawn from the softmax scores.  The kernel's draw
+    is the inverse CDF of the oracle's distribution at the mirrored counter-hash uniform; loss and gradients
+    match the oracle evaluated at the same assignment; over many seeds the frequencies follow the
+    distribution."""
+    from lirec_b200 import ops
+    from oracle import dropout as od, losses as ol
+    B = 32
+    case = _ragged_case(B, seed=21, with_rels=with_rels)
+    dev = lambda a: None if a is None else torch.from_numpy(a).cuda()
+    args = (dev(case["ints"]), dev(case["rels"]), dev(case["off"]), dev(case["labels"]), dev(case["rels_label"]),
+            dev(case["gt"]), dev(case["multilab"]), 0.101, 0.7 if with_rels else 1.0, R if with_rels else 0)
+    ints, rels, mem, rl = _dense(case)
+    labels, gt = torch.from_numpy(case["labels"]).long(), torch.from_numpy(case["gt"]).long()
+    mw = torch.from_numpy(case["multilab"]).double()
+    if with_rels:
+        _, _, xm, rm = ol.margin_track_rels(ints, rels, labels, rl, mem, mw, gt, 0.101, 0.7, R)
+        r0 = rl[torch.arange(B), gt[:, 0]]
+        probs = ol.cat_distr_probs(xm.detach(), labels, rm.detach(), r0)
+    else:
+        _, _, xm = ol.margin_loss(ints, labels, mem, mw, gt, 0.101)
+        probs = ol.cat_distr_probs(xm.detach(), labels)
+    probs = probs.numpy()
+    cdf = np.cumsum(probs, axis=1)
+    total = cdf[:, -1]
+    seed = 12345
+    lo, assign, d_i, d_r = ops.loss_track(*args, max_slots=T, cat_distr=True, seed=seed)
+    u = od.cat_distr_uniform(seed, B) * total
+    expect = np.array([int(np.searchsorted(cdf[b], u[b], side="right")) for b in range(B)])
+    edge = np.array([np.abs(cdf[b] - u[b]).min() < 1e-5 for b in range(B)])
+    got = assign.cpu().numpy()
+    assert (got[~edge] == expect[~edge]).all() and (~edge).sum() >= B - 2
+    assert all(got[b] < case["counts"][b] for b in range(B))
+    # same draw again; a different seed moves some assignments
+    _, assign2, _, _ = ops.loss_track(*args, max_slots=T, cat_distr=True, seed=seed)
+    assert torch.equal(assign, assign2)
+    # loss / gradients at the sampled assignment
+    forced = torch.from_numpy(got).long()
+    if with_rels:
+        ref, _, _, _ = ol.margin_track_rels(ints, rels, labels, rl, mem, mw, gt, 0.101, 0.7, R, assign=forced)
+    else:
+        ref, _, _ = ol.margin_loss(ints, labels, mem, mw, gt, 0.101, assign=forced)
+    ref.backward()
+    assert abs(lo.sum().item() - ref.item()) / abs(ref.item()) < 1e-5
+    gi = ints.grad[mem.bool()]
+    assert float((d_i.cpu().double() - gi).abs().max() / gi.abs().max()) < 1e-4
+    if with_rels:
+        gr = rels.grad[mem.bool()]
+        assert float((d_r.cpu().double() - gr).abs().max() / (gr.abs().max() + 1e-30)) < 1e-4
+    # statistics: 400 seeds, clips with >= 6 candidates
+    counts = np.zeros((B, T))
+    n_draws = 400
+    for s in range(n_draws):
+        _, a, _, _ = ops.loss_track(*args, max_slots=T, cat_distr=True, seed=1000 + s)
+        counts[np.arange(B), a.cpu().numpy()] += 1
+    freq = counts / n_draws
+    pn = probs / total[:, None]
+    assert np.abs(freq - pn).max() < 0.12
+    assert np.abs(freq - pn).mean() < 0.01
+
+
+def test_cross_entropy_loss():
+    """MultiTaskCrossEntropyLoss terms (model.py:357-378): weighted CE of the interaction logits, CE of the
+    relationship logits of rows whose label is not None."""
+    from lirec_b200 import ops
+    from oracle import losses as ol
+    rng = np.random.default_rng(5)
+    B = 70
+    x = (rng.standard_normal((B, C)) * 3).astype(np.float32)
+    y = rng.integers(C, size=B).astype(np.int32)
+    r = (rng.standard_normal((B, R)) * 3).astype(np.float32)
+    lab = rng.integers(R + 1, size=B).astype(np.int32)
+    for weights in (None, (rng.random(C) + 0.5).astype(np.float32)):
+        xt = torch.from_numpy(x).double().requires_grad_(True)
+        rt = torch.from_numpy(r).double().requires_grad_(True)
+        w64 = None if weights is None else torch.from_numpy(weights).double()
+        ref = ol.multitask_ce(xt, rt, torch.from_numpy(y).long(), torch.from_numpy(lab).long(), R, weights=w64)
+        ref.backward()
+        denom = B if weights is None else float(weights[y].sum())
+        t1, d1 = ops.loss_ce(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(),
+                             None if weights is None else torch.from_numpy(weights).cuda(), 1.0 / denom)
+        sel = lab.copy()
+        sel[sel == R] = -1
+        t2, d2 = ops.loss_ce(torch.from_numpy(r).cuda(), torch.from_numpy(sel).cuda(), None, 1.0 / int((lab != R).sum()))
+        total = t1.sum().item() + t2.sum().item()
+        assert abs(total - ref.item()) / ref.item() < 1e-5
+        assert float((d1.cpu().double() - xt.grad).abs().max() / xt.grad.abs().max()) < 1e-4
+        assert float((d2.cpu().double() - rt.grad).abs().max() / rt.grad.abs().max()) < 1e-4
+        assert float(d2[torch.from_numpy(lab == R).cuda()].abs().max()) == 0.0

@@ -155,3 +155,31 @@ def test_state_dict_surface(opt_preset):
     assert all(not torch.equal(before[k], v) for k, v in model.state_dict().items())
     model.load_state_dict(before)          # checkpoints round-trip through the flat buffer
     assert all(torch.equal(before[k], v) for k, v in model.state_dict().items())
+
+
+def test_cross_entropy_loss_module_end_to_end(opt_preset):
+    """MultiTaskCrossEntropyLoss (model.py:357-378, not wired into create_model) on the int_rels model: loss and
+    every parameter gradient against the oracle."""
+    import lirec_b200.mlp.model as M
+    from lirec_b200.mixed_utils import synthetic
+    from oracle import losses as ol, model as om
+    opt = opt_preset("int_rels", dropout=0.0)
+    model, _, _ = make_model()
+    model.eval()
+    pb = synthetic.make_batch(12, seed=9, preset="int_rels")
+    w = np.linspace(0.5, 1.5, N_CLASSES).astype(np.float32)
+    loss_fn = M.MultiTaskCrossEntropyLoss(N_CLASSES, weights=w, n_rels=N_RELS)
+    out = model(pb.to_device("cuda"))
+    lv = loss_fn(out, {})
+    lv.backward()
+    sd = rounded_state_dict(model)
+    dense = pb.to_dense(np.float64)
+    B = pb.B
+    f = dense["features"]
+    o = om.midfusion_forward(sd, f.reshape(B, -1, f.shape[-1]), dense["rels_mask"].reshape(B, -1, 1),
+                             om.default_cfg(ctx=1, gates=1, dropout=0.0), None)
+    ref = ol.multitask_ce(o["inters"], o["rels"], dense["labels"].reshape(B), dense["rels_label"].reshape(B), N_RELS,
+                          weights=torch.from_numpy(w).double())
+    ref.backward()
+    assert abs(lv.item() - ref.item()) / abs(ref.item()) < TOL
+    assert max(rel_err(p.grad, sd[k].grad) for k, p in model.named_parameters()) < TOL

@@ -310,6 +310,10 @@ typedef struct lirec_model_cfg {
   int32_t ctx, gates;                        /* opt.ctx, opt.gates (opt.ints is 1)     */
   int32_t guard_zero;                        /* 1: MaxTracks divider guard (model.py:303) */
   float dropout_p;                           /* opt.dropout                            */
+  int32_t slot_mask;                         /* bit s: modality slot present (0 txt, 1 vis, 2 tracks1,
+                                                3 tracks2); 0 = all.  Modalities with opt.modality 't' / 'v'
+                                                or without tracks (model.py:27-46, 78-86) drop slots; the
+                                                concatenated feature shrinks accordingly               */
 } lirec_model_cfg;
 
 /* Packed ragged batch (device pointers).  Every encoder row — candidate row or context

@@ -81,7 +81,7 @@ class ModelCfg(C.Structure):
                 ("joint_dim", C.c_int32), ("gate_dim", C.c_int32),
                 ("n_classes", C.c_int32), ("n_rels", C.c_int32),
                 ("ctx", C.c_int32), ("gates", C.c_int32), ("guard_zero", C.c_int32),
-                ("dropout_p", C.c_float)]
+                ("dropout_p", C.c_float), ("slot_mask", C.c_int32)]
 
 
 class Batch(C.Structure):

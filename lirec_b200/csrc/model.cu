@@ -38,6 +38,7 @@ struct Dims {
   int J, F, Gd, C, R, CP, RP;
   int Ni, Nx, nc, nci, nt, nti;
   int cs[4], outw[4], inw[4];
+  bool act[4];        // modality slot present (Modalities with opt.modality 't'/'v' or without tracks)
   int ones_rows;
   int NiP, ncP[2], ntP[2], onesP;   // row pitches of the transposed gradient buffers (multiples of 64)
   bool ctx, gates;
@@ -46,7 +47,6 @@ struct Dims {
 static Dims make_dims(const lirec_model_cfg& c, const lirec_batch& b) {
   Dims d;
   d.J = c.joint_dim;
-  d.F = 3 * d.J;
   d.Gd = c.gate_dim;
   d.C = c.n_classes;
   d.R = c.n_rels;
@@ -58,8 +58,14 @@ static Dims make_dims(const lirec_model_cfg& c, const lirec_batch& b) {
   d.nci = b.n_clip_ints;
   d.nt = b.n_track;
   d.nti = b.n_track_ints;
-  d.cs[0] = 0; d.cs[1] = d.J; d.cs[2] = 2 * d.J; d.cs[3] = 2 * d.J + d.J / 2;
   d.outw[0] = d.J; d.outw[1] = d.J; d.outw[2] = d.J / 2; d.outw[3] = d.J / 2;
+  const int mask = (c.slot_mask & 15) ? (c.slot_mask & 15) : 15;
+  d.F = 0;
+  for (int s = 0; s < 4; ++s) {     // concat order txt | vis | tracks1 | tracks2 (model.py:80-86, 296)
+    d.act[s] = (mask >> s) & 1;
+    d.cs[s] = d.F;
+    if (d.act[s]) d.F += d.outw[s];
+  }
   d.inw[0] = c.text_dim; d.inw[1] = c.visual_dim; d.inw[2] = c.track_dim; d.inw[3] = c.track_dim;
   d.ctx = c.ctx != 0;
   d.gates = c.gates != 0;
@@ -126,6 +132,7 @@ static size_t split_pool_floats(const Dims& d) {
   for (int br = 0; br < (d.ctx ? 2 : 1); ++br) {
     const int ncl = br ? d.nc : d.nci, ntr = br ? d.nt : d.nti;
     for (int s = 0; s < 4; ++s) {
+      if (!d.act[s]) continue;
       add(d.outw[s], d.J, 3, d.Ni); add(d.outw[s], 1, 2, d.Ni);
       const int nu = (s < 2) ? ncl : ntr;
       add(d.J, d.inw[s], 2, nu); add(d.J, 1, 2, nu);
@@ -154,6 +161,7 @@ static Workspace carve(const Dims& d, void* base) {
   for (int br = 0; br < nbr; ++br) {
     const int ncl = br ? d.nc : d.nci, ntr = br ? d.nt : d.nti;
     for (int s = 0; s < 4; ++s) {
+      if (!d.act[s]) continue;
       const int nu = (s < 2) ? ncl : ntr;
       const int nuP = (s < 2) ? d.ncP[br] : d.ntP[br];
       w.r1[br][s] = static_cast<float*>(take((size_t)nu * d.J * 4));
@@ -278,6 +286,8 @@ static int validate(const lirec_model_cfg* cfg, const lirec_model_params* P, con
   LIREC_REQUIRE(cfg->text_dim % 8 == 0 && cfg->visual_dim % 8 == 0 && cfg->track_dim % 8 == 0,
                 "model: feature dims must be multiples of 8");
   LIREC_REQUIRE(!cfg->gates || cfg->ctx, "model: gates need the context branch");
+  LIREC_REQUIRE(!cfg->ctx || (cfg->slot_mask & 15) == 0 || (cfg->slot_mask & 15) == 15,
+                "model: the context models always use all four modality slots (slot_mask=%d)", cfg->slot_mask);
   LIREC_REQUIRE(!cfg->gates || cfg->gate_dim % 8 == 0, "model: gate_dim=%d", cfg->gate_dim);
   LIREC_REQUIRE(cfg->n_classes > 0 && (!cfg->ctx || cfg->n_rels > 0), "model: n_classes=%d n_rels=%d",
                 cfg->n_classes, cfg->n_rels);
@@ -321,6 +331,7 @@ int forward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lirec
     const lirec_encoder& enc = br ? P.enc_ctx : P.enc_ints;
     const int ncl = br ? d.nc : d.nci, ntr = br ? d.nt : d.nti;
     for (int s = 0; s < 4; ++s) {
+      if (!d.act[s]) continue;
       const int nu = (s < 2) ? ncl : ntr;
       lirec_operand a;
       if (s == 0) a = op(B.clip_bank, nu, d.inw[0], B.clip_ld);
@@ -363,6 +374,7 @@ int forward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lirec
   for (int br = 0; br < nbr; ++br) {
     const lirec_encoder& enc = br ? P.enc_ctx : P.enc_ints;
     for (int s = 0; s < 4; ++s) {
+      if (!d.act[s]) continue;
       lirec_gemm_problem g = mk_problem(d.Ni, d.outw[s], false, false);
       const lirec_operand a = op(w.a2[br] + s * 2 * J, d.Ni, 2 * J, 8 * J);
       const lirec_operand b = op(enc.l2[s].w_bf16, d.outw[s], J, J);
@@ -533,6 +545,7 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
     if (d.gates) add(P.gate.w_bf16, Gd, 2 * F, w.gateT, Gd);
     for (int br = 0; br < nbr; ++br)
       for (int s = 0; s < 4; ++s)
+        if (d.act[s])
         add((br ? P.enc_ctx : P.enc_ints).l2[s].w_bf16, d.outw[s], J, w.l2T[br][s], d.outw[s]);
     if ((rc = rows::transpose_bf16(tj, stream)) != LIREC_OK) return rc;
   }
@@ -609,6 +622,7 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
   for (int br = 0; br < nbr; ++br) {
     const lirec_encoder& enc = br ? P.enc_ctx : P.enc_ints;
     for (int s = 0; s < 4; ++s) {
+      if (!d.act[s]) continue;
       const TGrad dz{w.dz2T[br], 2 * F, NiP, d.cs[s], F + d.cs[s]};
       push_reduction(pr, wgrad_t(d.outw[s], J, dz, w.a2[br], 8 * J, 8 * J, s * 2 * J, s * 2 * J + J, Ni, keep_scale,
                                  enc.l2[s].grad_w, J), d.outw[s], J, Ni, true, sc);
@@ -631,6 +645,7 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
     for (int br = 0; br < nbr; ++br) {
       const int ncl = br ? d.nc : d.nci, ntr = br ? d.nt : d.nti;
       for (int s = 0; s < 4; ++s) {
+        if (!d.act[s]) continue;
         rows::ExpandBwdJob& j = jobs.job[n++];
         const int inv = (s < 2) ? 0 : (s - 1);
         j.d_in = w.da2[br] + s * J;
@@ -659,6 +674,7 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
     const lirec_encoder& enc = br ? P.enc_ctx : P.enc_ints;
     const int ncl = br ? d.nc : d.nci, ntr = br ? d.nt : d.nti;
     for (int s = 0; s < 4; ++s) {
+      if (!d.act[s]) continue;
       const int nu = (s < 2) ? ncl : ntr;
       const int nuP = (s < 2) ? d.ncP[br] : d.ntP[br];
       const bf16* x;

@@ -108,6 +108,7 @@ expand_fwd_kernel(const ExpandFwdJobs jobs) {
       const uint32_t rkey = drop_row_key(jb.drop.seed, jb.drop.stream_id, static_cast<uint32_t>(x));
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
+        if (!src[s]) continue;                      // modality slot absent (Modalities 't' / 'v' / no tracks)
         float4 v = ld4(src[s] + static_cast<int64_t>(u[s]) * J + j);
         if (jb.drop.p > 0.f) {
           const uint32_t c = static_cast<uint32_t>(jb.drop.col_off + s * J + j);   // multiple of 4
@@ -136,7 +137,8 @@ expand_fwd_kernel(const ExpandFwdJobs jobs) {
     }
     __nv_bfloat16* orow = jb.out + static_cast<int64_t>(o) * jb.out_ld;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) store_split4(orow + s * 2 * J + j, orow + s * 2 * J + J + j, acc[s]);
+    for (int s = 0; s < 4; ++s)
+      if (src[s]) store_split4(orow + s * 2 * J + j, orow + s * 2 * J + J + j, acc[s]);
   }
   if (jb.row_flag_out && threadIdx.x == 0) jb.row_flag_out[o] = (n > 0) ? 1 : 0;
   if (jb.flag_bf16_out && threadIdx.x == 0) jb.flag_bf16_out[o] = __float2bfloat16_rn(n > 0 ? 1.f : 0.f);

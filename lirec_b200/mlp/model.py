@@ -104,27 +104,39 @@ class _HotPath(nn.Module):
     kind = None
 
     def _build(self, n_classes, n_rels, ints, ctx, gates):
-        if opt.modality != "m" or not opt.tracks:
-            raise NotImplementedError("lirec_b200 implements the multimodal model with tracks "
-                                      "(opt.modality='m', opt.tracks=True)")
         if not ints:
             raise NotImplementedError("opt.ints must be 1")
         self.n_classes, self.n_rels = n_classes, n_rels
         self._ctx, self._gates = bool(ctx), bool(gates and ctx)
         J = opt.joint_dim
         dims = {"txt": opt.text_dim, "vis": opt.visual_dim, "tracks1": opt.track_dim, "tracks2": opt.track_dim}
+        # Modality slots.  Only Modalities switches on opt.modality / opt.tracks (model.py:27-46); the
+        # context models always build all four (model.py:102-129, 220-246).
+        txt = vis = tracks = True
+        if self.kind == "modalities":
+            txt, vis, tracks = opt.modality in ("m", "t"), opt.modality in ("m", "v"), bool(opt.tracks)
+            if opt.modality not in ("m", "t", "v"):
+                raise ValueError("opt.modality must be m, t or v")
+            if opt.modality != "m" and tracks:
+                # the reference sizes out_ints for J + J inputs but feeds it J (model.py:47, 83-86): it crashes
+                raise ValueError("Modalities with opt.modality='%s' needs opt.tracks=False (the reference's "
+                                 "forward fails on the out_ints shape otherwise)" % opt.modality)
+        self._slot_mask = (1 if txt else 0) | (2 if vis else 0) | (12 if tracks else 0)
         # same construction order as the reference (mlp/model.py:29-50, 104-143, 222-259) so that the
         # same torch seed gives bit-identical initial weights
         for br in (["ints"] + (["ctx"] if self._ctx else [])):
-            setattr(self, "txt_%s" % br, nn.Linear(dims["txt"], J))
-            setattr(self, "txt2_%s" % br, nn.Linear(J, J))
-            setattr(self, "vis_%s" % br, nn.Linear(dims["vis"], J))
-            setattr(self, "vis2_%s" % br, nn.Linear(J, J))
-            setattr(self, "tracks1_%s" % br, nn.Linear(dims["tracks1"], J))
-            setattr(self, "tracks2_%s" % br, nn.Linear(dims["tracks2"], J))
-            setattr(self, "tracks12_%s" % br, nn.Linear(J, J // 2))
-            setattr(self, "tracks22_%s" % br, nn.Linear(J, J // 2))
-        out_dim_ints = 3 * J
+            if txt:
+                setattr(self, "txt_%s" % br, nn.Linear(dims["txt"], J))
+                setattr(self, "txt2_%s" % br, nn.Linear(J, J))
+            if vis:
+                setattr(self, "vis_%s" % br, nn.Linear(dims["vis"], J))
+                setattr(self, "vis2_%s" % br, nn.Linear(J, J))
+            if tracks:
+                setattr(self, "tracks1_%s" % br, nn.Linear(dims["tracks1"], J))
+                setattr(self, "tracks2_%s" % br, nn.Linear(dims["tracks2"], J))
+                setattr(self, "tracks12_%s" % br, nn.Linear(J, J // 2))
+                setattr(self, "tracks22_%s" % br, nn.Linear(J, J // 2))
+        out_dim_ints = (J if txt else 0) + (J if vis else 0) + (J if tracks else 0)
         if self._gates:
             out_dim_ints = J * opt.mid_m_ints
             self.gates_ints = GatingUnit(in_dim1=3 * J, in_dim2=3 * J, out_dim=out_dim_ints)
@@ -222,6 +234,8 @@ class _HotPath(nn.Module):
             if br == "ctx" and not self._ctx:
                 continue
             for s in range(4):
+                if not (self._slot_mask >> s) & 1:
+                    continue
                 enc.l1[s] = self._linear_struct(getattr(self, "%s_%s" % (_SLOTS[s], br)))
                 enc.l2[s] = self._linear_struct(getattr(self, "%s_%s" % (_SECOND[s], br)))
         if self._gates:
@@ -236,6 +250,7 @@ class _HotPath(nn.Module):
         cfg.ctx, cfg.gates = int(self._ctx), int(self._gates)
         cfg.guard_zero = int(self.kind == "maxtracks")
         cfg.dropout_p = float(self.dropout.p)
+        cfg.slot_mask = int(self._slot_mask)
         self._params_c, self._cfg_c = P, cfg
 
     def _batch_struct(self, pb, training, seed):

@@ -48,7 +48,7 @@ def keep_mask(seed, stream_id, rows, cols, p):
 DS_L1_INTS, DS_L1_CTX, DS_CAT_INTS, DS_CAT_CTX, DS_GATE = 1, 2, 3, 4, 5
 
 
-def dense_masks(pb, seed, p, J=512, gate_dim=3072, kind="maxtracks"):
+def dense_masks(pb, seed, p, J=512, gate_dim=3072, kind="maxtracks", cat_width=None):
     """Masks of one step, laid out for the DENSE oracle (oracle/model.py `masks=`) from the packed
     tables of host PackedBatch `pb`: candidate r sits at dense row (clip, slot), context row x at
     (clip, slot, position).  Empty slots get all-ones masks (they are masked out downstream)."""
@@ -63,8 +63,9 @@ def dense_masks(pb, seed, p, J=512, gate_dim=3072, kind="maxtracks"):
         m = np.ones((B * T, J), dtype=bool)
         m[dense_row] = keep_mask(seed, DS_L1_INTS, np.arange(Ni), s * J + np.arange(J), p)
         masks[("l1", "ints", name)] = torch.from_numpy(m)
-    m = np.ones((B * T, 3 * J), dtype=bool)
-    m[dense_row] = keep_mask(seed, DS_CAT_INTS, np.arange(Ni), np.arange(3 * J), p)
+    cw = 3 * J if cat_width is None else int(cat_width)      # Modalities without some slots: narrower concat
+    m = np.ones((B * T, cw), dtype=bool)
+    m[dense_row] = keep_mask(seed, DS_CAT_INTS, np.arange(Ni), np.arange(cw), p)
     masks[("cat", "ints")] = torch.from_numpy(m)
     if pb.has_ctx:
         Nx = pb.n_ctx_rows

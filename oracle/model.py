@@ -28,7 +28,7 @@ SECOND = {"txt": "txt2", "vis": "vis2", "tracks1": "tracks12", "tracks2": "track
 
 def default_cfg(**kw):
     cfg = SimpleNamespace(text_dim=768, visual_dim=2048, track_dim=2048, joint_dim=512, mid_m_ints=6,
-                          ints=1, ctx=1, gates=1, dropout=0.3)
+                          ints=1, ctx=1, gates=1, dropout=0.3, modality="m", tracks=True)
     for k, v in kw.items():
         setattr(cfg, k, v)
     return cfg
@@ -56,13 +56,13 @@ def _tape(cfg, name, t):
     return t
 
 
-def encode(sd, branch, x, cfg, masks):
-    """x[..., text|visual|track1|track2] -> list of the four second-layer outputs."""
+def encode(sd, branch, x, cfg, masks, slots=SLOTS):
+    """x[..., text|visual|track1|track2] -> list of the second-layer outputs of `slots`."""
     T, V, P = cfg.text_dim, cfg.visual_dim, cfg.track_dim
     parts = {"txt": x[..., :T], "vis": x[..., T:T + V],
              "tracks1": x[..., T + V:T + V + P], "tracks2": x[..., T + V + P:T + V + 2 * P]}
     outs = []
-    for slot in SLOTS:
+    for slot in slots:
         h = _tape(cfg, "z1_%s_%s" % (slot, branch), _lin(sd, "%s_%s" % (slot, branch), parts[slot]))
         h = torch.relu(_drop(h, masks, ("l1", branch, slot), cfg.dropout))  # relu(dropout(.)): model.py:62
         outs.append(_lin(sd, "%s_%s" % (SECOND[slot], branch), h))
@@ -76,9 +76,12 @@ def gating_unit(sd, feat_ints, feat_ctx, cfg, masks):
 
 
 def modalities_forward(sd, features, cfg, masks=None):
-    """features [B, 1, D] -> inters [B, C]."""
+    """features [B, 1, D] -> inters [B, C].  cfg.modality in m / t / v and cfg.tracks select the slots
+    (model.py:27-46, 57-86; 't' / 'v' only work without tracks in the reference)."""
     x = features[:, 0, :]
-    f = torch.cat(encode(sd, "ints", x, cfg, masks), dim=-1)
+    slots = [s for s in SLOTS if (s == "txt" and cfg.modality in ("m", "t")) or (s == "vis" and cfg.modality in ("m", "v"))
+             or (s.startswith("tracks") and cfg.tracks)]
+    f = torch.cat(encode(sd, "ints", x, cfg, masks, slots), dim=-1)
     f = _drop(torch.tanh(f), masks, ("cat", "ints"), cfg.dropout)
     return {"inters": _lin(sd, "out_ints", f)}
 

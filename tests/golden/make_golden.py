@@ -25,7 +25,8 @@ C, R, B, T, S = 11, 5, 4, 5, 3
 D = DIMS["text_dim"] + DIMS["visual_dim"] + 2 * DIMS["track_dim"]
 
 CASES = [
-    ("modalities", {}), ("int_rels", {}), ("int_ch", {}), ("int_ch", dict(tr_correct=True)),
+    ("modalities", {}), ("modalities", dict(modality="t", tracks=False)), ("modalities", dict(modality="v", tracks=False)),
+    ("modalities", dict(tracks=False)), ("int_rels", {}), ("int_ch", {}), ("int_ch", dict(tr_correct=True)),
     ("int_ch", dict(tr_max_neg=True)), ("int_rel_ch", {}), ("int_rel_ch", dict(tr_correct=True)),
     ("int_rel_ch", dict(tr_max_neg=True)), ("int_rel_ch", dict(tr_correct=True, tr_max_neg=True)),
 ]
@@ -76,6 +77,7 @@ def main():
         for k, v in DIMS.items():
             setattr(opt, k, v)
         opt.mlp_dim = D
+        opt.modality, opt.tracks = "m", True
         model, loss = rs.create_model(preset, C, R, seed=idx, **over)
         model.eval()
         batch = make_batch(preset, rng)
@@ -94,11 +96,12 @@ def main():
             if v is not None:
                 rec["out_" + k] = v.detach().numpy()
         rec["meta"] = np.array([preset, repr(sorted(over.items()))])
-        name = "%s%s.npz" % (preset, "".join("_" + k for k in sorted(over)))
+        name = "%s%s.npz" % (preset, "".join("_" + (k if over[k] is True else "%s-%s" % (k, over[k])) for k in sorted(over)))
         np.savez_compressed(os.path.join(HERE, name), **rec)
         print("wrote", name, "loss", lv.item())
     # restore the full-size dims for anything else importing the shim in this process
     opt.text_dim, opt.visual_dim, opt.track_dim, opt.joint_dim, opt.mlp_dim = 768, 2048, 2048, 512, 6912
+    opt.modality, opt.tracks = "m", True
 
 
 if __name__ == "__main__":

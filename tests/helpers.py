@@ -40,6 +40,8 @@ def oracle_forward_loss(pb, sd, preset, opt, masks, tape=None):
     kind = synthetic.PRESETS[preset]["kind"]
     dense = pb.to_dense(np.float64)
     cfg = om.default_cfg(ctx=int(opt.ctx), gates=int(opt.gates), dropout=opt.dropout)
+    if kind == "modalities":
+        cfg.modality, cfg.tracks = opt.modality, bool(opt.tracks)
     if tape is not None:
         cfg.tape = tape
     B = pb.B

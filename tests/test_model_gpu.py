@@ -50,7 +50,8 @@ def _run(preset, opt, B, seed, train, **flags):
         lv.backward()
         torch.cuda.synchronize()
         sd = rounded_state_dict(model)
-        masks = odrop.dense_masks(pb, step_seed, opt.dropout) if train else None
+        cw = model.out_ints.in_features if model.kind == "modalities" else None
+        masks = odrop.dense_masks(pb, step_seed, opt.dropout, cat_width=cw) if train else None
         tape = {}
         ragged, l, extra = oracle_forward_loss(pb, sd, preset, opt, masks, tape=tape)
         l.backward()
@@ -183,3 +184,25 @@ def test_cross_entropy_loss_module_end_to_end(opt_preset):
     ref.backward()
     assert abs(lv.item() - ref.item()) / abs(ref.item()) < TOL
     assert max(rel_err(p.grad, sd[k].grad) for k, p in model.named_parameters()) < TOL
+
+
+@pytest.mark.parametrize("modality,tracks", [("t", False), ("v", False), ("m", False)])
+@pytest.mark.parametrize("train", [False, True])
+def test_modalities_variants(modality, tracks, train, opt_preset):
+    """Modalities with a subset of the modality slots (reference model.py:27-46, 78-86): text only, visual
+    only, text + visual without tracks — the concatenated feature and out_ints shrink accordingly."""
+    opt = opt_preset("modalities", modality=modality, tracks=tracks)
+    model, loss_fn, out, lv, sd, ragged, l, extra, tape = _run("modalities", opt, 10, 2, train)
+    width = {"t": 512, "v": 512, "m": 1024}[modality]
+    assert model.out_ints.in_features == width and len(model.state_dict()) == {"t": 6, "v": 6, "m": 10}[modality]
+    assert rel_err(out.ragged_inters, ragged["inters"]) < TOL
+    assert abs(lv.item() - l.item()) / abs(l.item()) < TOL
+    assert max(rel_err(p.grad, sd[k].grad) for k, p in model.named_parameters()) < TOL
+
+
+def test_modalities_single_modality_with_tracks_is_rejected(opt_preset):
+    """The reference sizes out_ints for J + J inputs but feeds it J when opt.modality is 't' / 'v' with tracks
+    (model.py:47, 83-86) and crashes in forward; here the constructor says so."""
+    opt_preset("modalities", modality="t", tracks=True)
+    with pytest.raises(ValueError):
+        make_model()

@@ -18,7 +18,7 @@ C, R = 11, 5
 
 
 def test_golden_files_present():
-    assert len(GOLDEN) == 9
+    assert len(GOLDEN) == 12
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -31,7 +31,8 @@ def test_oracle_reproduces_reference(path):
     feats = inp["features"].float()
     kind = {"modalities": "modalities", "int_rels": "midfusion"}.get(preset, "maxtracks")
     ctx = preset in ("int_rels", "int_rel_ch")
-    cfg = om.default_cfg(ctx=int(ctx), gates=int(ctx), **DIMS)
+    cfg = om.default_cfg(ctx=int(ctx), gates=int(ctx), modality=over.get("modality", "m"),
+                         tracks=over.get("tracks", True), **DIMS)
     masked = {}
     if kind == "modalities":
         o = om.modalities_forward(sd, feats, cfg)

@@ -135,7 +135,9 @@ def load_dataloader():
         import mixed_utils.classification_dataloader as ref_dl  # noqa
         import mixed_utils.mixed_features as ref_mf  # noqa
         import utils.util_functions as ref_uf  # noqa
+        import utils.evaluation as ref_ev  # noqa
         _state["dataloader"], _state["mixed_features"], _state["util_functions"] = ref_dl, ref_mf, ref_uf
+        _state["evaluation"] = ref_ev
         _state["modules"] = {k: v for k, v in sys.modules.items() if k.split(".")[0] in prefixes}
     finally:
         sys.argv, sys.path[:] = saved_argv, saved_path

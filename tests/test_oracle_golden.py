@@ -12,7 +12,7 @@ import torch
 from oracle import losses as ol, model as om
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz"))
-                if not os.path.basename(p).startswith(("dataloader_", "pooling_")))
+                if not os.path.basename(p).startswith(("dataloader_", "pooling_", "eval_")))
 DIMS = dict(text_dim=24, visual_dim=40, track_dim=40, joint_dim=16, mid_m_ints=6)
 C, R = 11, 5
 

@@ -32,14 +32,14 @@ def _knife_edges(tape):
     return bad
 
 
-def _run(preset, opt, B, seed, train, **flags):
+def _run(preset, opt, B, seed, train, batch_fn=None, **flags):
     """Ours vs oracle on one synthetic batch.  If the oracle sits on a ReLU knife-edge, the affected
     bias entries are nudged by 1e-3 (on both sides, they share the parameters) and the step is redone."""
     from lirec_b200.mixed_utils import synthetic
     from oracle import dropout as odrop
     model, loss_fn, _ = make_model()
     model.train(train)
-    pb = synthetic.make_batch(B, seed=seed, preset=preset)
+    pb = batch_fn() if batch_fn is not None else synthetic.make_batch(B, seed=seed, preset=preset)
     pbd = pb.to_device("cuda")
     step_seed = 1000 + seed
     for attempt in range(8):
@@ -206,3 +206,48 @@ def test_modalities_single_modality_with_tracks_is_rejected(opt_preset):
     opt_preset("modalities", modality="t", tracks=True)
     with pytest.raises(ValueError):
         make_model()
+
+
+def _check_all(model, loss_fn, out, lv, sd, ragged, l, extra):
+    assert rel_err(out.ragged_inters, ragged["inters"]) < TOL
+    if "rels" in ragged:
+        assert rel_err(out.ragged_rels, ragged["rels"]) < TOL
+    assert abs(lv.item() - l.item()) / abs(l.item()) < TOL
+    if "assignment" in extra:
+        assert torch.equal(loss_fn.last_assignment.cpu().long(), extra["assignment"])
+    worst = max(rel_err(p.grad, sd[k].grad) for k, p in model.named_parameters())
+    assert worst < TOL, worst
+
+
+def test_long_clip_stress_config_parity(opt_preset):
+    """BASELINE config 5: 4x context rows (72) and 4x candidate slots (80) per clip, 2..8 characters."""
+    from lirec_b200.mixed_utils import synthetic
+    opt = opt_preset("int_rel_ch", rels_n_clips=72, max_n_tripl=80)
+    fn = lambda: synthetic.stress_batch(3, seed=5)
+    model, loss_fn, out, lv, sd, ragged, l, extra, tape = _run("int_rel_ch", opt, 2, 5, True, batch_fn=fn)
+    pb = out.batch
+    counts, ctx = np.diff(pb.host["cand_off"]), np.diff(pb.host["ctx_off"])
+    assert pb.n_slots == 80 and pb.n_ctx_slots == 72 and counts.max() > 20 and ctx.max() > 18
+    _check_all(model, loss_fn, out, lv, sd, ragged, l, extra)
+
+
+@pytest.mark.parametrize("case", ["one_clip", "single_characters", "no_relationships"])
+def test_edge_case_batches(case, opt_preset):
+    """Smallest / most degenerate ragged shapes: a batch of ONE clip, clips with a single character
+    (two candidates, no pair), clips where no pair has a relationship (every context is the one tiled
+    self row)."""
+    from lirec_b200.mixed_utils import synthetic
+    opt = opt_preset("int_rel_ch")
+    if case == "one_clip":
+        fn = lambda: synthetic.make_batch(1, seed=12, preset="int_rel_ch")
+    elif case == "single_characters":
+        fn = lambda: synthetic.make_batch(5, seed=13, preset="int_rel_ch", n_chars_probs={1: 1.0})
+    else:
+        fn = lambda: synthetic.make_batch(5, seed=14, preset="int_rel_ch", p_rel=0.0)
+    model, loss_fn, out, lv, sd, ragged, l, extra, tape = _run("int_rel_ch", opt, 0, 1, True, batch_fn=fn)
+    pb = out.batch
+    if case == "single_characters":
+        assert pb.n_cand == 2 * pb.B
+    if case == "no_relationships":
+        assert pb.n_ctx_rows == pb.n_cand
+    _check_all(model, loss_fn, out, lv, sd, ragged, l, extra)

@@ -200,12 +200,15 @@ int lirec_rows_expand_bwd(const float* d_in, int64_t d_ld, const float* r1, int3
  * the reference's float64 box arithmetic (lirec_b200/visual_utils/visual_features.py);
  * seg_off: [nseg+1] prefix sums over elements.  frame < 0: an all-zero row that takes part in the max
  * (reference visual_features.py:130-131); empty box: NaN; empty segment: zeros.
+ * scratch: NULL, or fp32 [n_elem, C] (16-byte aligned, C % 4 == 0): the means of all elements are then
+ * computed in one fully parallel pass and reduced by the segmented-max kernel (2-3x the bandwidth of
+ * the single-pass form on long tracks).
  * Replaces np.mean over H x W / over the person box (visual_utils/visual_features.py:67-69, 133-134)
  * followed by np.max over frames / track elements (mixed_utils/mixed_features.py:54, 104-105).  */
 int lirec_roi_max_pool_f32(const float* maps, int32_t T, int32_t C, int32_t H, int32_t W,
-                           const int32_t* elem, const int32_t* seg_off, int32_t nseg,
-                           float* out_f32, int64_t out_f32_ld, void* out_bf16, int64_t out_bf16_ld,
-                           void* stream);
+                           const int32_t* elem, int32_t n_elem, const int32_t* seg_off, int32_t nseg,
+                           float* scratch, float* out_f32, int64_t out_f32_ld, void* out_bf16,
+                           int64_t out_bf16_ld, void* stream);
 
 /* Row gather out[i, :] = bank[idx[i], :] over bf16 rows (dim, bank_ld, out_ld in elements,
  * multiples of 8; idx outside [0, n_bank) gives a zero row).  Replaces the host-side

@@ -464,6 +464,60 @@ roi_max_pool_kernel(const float* __restrict__ maps, int C, int HW, int W, const 
   }
 }
 
+// Two-stage form of the same pooling, used when the caller provides a scratch buffer: stage 1 writes the
+// box mean of EVERY (element, channel) — one warp per element and four channels, so thousands of warps
+// keep independent plane reads in flight instead of walking a segment's elements one after another —
+// and stage 2 is the segmented max kernel above (which runs at the HBM roofline).  The scratch costs
+// n_elem * C * 4 B of extra traffic, ~1 % of the map bytes read.
+__global__ void __launch_bounds__(256)
+roi_mean_kernel(const float* __restrict__ maps, int C, int HW, int W, const int32_t* __restrict__ elem,
+                float* __restrict__ out, int64_t out_ld) {
+  const int e = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = (blockIdx.y * (blockDim.x >> 5) + warp) * 4;
+  if (c0 >= C) return;
+  const int32_t* el = elem + 5 * static_cast<int64_t>(e);
+  const int frame = el[0], y0 = el[1], y1 = el[2], x0 = el[3], x1 = el[4];
+  const int w = x1 - x0, h = y1 - y0;
+  const int n = (w > 0 && h > 0) ? w * h : 0;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (frame >= 0 && n > 0) {
+    const float* plane = maps + (static_cast<int64_t>(frame) * C + c0) * HW;
+    if (w == W) {
+      const float* p = plane + y0 * W;
+#pragma unroll 2
+      for (int i = lane; i < n; i += 32) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (c0 + k < C) acc[k] += p[static_cast<int64_t>(k) * HW + i];
+      }
+    } else {
+      for (int i = lane; i < n; i += 32) {
+        const int yy = i / w, xx = i - yy * w;
+        const int o = (y0 + yy) * W + x0 + xx;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (c0 + k < C) acc[k] += plane[static_cast<int64_t>(k) * HW + o];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  }
+  if (lane == 0) {
+    float* orow = out + static_cast<int64_t>(e) * out_ld + c0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (c0 + k >= C) break;
+      float v = 0.f;                                            // frame < 0: the zero row the reference keeps
+      if (frame >= 0) v = (n > 0) ? acc[k] / static_cast<float>(n) : __int_as_float(0x7fc00000);
+      orow[k] = v;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Row gather: out[i, :] = bank[idx[i], :] (bf16 rows, 16-byte column groups).  Builds the per-batch
 // feature banks from dataset banks that stay resident in HBM; one warp-wide 128-bit load and store
@@ -486,12 +540,20 @@ gather_rows_kernel(const uint4* __restrict__ bank, int64_t bank_ld16, int n_bank
 // ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
-int roi_max_pool(const float* maps, int T, int C, int H, int W, const int32_t* elem, const int32_t* seg_off, int nseg,
-                 float* out_f32, int64_t out_f32_ld, void* out_bf16, int64_t out_bf16_ld, cudaStream_t stream) {
+int roi_max_pool(const float* maps, int T, int C, int H, int W, const int32_t* elem, int n_elem,
+                 const int32_t* seg_off, int nseg, float* scratch, float* out_f32, int64_t out_f32_ld, void* out_bf16,
+                 int64_t out_bf16_ld, cudaStream_t stream) {
   LIREC_REQUIRE(maps && elem && seg_off, "roi_max_pool: null argument");
   LIREC_REQUIRE(T > 0 && C > 0 && H > 0 && W > 0, "roi_max_pool: maps [%d, %d, %d, %d]", T, C, H, W);
   LIREC_REQUIRE(out_f32 || out_bf16, "roi_max_pool: no output");
   if (nseg <= 0) return LIREC_OK;
+  if (scratch && n_elem > 0 && C % 4 == 0 && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0) {
+    dim3 g1(n_elem, (C + 31) / 32);
+    roi_mean_kernel<<<g1, 256, 0, stream>>>(maps, C, H * W, W, elem, scratch, C);
+    LIREC_CUDA_OK(cudaGetLastError());
+    note_launch();
+    return seg_reduce(scratch, seg_off, nseg, C, 0, out_f32, out_f32_ld, out_bf16, out_bf16_ld, stream);
+  }
   dim3 grid(nseg, (C + 7) / 8);
   roi_max_pool_kernel<<<grid, 256, 0, stream>>>(maps, C, H * W, W, elem, seg_off, out_f32, out_f32_ld,
                                                 reinterpret_cast<__nv_bfloat16*>(out_bf16), out_bf16_ld);
@@ -698,11 +760,12 @@ extern "C" int lirec_rows_expand_bwd(const float* d_in, int64_t d_ld, const floa
 }
 
 extern "C" int lirec_roi_max_pool_f32(const float* maps, int32_t T, int32_t C, int32_t H, int32_t W,
-                                      const int32_t* elem, const int32_t* seg_off, int32_t nseg, float* out_f32,
-                                      int64_t out_f32_ld, void* out_bf16, int64_t out_bf16_ld, void* stream) {
+                                      const int32_t* elem, int32_t n_elem, const int32_t* seg_off, int32_t nseg,
+                                      float* scratch, float* out_f32, int64_t out_f32_ld, void* out_bf16,
+                                      int64_t out_bf16_ld, void* stream) {
   LIREC_ENTER();
-  return rows::roi_max_pool(maps, T, C, H, W, elem, seg_off, nseg, out_f32, out_f32_ld, out_bf16, out_bf16_ld,
-                            static_cast<cudaStream_t>(stream));
+  return rows::roi_max_pool(maps, T, C, H, W, elem, n_elem, seg_off, nseg, scratch, out_f32, out_f32_ld, out_bf16,
+                            out_bf16_ld, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int lirec_gather_rows(const void* bank, int64_t bank_ld, int32_t n_bank, const int32_t* idx, int32_t n,

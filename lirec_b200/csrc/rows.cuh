@@ -71,8 +71,9 @@ int expand_bwd(const ExpandBwdJobs& jobs, cudaStream_t stream);
 int split_f32(const float* x, int64_t ld, int rows, int cols, void* out, int64_t out_ld, int pad_cols,
               cudaStream_t stream);
 int cast_bf16(const float* x, void* out, int64_t n, cudaStream_t stream);
-int roi_max_pool(const float* maps, int T, int C, int H, int W, const int32_t* elem, const int32_t* seg_off, int nseg,
-                 float* out_f32, int64_t out_f32_ld, void* out_bf16, int64_t out_bf16_ld, cudaStream_t stream);
+int roi_max_pool(const float* maps, int T, int C, int H, int W, const int32_t* elem, int n_elem,
+                 const int32_t* seg_off, int nseg, float* scratch, float* out_f32, int64_t out_f32_ld, void* out_bf16,
+                 int64_t out_bf16_ld, cudaStream_t stream);
 int gather_rows(const void* bank, int64_t bank_ld, int n_bank, const int32_t* idx, int n, int dim, void* out,
                 int64_t out_ld, cudaStream_t stream);
 int split_f32_t(const float* x, int64_t ld, int rows, int cols, void* out, int64_t pitch, int pad,

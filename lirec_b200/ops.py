@@ -99,17 +99,20 @@ def cast_bf16(x, out):
     _ext.check(L.lirec_cast_bf16(_ext.ptr(x), _ext.ptr(out), x.numel(), _ext.stream_ptr()))
 
 
-def roi_max_pool(maps, elem, seg_off, out_f32=None, out_bf16=None):
+def roi_max_pool(maps, elem, seg_off, out_f32=None, out_bf16=None, two_stage=True):
     """out[s, c] = max_{e in segment s} mean(maps[frame_e, c, y0:y1, x0:x1]) (lirec_roi_max_pool_f32).
-    maps fp32 [T, C, H, W]; elem int32 [n, 5]; seg_off int32 [nseg + 1]."""
+    maps fp32 [T, C, H, W]; elem int32 [n, 5]; seg_off int32 [nseg + 1].  two_stage: give the kernel a
+    scratch of per-element means (fully parallel pass + segmented max) instead of the single-pass form."""
     assert maps.dtype == torch.float32 and maps.dim() == 4 and maps.is_contiguous()
     assert elem.dtype == torch.int32 and seg_off.dtype == torch.int32 and elem.is_contiguous()
     T, Cc, H, W = maps.shape
     nseg = seg_off.numel() - 1
     if out_f32 is None and out_bf16 is None:
         out_f32 = torch.empty(nseg, Cc, dtype=torch.float32, device=maps.device)
+    n_elem = elem.shape[0]
+    scratch = torch.empty(n_elem, Cc, dtype=torch.float32, device=maps.device) if (two_stage and Cc % 4 == 0) else None
     _ext.check(_ext.lib().lirec_roi_max_pool_f32(
-        _ext.ptr(maps), T, Cc, H, W, _ext.ptr(elem), _ext.ptr(seg_off), nseg,
+        _ext.ptr(maps), T, Cc, H, W, _ext.ptr(elem), n_elem, _ext.ptr(seg_off), nseg, _ext.ptr(scratch),
         _ext.ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
         _ext.ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, _ext.stream_ptr()))
     return out_f32 if out_f32 is not None else out_bf16

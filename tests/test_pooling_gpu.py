@@ -67,6 +67,8 @@ def test_roi_pool_full_size_maps_against_numpy():
     maps = torch.from_numpy(feats).cuda()
     out = ops.roi_max_pool(maps, torch.from_numpy(el).cuda(), torch.from_numpy(seg).cuda()).cpu().numpy()
     np.testing.assert_allclose(out, ref, rtol=RTOL, atol=0)
+    one = ops.roi_max_pool(maps, torch.from_numpy(el).cuda(), torch.from_numpy(seg).cuda(), two_stage=False).cpu().numpy()
+    np.testing.assert_allclose(one, ref, rtol=RTOL, atol=0)             # the single-pass form of the same pooling
     per = ops.roi_max_pool(maps, torch.from_numpy(el).cuda(),
                            torch.arange(n + 1, dtype=torch.int32).cuda()).cpu().numpy()
     sel = np.stack([per[a:b].max(axis=0) if b > a else np.zeros(C, dtype=np.float32) for a, b in zip(seg[:-1], seg[1:])])

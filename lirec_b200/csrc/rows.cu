@@ -87,6 +87,7 @@ __device__ __forceinline__ void store_split4(__nv_bfloat16* hi_ptr, __nv_bfloat1
   *reinterpret_cast<uint2*>(lo_ptr) = wl;
 }
 
+constexpr int EF_IDX = 96;     // row triples of a segment staged in shared memory (longer segments read the rest in place)
 __global__ void __launch_bounds__(128)
 expand_fwd_kernel(const ExpandFwdJobs jobs) {
   const ExpandFwdJob& jb = jobs.job[blockIdx.y];
@@ -97,28 +98,42 @@ expand_fwd_kernel(const ExpandFwdJobs jobs) {
   int beg = o, end = o + 1;
   if (jb.seg_off) { beg = jb.seg_off[o]; end = jb.seg_off[o + 1]; }
   const int n = end - beg;
+  // The segment's (clip, track1, track2) triples are fetched ONCE, coalesced, into shared memory: the row
+  // gathers of consecutive context rows then depend on no global load and several of them are in flight
+  // at a time (the kernel was bound by the idx -> row load chain: 70 % long-scoreboard stalls in ncu).
+  __shared__ int32_t s_idx[3 * EF_IDX];
+  for (int k = threadIdx.x; k < 3 * min(n, EF_IDX); k += blockDim.x) s_idx[k] = jb.rows[3 * static_cast<int64_t>(beg) + k];
+  __syncthreads();
   const uint32_t thr = drop_threshold(jb.drop.p);
   for (int j = threadIdx.x * 4; j < J; j += blockDim.x * 4) {
     float4 acc[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
     for (int x = beg; x < end; ++x) {
-      const int3 idx = *reinterpret_cast<const int3*>(jb.rows + 3 * static_cast<int64_t>(x));
+      int3 idx;
+      if (x - beg < EF_IDX) idx = make_int3(s_idx[3 * (x - beg)], s_idx[3 * (x - beg) + 1], s_idx[3 * (x - beg) + 2]);
+      else idx = *reinterpret_cast<const int3*>(jb.rows + 3 * static_cast<int64_t>(x));
       const int u[4] = {idx.x, idx.x, idx.y, idx.z};
-      const uint32_t rkey = drop_row_key(jb.drop.seed, jb.drop.stream_id, static_cast<uint32_t>(x));
+      float4 v[4];
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        if (!src[s]) continue;                      // modality slot absent (Modalities 't' / 'v' / no tracks)
-        float4 v = ld4(src[s] + static_cast<int64_t>(u[s]) * J + j);
-        if (jb.drop.p > 0.f) {
+      for (int s = 0; s < 4; ++s)
+        v[s] = src[s] ? ld4(src[s] + static_cast<int64_t>(u[s]) * J + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (jb.drop.p > 0.f) {
+        const uint32_t rkey = drop_row_key(jb.drop.seed, jb.drop.stream_id, static_cast<uint32_t>(x));
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
           const uint32_t c = static_cast<uint32_t>(jb.drop.col_off + s * J + j);   // multiple of 4
           const uint32_t w0 = drop_word(rkey, c >> 1), w1 = drop_word(rkey, (c >> 1) + 1);
-          if ((w0 & 0xFFFFu) < thr) v.x = 0.f;
-          if ((w0 >> 16) < thr) v.y = 0.f;
-          if ((w1 & 0xFFFFu) < thr) v.z = 0.f;
-          if ((w1 >> 16) < thr) v.w = 0.f;
+          if ((w0 & 0xFFFFu) < thr) v[s].x = 0.f;
+          if ((w0 >> 16) < thr) v[s].y = 0.f;
+          if ((w1 & 0xFFFFu) < thr) v[s].z = 0.f;
+          if ((w1 >> 16) < thr) v[s].w = 0.f;
         }
-        acc[s].x += v.x; acc[s].y += v.y; acc[s].z += v.z; acc[s].w += v.w;
+      }
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        acc[s].x += v[s].x; acc[s].y += v[s].y; acc[s].z += v[s].z; acc[s].w += v[s].w;
       }
     }
     if (jb.seg_off) {
@@ -243,6 +258,7 @@ expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.f;
     const int j = c0 + cq;
+#pragma unroll 2
     for (int q = beg; q < end; ++q) {
       int i, o;
       float w;

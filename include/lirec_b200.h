@@ -155,6 +155,13 @@ int lirec_seg_reduce_f32(const float* x, const int32_t* seg_off, int32_t nseg,
                          int32_t dim, int32_t mode, float* out_f32, int64_t out_f32_ld,
                          void* out_bf16, int64_t out_bf16_ld, void* stream);
 
+/* Same reduction over GATHERED rows: segment s reduces x[row_idx[r]] for r in [seg_off[s], seg_off[s+1]).
+ * The dialog tokens of a clip are the union of the token ranges of every subtitle line that overlaps the
+ * clip's time span (reference text_utils/text_features.py:151-168), not one contiguous range.          */
+int lirec_seg_reduce_gather_f32(const float* x, const int32_t* row_idx, const int32_t* seg_off,
+                                int32_t nseg, int32_t dim, int32_t mode, float* out_f32,
+                                int64_t out_f32_ld, void* out_bf16, int64_t out_bf16_ld, void* stream);
+
 /* ---- ragged row kernels of the modality encoder --------------------------
  * Layer-1 outputs are computed once per UNIQUE bank row (clip text, clip
  * visual, person track).  These kernels expand them to encoder rows by the

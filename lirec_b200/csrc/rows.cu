@@ -19,7 +19,8 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 // NaN propagates like np.max.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-seg_reduce_kernel(const float* __restrict__ x, const int32_t* __restrict__ seg_off, int dim,
+seg_reduce_kernel(const float* __restrict__ x, const int32_t* __restrict__ seg_off,
+                  const int32_t* __restrict__ row_idx, int dim,
                   int mode, float* __restrict__ out_f32, int64_t out_f32_ld,
                   __nv_bfloat16* __restrict__ out_bf16, int64_t out_bf16_ld) {
   const int seg = blockIdx.x;
@@ -27,7 +28,28 @@ seg_reduce_kernel(const float* __restrict__ x, const int32_t* __restrict__ seg_o
   if (col >= dim) return;
   const int beg = seg_off[seg], end = seg_off[seg + 1];
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (end > beg) {
+  if (end > beg && row_idx) {
+    // gathered segment (the token ranges of a clip's dialog lines, text_features.py:151-168): same
+    // reduction over rows x[row_idx[r]]
+    for (int r = beg; r < end; ++r) {
+      const float4 a = ld4(x + static_cast<int64_t>(row_idx[r]) * dim + col);
+      if (mode == 0) {
+        if (r == beg) acc = a;
+        else {
+          if (a.x > acc.x || a.x != a.x) acc.x = a.x;
+          if (a.y > acc.y || a.y != a.y) acc.y = a.y;
+          if (a.z > acc.z || a.z != a.z) acc.z = a.z;
+          if (a.w > acc.w || a.w != a.w) acc.w = a.w;
+        }
+      } else {
+        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+      }
+    }
+    if (mode == 1) {
+      const float inv = 1.0f / static_cast<float>(end - beg);
+      acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    }
+  } else if (end > beg) {
     const float* p = x + static_cast<int64_t>(beg) * dim + col;
     if (mode == 0) {
       acc = ld4(p);
@@ -597,7 +619,7 @@ int gather_rows(const void* bank, int64_t bank_ld, int n_bank, const int32_t* id
 }
 
 int seg_reduce(const float* x, const int32_t* seg_off, int nseg, int dim, int mode, float* out_f32,
-               int64_t out_f32_ld, void* out_bf16, int64_t out_bf16_ld, cudaStream_t stream) {
+               int64_t out_f32_ld, void* out_bf16, int64_t out_bf16_ld, cudaStream_t stream, const int32_t* row_idx) {
   LIREC_REQUIRE(dim > 0 && dim % 4 == 0, "seg_reduce: dim=%d must be a positive multiple of 4", dim);
   LIREC_REQUIRE(mode == 0 || mode == 1, "seg_reduce: mode=%d", mode);
   LIREC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "seg_reduce: x not 16-byte aligned");
@@ -608,7 +630,7 @@ int seg_reduce(const float* x, const int32_t* seg_off, int nseg, int dim, int mo
                 "seg_reduce: bf16 output not 8-byte aligned");
   if (nseg <= 0) return LIREC_OK;
   dim3 grid(nseg, (dim / 4 + 127) / 128);
-  seg_reduce_kernel<<<grid, 128, 0, stream>>>(x, seg_off, dim, mode, out_f32, out_f32_ld,
+  seg_reduce_kernel<<<grid, 128, 0, stream>>>(x, seg_off, row_idx, dim, mode, out_f32, out_f32_ld,
                                               reinterpret_cast<__nv_bfloat16*>(out_bf16), out_bf16_ld);
   LIREC_CUDA_OK(cudaGetLastError());
   note_launch();
@@ -730,7 +752,16 @@ extern "C" int lirec_seg_reduce_f32(const float* x, const int32_t* seg_off, int3
                                     int64_t out_bf16_ld, void* stream) {
   LIREC_ENTER();
   return rows::seg_reduce(x, seg_off, nseg, dim, mode, out_f32, out_f32_ld, out_bf16, out_bf16_ld,
-                          static_cast<cudaStream_t>(stream));
+                          static_cast<cudaStream_t>(stream), nullptr);
+}
+
+extern "C" int lirec_seg_reduce_gather_f32(const float* x, const int32_t* row_idx, const int32_t* seg_off,
+                                           int32_t nseg, int32_t dim, int32_t mode, float* out_f32,
+                                           int64_t out_f32_ld, void* out_bf16, int64_t out_bf16_ld, void* stream) {
+  LIREC_ENTER();
+  LIREC_REQUIRE(row_idx != nullptr, "seg_reduce_gather: null row index");
+  return rows::seg_reduce(x, seg_off, nseg, dim, mode, out_f32, out_f32_ld, out_bf16, out_bf16_ld,
+                          static_cast<cudaStream_t>(stream), row_idx);
 }
 
 extern "C" int lirec_rows_expand_fwd(const float* r1_txt, const float* r1_vis, const float* r1_tr1,

@@ -65,7 +65,7 @@ struct TransposeJobs {
 };
 
 int seg_reduce(const float* x, const int32_t* seg_off, int nseg, int dim, int mode, float* out_f32,
-               int64_t out_f32_ld, void* out_bf16, int64_t out_bf16_ld, cudaStream_t stream);
+               int64_t out_f32_ld, void* out_bf16, int64_t out_bf16_ld, cudaStream_t stream, const int32_t* row_idx = nullptr);
 int expand_fwd(const ExpandFwdJobs& jobs, cudaStream_t stream);
 int expand_bwd(const ExpandBwdJobs& jobs, cudaStream_t stream);
 int split_f32(const float* x, int64_t ld, int rows, int cols, void* out, int64_t out_ld, int pad_cols,

@@ -58,12 +58,20 @@ def gemm_grouped(problems):
     _ext.gemm_grouped(problems)
 
 
-def seg_reduce(x, seg_off, mode="max", out_f32=None, out_bf16=None):
-    """Segmented max/mean of ragged fp32 rows. x [total, dim], seg_off int32 [nseg+1]."""
+def seg_reduce(x, seg_off, mode="max", out_f32=None, out_bf16=None, row_idx=None):
+    """Segmented max/mean of ragged fp32 rows. x [total, dim], seg_off int32 [nseg+1].  row_idx (int32):
+    segment s reduces the gathered rows x[row_idx[seg_off[s]:seg_off[s+1]]] instead of a contiguous range."""
     assert x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
     assert seg_off.dtype == torch.int32
     nseg = seg_off.numel() - 1
     L = _ext.lib()
+    if row_idx is not None:
+        assert row_idx.dtype == torch.int32
+        _ext.check(L.lirec_seg_reduce_gather_f32(
+            _ext.ptr(x), _ext.ptr(row_idx), _ext.ptr(seg_off), nseg, x.shape[1], 0 if mode == "max" else 1,
+            _ext.ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
+            _ext.ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, _ext.stream_ptr()))
+        return
     _ext.check(L.lirec_seg_reduce_f32(
         _ext.ptr(x), _ext.ptr(seg_off), nseg, x.shape[1], 0 if mode == "max" else 1,
         _ext.ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,

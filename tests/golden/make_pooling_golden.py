@@ -49,6 +49,46 @@ def make_world(seed=0, T=9, C=32, H=13, W=30):
     return feats, frame2time, dims, time_nodes, tracks
 
 
+def text_world(seed=1, n_lines=9, dim=24):
+    rng = np.random.RandomState(seed)
+    times, ranges, start, tok = [], [], 0, 0
+    for i in range(n_lines):
+        dur = int(rng.randint(1, 5))
+        gap = int(rng.randint(0, 4))
+        times.append((start + gap, start + gap + dur))
+        n = int(rng.randint(2, 9))
+        ranges.append(list(range(tok, tok + n)))
+        tok += n
+        start += gap + dur - (1 if rng.rand() < 0.3 else 0)      # some lines overlap in time
+    feats = (rng.randint(-40, 41, size=(tok, dim)) / 8.0).astype(np.float32)
+    nodes = [dict(start=0, end=2), dict(start=5, end=6), dict(start=3, end=40), dict(start=200, end=210),
+             dict(start=times[4][0], end=times[4][0]), dict(start=times[2][1], end=times[6][0])]
+    return feats, times, ranges, nodes
+
+
+def text_golden(opt):
+    import contextlib
+    import io
+    tf_mod = rs._state["modules"]["text_utils.text_features"]
+    feats, times, ranges, nodes = text_world()
+    opt.text_dim, opt.contextualization = feats.shape[1], "second-to-last"
+    t = tf_mod.TextFeatures.__new__(tf_mod.TextFeatures)
+    t.features, t.video_idx = feats, "tt"
+    t.times = [tf_mod.Time(a, b) for a, b in times]
+    t.time_idx2token_range = ranges
+    t.dialogs = []
+    out = {"features": feats, "meta": json.dumps(dict(times=times, ranges=ranges, nodes=nodes))}
+    for i, tn in enumerate(nodes):
+        with contextlib.redirect_stdout(io.StringIO()):          # the reference prints a line per call (:145)
+            rows = t.get_features_by_time(tn)
+        out["rows_%d" % i] = np.asarray(rows, dtype=np.float32)
+        out["max_%d" % i] = np.max(rows, axis=0).reshape(1, -1).astype(np.float32)      # mixed_features.py:61
+    path = os.path.join(HERE, "pooling_text.npz")
+    np.savez_compressed(path, **out)
+    opt.text_dim = 768
+    print(path, "%.1f KB" % (os.path.getsize(path) / 1e3), [out["rows_%d" % i].shape for i in range(len(nodes))])
+
+
 def main():
     opt, _ = rs.load_dataloader()
     mods = rs._state["modules"]
@@ -84,6 +124,7 @@ def main():
             out[k] = a32
     path = os.path.join(HERE, "pooling_visual.npz")
     np.savez_compressed(path, **out)
+    text_golden(opt)
     print(path, "%.1f KB" % (os.path.getsize(path) / 1e3), "nan tracks:",
           [i for i in range(len(tracks)) if np.isnan(out["track_max_%d" % i]).any()])
 

@@ -63,3 +63,32 @@ def test_frame_and_box_arithmetic_matches_the_reference(opt_preset):
         np.testing.assert_allclose(got, ref, rtol=2e-6, atol=0)
     # the frame-index == T element is a zero row, not a skipped one
     assert hv.track_elements(meta["tracks"][5])[0, 0] == -1
+
+
+GT = os.path.join(HERE, "golden", "pooling_text.npz")
+
+
+def load_text_world():
+    g = np.load(GT)
+    meta = json.loads(str(g["meta"]))
+    return g, meta, g["features"].astype(np.float32)
+
+
+def test_token_ranges_match_the_reference():
+    """Subtitle-line overlap -> token index list (reference text_features.py:151-168): the gathered rows equal
+    the rows the reference's unmodified TextFeatures returned, a clip without dialog gives one zero row."""
+    from lirec_b200.text_utils.text_features import TextFeatures, Time
+    g, meta, feats = load_text_world()
+    t = TextFeatures.__new__(TextFeatures)
+    t.times = [Time(a, b) for a, b in meta["times"]]
+    t.time_idx2token_range = meta["ranges"]
+    empty = 0
+    for i, tn in enumerate(meta["nodes"]):
+        rng = t.tokens_range(tn)
+        ref = g["rows_%d" % i]
+        if not rng:
+            assert ref.shape == (1, feats.shape[1]) and not ref.any()
+            empty += 1
+        else:
+            assert np.array_equal(feats[rng], ref)
+    assert empty >= 1

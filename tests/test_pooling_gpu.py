@@ -73,3 +73,33 @@ def test_roi_pool_full_size_maps_against_numpy():
                            torch.arange(n + 1, dtype=torch.int32).cuda()).cpu().numpy()
     sel = np.stack([per[a:b].max(axis=0) if b > a else np.zeros(C, dtype=np.float32) for a, b in zip(seg[:-1], seg[1:])])
     assert np.array_equal(out, sel)                                   # max = exact selection of the means
+
+
+def test_text_pooling_matches_the_reference():
+    """Gathered segmented max over dialog tokens (lirec_seg_reduce_gather_f32): bit-exact with np.max over the rows
+    the reference's unmodified TextFeatures returned; zero row for clips without dialog."""
+    from test_pooling_cpu import load_text_world
+    from lirec_b200.text_utils.text_features import TextFeatures
+    g, meta, feats = load_text_world()
+    t = TextFeatures(feats, meta["times"], meta["ranges"], device="cuda")
+    for i, tn in enumerate(meta["nodes"]):
+        assert np.array_equal(t.get_features_by_time(tn).cpu().numpy(), g["rows_%d" % i])
+    pooled = t.pool(meta["nodes"]).cpu().numpy()
+    for i in range(len(meta["nodes"])):
+        assert np.array_equal(pooled[i:i + 1], g["max_%d" % i]), i
+    bank = torch.empty(len(meta["nodes"]), feats.shape[1], dtype=torch.bfloat16, device="cuda")
+    t.pool(meta["nodes"], out_bf16=bank)
+    assert torch.equal(bank.cpu(), torch.from_numpy(pooled).to(torch.bfloat16))
+    # gathered mean against numpy on random index lists
+    from lirec_b200 import ops
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((500, 768)).astype(np.float32)
+    lists = [rng.integers(0, 500, size=int(n)) for n in rng.integers(0, 40, size=30)]
+    off = np.zeros(31, dtype=np.int32)
+    np.cumsum([len(l) for l in lists], out=off[1:])
+    idx = np.concatenate(lists).astype(np.int32)
+    out = torch.empty(30, 768, device="cuda")
+    ops.seg_reduce(torch.from_numpy(x).cuda(), torch.from_numpy(off).cuda(), "mean", out_f32=out,
+                   row_idx=torch.from_numpy(idx).cuda())
+    ref = np.stack([x[l].mean(0) if len(l) else np.zeros(768, dtype=np.float32) for l in lists])
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-6)

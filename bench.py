@@ -346,8 +346,15 @@ def run_ours(args):
     alg_flops_step = algorithmic_flops(nc, nx)
     achieved = alg_flops_step * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     executed = exec_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "lirec_gemm_tcgen05_kernel", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+    traffic = None          # DRAM bytes of the GEMM launches of one step, from the committed ncu --set full capture
+    tpath = os.path.join(HERE, "profiles", "r01_gemm_dram_traffic.json")
+    if os.path.exists(tpath) and args.batch == 1024:
+        with open(tpath) as f:
+            traffic = int(json.load(f)["bytes_per_step"])
+    roofline = {"bound": "tensor", "kernel": "lirec_gemm_tcgen05_pair_kernel", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": "bytes per step over the 8 GEMM launches (profiles/r01_gemm_dram_traffic.json)",
+                "peak_source": peak_src,
                 "launches_per_step": len(prof) / float(args.steps), "gemm_ms_per_step": gemm_ms / args.steps,
                 "executed_tflops": executed, "executed_frac": executed / peak,
                 "note": "achieved = algorithmic fwd+bwd FLOPs of the step (SURVEY.md §8d, valid rows, no credit "

@@ -280,7 +280,6 @@ expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.f;
     const int j = c0 + cq;
-#pragma unroll 2
     for (int q = beg; q < end; ++q) {
       int i, o;
       float w;

@@ -60,6 +60,9 @@ def parse_args():
     ap.add_argument("--dump_profile", default="", help="write the per-launch GEMM event timings to this file")
     ap.add_argument("--nccl_allreduce", action="store_true",
                     help="N > 1: use ncclAllReduce + Adam instead of the fused in-switch reduce + Adam kernel")
+    ap.add_argument("--autograd_step", action="store_true",
+                    help="drive the step through model()/loss()/backward()/optimizer.step() and the autograd engine "
+                         "(the drop-in surface) instead of lirec_b200.mlp.train.train_step's native sequence")
     ap.add_argument("--ncu_window", action="store_true",
                     help="bracket the device-resident timed loop with cudaProfilerStart/Stop "
                          "(run under `ncu --profile-from-start off`; numbers printed under ncu are not bench values)")
@@ -183,13 +186,14 @@ def run_ours(args):
     torch.cuda.synchronize()
     in_bytes = sum(h.h2d_bytes() for h in host) / len(host)
 
-    def step(pb, grad_scale_world=True):
-        out = model(pb)
-        lv = loss_fn(out, {})
-        optimizer.zero_grad()
-        lv.backward()
-        dp.reduce_and_step(model, optimizer, fused)
-        return lv
+    # the loop body a user runs: lirec_b200/mlp/train.py:train_step (forward + loss + backward as three
+    # native calls, then gradient exchange + Adam); --autograd_step takes the reference's
+    # model() / loss() / zero_grad() / backward() / step() sequence through the autograd engine instead
+    import lirec_b200.mlp.train as TR
+    opt.native_step = 0 if args.autograd_step else 1
+
+    def step(pb):
+        return TR.train_step(model, loss_fn, optimizer, pb, world, fused)
 
     def barrier():
         if world > 1:
@@ -379,6 +383,8 @@ def run_ours(args):
                        "clips_per_gpu": args.batch, "global_batch": args.batch * world,
                        "candidate_rows_per_step": float(nc), "context_rows_per_step": float(nx),
                        "parallelism": "dp%d" % world, "optimizer": "fused flat Adam",
+                       "step_api": ("model()/loss()/backward()/optimizer.step() (autograd)" if args.autograd_step
+                                    else "lirec_b200.mlp.train.train_step (native forward+loss+backward, no autograd)"),
                        "gradient_exchange": ("none (1 GPU)" if world == 1 else
                                              "in-switch multimem reduce fused with Adam (lirec_dp_allreduce_adam)"
                                              if fused is not None else "ncclAllReduce fp32 + Adam"),

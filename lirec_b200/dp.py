@@ -140,9 +140,7 @@ class SwitchReduceAdam:
         ops.dp_allreduce_adam(m._flat, self.grad, self.hdl.multicast_ptr, o._m, o._v, m._flat_bf16, g["lr"],
                               g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], o._t, scale, self.rank,
                               self.world, self.flag_hdl.buffer_ptrs_dev, self.ws, self.epoch)
-        for p in m._param_list:
-            o.state[p]["step"] += 1
-        m.mark_bf16_fresh()
+        m.mark_bf16_fresh()          # FlatAdam materialises the per-parameter step counters lazily
 
 
 def reduce_and_step(model, optimizer, fused=None, local_clips=None, global_clips=None):

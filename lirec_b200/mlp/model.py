@@ -63,19 +63,14 @@ class ModelOutput(dict):
 
 
 class _ModelFn(torch.autograd.Function):
-    """lirec_model_forward / lirec_model_backward as one autograd node over all parameters."""
+    """lirec_model_forward / lirec_model_backward as one autograd node.  Parameter gradients are
+    written by the backward kernels straight into the flat gradient buffer that every `p.grad`
+    aliases (`_publish_grads`), so the node takes ONE parameter as its differentiable input — the
+    anchor that makes the outputs require grad — instead of all 38 (host time per step)."""
 
     @staticmethod
-    def forward(ctx, module, pb, training, seed, *params):
-        batch_c = module._batch_struct(pb, training, seed)
-        nbytes = _ext.lib().lirec_model_workspace_bytes(C.byref(module._cfg_c), C.byref(batch_c))
-        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=pb.device)
-        Ni = pb.n_cand
-        inters = torch.empty(Ni, module.n_classes, dtype=torch.float32, device=pb.device)
-        rels = torch.empty(Ni, module.n_rels, dtype=torch.float32, device=pb.device) if module._ctx else None
-        _ext.check(_ext.lib().lirec_model_forward(
-            C.byref(module._cfg_c), C.byref(module._params_c), C.byref(batch_c), ws.data_ptr(), ws.numel(),
-            inters.data_ptr(), rels.data_ptr() if rels is not None else None, _ext.stream_ptr()))
+    def forward(ctx, module, pb, training, seed, anchor):
+        batch_c, ws, inters, rels = module._run_forward(pb, training, seed)
         ctx.module, ctx.pb, ctx.batch_c, ctx.ws = module, pb, batch_c, ws
         if rels is None:
             none = inters.new_empty(0)
@@ -85,18 +80,9 @@ class _ModelFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_inters, d_rels):
-        m = ctx.module
-        d_inters = d_inters.contiguous()
-        d_rels_ptr = None
-        if m._ctx:
-            d_rels = d_rels.contiguous()
-            d_rels_ptr = d_rels.data_ptr()
-        _ext.check(_ext.lib().lirec_model_backward(
-            C.byref(m._cfg_c), C.byref(m._params_c), C.byref(ctx.batch_c), ctx.ws.data_ptr(), ctx.ws.numel(),
-            d_inters.data_ptr(), d_rels_ptr, _ext.stream_ptr()))
-        m._publish_grads()
+        ctx.module._run_backward(ctx.batch_c, ctx.ws, d_inters, d_rels)
         ctx.ws = None
-        return (None,) * (4 + len(m._param_list))
+        return None, None, None, None, None
 
 
 class _HotPath(nn.Module):
@@ -148,11 +134,19 @@ class _HotPath(nn.Module):
         self._flat = self._flat_grad = self._flat_bf16 = None
         self._param_list = None
         self._versions = None
+        self._dirty = True
         self._step = 0
 
     # ---- flat parameter storage ----------------------------------------------------------------
     def _sync_flat(self):
         """(Re)build the flat fp32 / grad / bf16 buffers and point every parameter into them."""
+        pl = self._param_list
+        if pl is not None and not self._dirty and self._flat is not None:
+            # fast path (every step): nn.Module._apply (.to / .cuda / .float) marks the model dirty;
+            # the two end-point checks catch a parameter re-pointed by hand
+            if pl[0].data_ptr() == self._flat.data_ptr() and \
+                    pl[-1].data_ptr() == self._flat.data_ptr() + 4 * self._offsets[-1]:
+                return
         params = [p for p in self.parameters()]
         dev = params[0].device
         if dev.type != "cuda":
@@ -166,6 +160,7 @@ class _HotPath(nn.Module):
                     ok = False
                     break
         if ok:
+            self._dirty = False
             return
         _ext.require_device(dev)
         offsets, total = [], 0
@@ -180,7 +175,12 @@ class _HotPath(nn.Module):
         self._flat_grad = torch.zeros_like(flat)
         self._flat_bf16 = torch.zeros(total, dtype=torch.bfloat16, device=dev)
         self._versions = None
+        self._dirty = False
         self._build_structs()
+
+    def _apply(self, fn, *args, **kwargs):
+        self._dirty = True                    # parameters may have been re-allocated (model.to(...))
+        return super()._apply(fn, *args, **kwargs)
 
     def use_grad_buffer(self, buf):
         """Adopt `buf` (flat fp32, same size) as the gradient buffer — e.g. symmetric memory for the
@@ -199,12 +199,12 @@ class _HotPath(nn.Module):
 
     def _publish_grads(self):
         """Expose the flat gradient buffer through p.grad (zero-copy when p.grad is None)."""
-        for i, p in enumerate(self._param_list):
-            g = self._grad_view(i)
-            if p.grad is None:
+        for p, g in zip(self._param_list, self._grad_views):
+            pg = p.grad
+            if pg is None:
                 p.grad = g
-            elif p.grad.data_ptr() != g.data_ptr():
-                p.grad.add_(g)
+            elif pg is not g and pg.data_ptr() != g.data_ptr():
+                pg.add_(g)
             # else: p.grad already aliases the flat buffer, which backward has just overwritten
 
     def _refresh_bf16(self):
@@ -252,30 +252,67 @@ class _HotPath(nn.Module):
         cfg.dropout_p = float(self.dropout.p)
         cfg.slot_mask = int(self._slot_mask)
         self._params_c, self._cfg_c = P, cfg
+        self._grad_views = [self._grad_view(i) for i in range(len(self._param_list))]
+        self._anchor = next((p for p in self._param_list if p.requires_grad), self._param_list[0])
 
     def _batch_struct(self, pb, training, seed):
-        b = _ext.Batch()
-        b.clip_bank, b.clip_ld = pb.clip_bank.data_ptr(), pb.clip_bank.stride(0)
-        b.n_clip, b.n_clip_ints = pb.n_clip, pb.n_clip_ints
-        b.track_bank, b.track_ld = pb.track_bank.data_ptr(), pb.track_bank.stride(0)
-        b.n_track, b.n_track_ints = pb.n_track, pb.n_track_ints
-        b.n_cand, b.n_ctx_rows = pb.n_cand, pb.n_ctx_rows if self._ctx else 0
-        b.cand_rows = pb["cand_rows"].data_ptr()
-        if self._ctx:
-            if not pb.has_ctx:
-                raise RuntimeError("the model has a context branch but the batch carries no context tables")
-            b.ctx_rows, b.ctx_off = pb["ctx_rows"].data_ptr(), pb["ctx_off"].data_ptr()
-            b.ctx_owner = pb["ctx_owner"].data_ptr()
-        else:  # ints-only models ignore context tables; bank prefixes still apply
-            b.n_clip, b.n_track = pb.n_clip_ints, pb.n_track_ints
-        for s in range(3):
-            b.inv_cand_off[s] = pb["inv_cand_off%d" % s].data_ptr()
-            b.inv_cand_idx[s] = pb["inv_cand_idx%d" % s].data_ptr()
+        """lirec_batch of `pb`; the pointer part is built once per (batch, branch set) and cached on the
+        batch — per step only the dropout seed and the training flag change."""
+        cache = pb.__dict__.setdefault("_c_batch", {})
+        b = cache.get(self._ctx)
+        if b is None:
+            b = _ext.Batch()
+            b.clip_bank, b.clip_ld = pb.clip_bank.data_ptr(), pb.clip_bank.stride(0)
+            b.n_clip, b.n_clip_ints = pb.n_clip, pb.n_clip_ints
+            b.track_bank, b.track_ld = pb.track_bank.data_ptr(), pb.track_bank.stride(0)
+            b.n_track, b.n_track_ints = pb.n_track, pb.n_track_ints
+            b.n_cand, b.n_ctx_rows = pb.n_cand, pb.n_ctx_rows if self._ctx else 0
+            b.cand_rows = pb.table_ptr("cand_rows")
             if self._ctx:
-                b.inv_ctx_off[s] = pb["inv_ctx_off%d" % s].data_ptr()
-                b.inv_ctx_idx[s] = pb["inv_ctx_idx%d" % s].data_ptr()
+                if not pb.has_ctx:
+                    raise RuntimeError("the model has a context branch but the batch carries no context tables")
+                b.ctx_rows, b.ctx_off = pb.table_ptr("ctx_rows"), pb.table_ptr("ctx_off")
+                b.ctx_owner = pb.table_ptr("ctx_owner")
+            else:  # ints-only models ignore context tables; bank prefixes still apply
+                b.n_clip, b.n_track = pb.n_clip_ints, pb.n_track_ints
+            for s in range(3):
+                b.inv_cand_off[s] = pb.table_ptr("inv_cand_off%d" % s)
+                b.inv_cand_idx[s] = pb.table_ptr("inv_cand_idx%d" % s)
+                if self._ctx:
+                    b.inv_ctx_off[s] = pb.table_ptr("inv_ctx_off%d" % s)
+                    b.inv_ctx_idx[s] = pb.table_ptr("inv_ctx_idx%d" % s)
+            cache[self._ctx] = b
+        b = _ext.Batch.from_buffer_copy(b)       # backward keeps this step's copy (its dropout seed)
         b.seed, b.training = int(seed) & 0xFFFFFFFF, int(bool(training))
         return b
+
+    # ---- the two native calls ------------------------------------------------------------------
+    def _run_forward(self, pb, training, seed):
+        """lirec_model_forward on `pb`.  Returns (batch struct, workspace, inters [Ni,C], rels [Ni,R] | None);
+        the first two are what lirec_model_backward needs."""
+        batch_c = self._batch_struct(pb, training, seed)
+        L = _ext.lib()
+        nbytes = L.lirec_model_workspace_bytes(C.byref(self._cfg_c), C.byref(batch_c))
+        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=pb.device)
+        Ni = pb.n_cand
+        inters = torch.empty(Ni, self.n_classes, dtype=torch.float32, device=pb.device)
+        rels = torch.empty(Ni, self.n_rels, dtype=torch.float32, device=pb.device) if self._ctx else None
+        _ext.check(L.lirec_model_forward(
+            C.byref(self._cfg_c), C.byref(self._params_c), C.byref(batch_c), ws.data_ptr(), ws.numel(),
+            inters.data_ptr(), rels.data_ptr() if rels is not None else None, _ext.stream_ptr()))
+        return batch_c, ws, inters, rels
+
+    def _run_backward(self, batch_c, ws, d_inters, d_rels):
+        """lirec_model_backward: every parameter gradient of the step into the flat gradient buffer."""
+        d_inters = d_inters.contiguous()
+        d_rels_ptr = None
+        if self._ctx:
+            d_rels = d_rels.contiguous()
+            d_rels_ptr = d_rels.data_ptr()
+        _ext.check(_ext.lib().lirec_model_backward(
+            C.byref(self._cfg_c), C.byref(self._params_c), C.byref(batch_c), ws.data_ptr(), ws.numel(),
+            d_inters.data_ptr(), d_rels_ptr, _ext.stream_ptr()))
+        self._publish_grads()
 
     # ---- batches -------------------------------------------------------------------------------
     def _packed(self, x):
@@ -311,7 +348,10 @@ class _HotPath(nn.Module):
         training = self.training and self.dropout.p > 0
         if seed is None:
             seed = self.next_seed() if training else 0
-        inters, rels = _ModelFn.apply(self, pb, training, seed, *self._param_list)
+        anchor = self._anchor
+        if not anchor.requires_grad:             # parameters frozen since the structs were built
+            anchor = self._anchor = next((p for p in self._param_list if p.requires_grad), anchor)
+        inters, rels = _ModelFn.apply(self, pb, training, seed, anchor)
         return ModelOutput(pb, inters, rels if self._ctx else None, dense_tracks=(self.kind == "maxtracks"))
 
 
@@ -381,21 +421,39 @@ def _batch_of(output, args):
     raise TypeError("lirec_b200 losses expect the ModelOutput returned by a lirec_b200 model")
 
 
-class MaxMarginCrossEntropyLoss(nn.Module):
+class _FusedLoss(nn.Module):
+    """Base of the five losses.  `terms_and_grads(x, args)` runs the fused forward+gradient kernels and
+    returns (loss terms, d loss / d inters | None, d loss / d rels | None); `forward` wraps that in one
+    autograd node, `train_step` below consumes it directly."""
+
+    def terms_and_grads(self, x, args):
+        raise NotImplementedError
+
+    def forward(self, x, args):
+        terms, d_i, d_r = self.terms_and_grads(x, args)
+        grads, logits = [], []
+        if d_i is not None:
+            grads.append(d_i), logits.append(x.ragged_inters)
+        if d_r is not None:
+            grads.append(d_r), logits.append(x.ragged_rels)
+        return _LossFn.apply(terms, tuple(grads), *logits)
+
+
+class MaxMarginCrossEntropyLoss(_FusedLoss):
     """Reference: mlp/model.py:422-441."""
 
     def __init__(self):
         super().__init__()
         self.m = opt.margin
 
-    def forward(self, x, args):
+    def terms_and_grads(self, x, args):
         pb = _batch_of(x, args)
         logits = x.ragged_inters
         terms, d = ops.loss_rowmargin(logits, pb["labels"], pb.multilab, self.m, 1.0 / logits.shape[0])
-        return _LossFn.apply(terms, (d,), logits)
+        return terms, d, None
 
 
-class MultiTaskMaxMargin(nn.Module):
+class MultiTaskMaxMargin(_FusedLoss):
     """Reference: mlp/model.py:381-419."""
 
     def __init__(self, n_rels=0):
@@ -403,13 +461,13 @@ class MultiTaskMaxMargin(nn.Module):
         self.m = opt.margin
         self.n_rels = n_rels
 
-    def forward(self, x, args):
+    def terms_and_grads(self, x, args):
         pb = _batch_of(x, args)
-        terms, grads, logits = [], [], []
+        terms, d_i, d_r = [], None, None
         if opt.ints == 1:
             li = x.ragged_inters
-            t, d = ops.loss_rowmargin(li, pb["labels"], pb.multilab, self.m, opt.lymbda / li.shape[0])
-            terms.append(t), grads.append(d), logits.append(li)
+            t, d_i = ops.loss_rowmargin(li, pb["labels"], pb.multilab, self.m, opt.lymbda / li.shape[0])
+            terms.append(t)
         if opt.ctx == 1:
             lr = x.ragged_rels
             host = pb.host if pb.device is not None else pb
@@ -418,12 +476,12 @@ class MultiTaskMaxMargin(nn.Module):
             if n_sel:
                 sel = pb["rels_label"].clone()
                 sel[sel == self.n_rels] = -1                     # rows labelled None are skipped (model.py:406)
-                t, d = ops.loss_rowmargin(lr, sel, None, self.m, 1.0 / n_sel)
-                terms.append(t), grads.append(d), logits.append(lr)
-        return _LossFn.apply(torch.cat(terms), tuple(grads), *logits)
+                t, d_r = ops.loss_rowmargin(lr, sel, None, self.m, 1.0 / n_sel)
+                terms.append(t)
+        return torch.cat(terms), d_i, d_r
 
 
-class _TrackLoss(nn.Module):
+class _TrackLoss(_FusedLoss):
     def _run(self, x, args, n_rels, lymbda):
         assert opt.tr_maximize
         assert not (opt.tr_cat_distr and opt.tr_correct)                 # model.py:469, 539
@@ -436,9 +494,7 @@ class _TrackLoss(nn.Module):
             max_neg=bool(opt.tr_max_neg and opt.tr_sum_max_flag), max_slots=pb.n_slots,
             cat_distr=bool(opt.tr_cat_distr), seed=(int(opt.seed) * 0x9E3779B1 + self._draws * 0xC2B2AE35))
         self.last_assignment = assign
-        if n_rels:
-            return _LossFn.apply(terms, (d_i, d_r), li, lr)
-        return _LossFn.apply(terms, (d_i,), li)
+        return terms, d_i, (d_r if n_rels else None)
 
 
 class MarginLoss(_TrackLoss):
@@ -448,7 +504,7 @@ class MarginLoss(_TrackLoss):
         super().__init__()
         self.m = opt.tr_margin
 
-    def forward(self, input, args):
+    def terms_and_grads(self, input, args):
         return self._run(input, args, 0, 1.0)
 
 
@@ -460,11 +516,11 @@ class MarginTrackRelsLoss(_TrackLoss):
         self.m = opt.tr_margin
         self.n_rels = n_rels
 
-    def forward(self, x, args):
+    def terms_and_grads(self, x, args):
         return self._run(x, args, self.n_rels, opt.lymbda)
 
 
-class MultiTaskCrossEntropyLoss(nn.Module):
+class MultiTaskCrossEntropyLoss(_FusedLoss):
     """Reference: mlp/model.py:357-378 (never selected by create_model, model.py:586-597): softmax
     cross-entropy of the interaction logits (optionally class-weighted) plus that of the relationship
     logits of the rows whose label is not None, both as fused forward+gradient kernels."""
@@ -474,7 +530,7 @@ class MultiTaskCrossEntropyLoss(nn.Module):
         self.n_classes, self.n_rels = n_classes, n_rels
         self.weights = None if weights is None else torch.tensor(weights).float()
 
-    def forward(self, x, args):
+    def terms_and_grads(self, x, args):
         pb = _batch_of(x, args)
         host = pb.host if pb.device is not None else pb
         li = x.ragged_inters
@@ -483,17 +539,45 @@ class MultiTaskCrossEntropyLoss(nn.Module):
             raise RuntimeError("MultiTaskCrossEntropyLoss expects one interaction row per clip")
         w = None if self.weights is None else self.weights.to(li.device)
         denom = float(self.weights[torch.as_tensor(host["labels"]).long()].sum()) if w is not None else li.shape[0]
-        t, d = ops.loss_ce(li, lab_i, w, 1.0 / denom)
-        terms, grads, logits = [t], [d], [li]
+        t, d_i = ops.loss_ce(li, lab_i, w, 1.0 / denom)
+        terms, d_r = [t], None
         if x.ragged_rels is not None:
             lab = host["rels_label"]
             n_sel = int((lab != self.n_rels).sum())
             if n_sel:
                 sel = pb["rels_label"].clone()
                 sel[sel == self.n_rels] = -1                     # rows labelled None are skipped (model.py:369)
-                t, d = ops.loss_ce(x.ragged_rels, sel, None, 1.0 / n_sel)
-                terms.append(t), grads.append(d), logits.append(x.ragged_rels)
-        return _LossFn.apply(torch.cat(terms), tuple(grads), *logits)
+                t, d_r = ops.loss_ce(x.ragged_rels, sel, None, 1.0 / n_sel)
+                terms.append(t)
+        return torch.cat(terms), d_i, d_r
+
+
+def train_step(model, loss, x, seed=None):
+    """forward + loss + backward of one iteration WITHOUT the autograd engine: the loss kernels already
+    emit d loss / d logits, so `loss(model(x), x).backward()` (mlp/train.py:57-62) is three native calls
+    in a row.  Gradients land in the flat buffer behind every `p.grad` exactly as after `.backward()`
+    (bit-identical: the autograd path multiplies them by the incoming 1.0); the caller then runs
+    `optimizer.step()`.  Returns the loss as a 0-d device tensor.  At the reference's batch size (64
+    clips) the host time of the autograd round trip exceeded the device time of the whole step."""
+    if not isinstance(model, _HotPath) or not isinstance(loss, _FusedLoss):
+        raise TypeError("train_step needs a lirec_b200 model and a lirec_b200 loss")
+    model._sync_flat()
+    model._refresh_bf16()
+    pb = model._packed(x)
+    training = model.training and model.dropout.p > 0
+    if seed is None:
+        seed = model.next_seed() if training else 0
+    with torch.no_grad():
+        batch_c, ws, inters, rels = model._run_forward(pb, training, seed)
+        out = ModelOutput(pb, inters, rels if model._ctx else None, dense_tracks=(model.kind == "maxtracks"))
+        terms, d_i, d_r = loss.terms_and_grads(out, x if isinstance(x, dict) else {})
+        value = terms.sum()
+        if d_i is None:
+            d_i = torch.zeros_like(inters)
+        if d_r is None and model._ctx:
+            d_r = torch.zeros_like(rels)
+        model._run_backward(batch_c, ws, d_i, d_r)
+    return value
 
 
 # =================================================================================================
@@ -523,8 +607,6 @@ class FlatAdam(torch.optim.Optimizer):
         self._t += 1
         ops.adam_flat(m._flat, m._flat_grad, self._m, self._v, m._flat_bf16, g["lr"], g["betas"][0],
                       g["betas"][1], g["eps"], g["weight_decay"], self._t, grad_scale)
-        for p in m._param_list:
-            self.state[p]["step"] += 1
         m.mark_bf16_fresh()
 
     def zero_grad(self, set_to_none=True):
@@ -532,6 +614,39 @@ class FlatAdam(torch.optim.Optimizer):
         if set_to_none:
             for p in self.model._param_list:
                 p.grad = None
+
+    # The per-parameter 'step' counters of torch.optim.Adam's state layout are all equal to the
+    # number of fused steps taken; they are materialised when the state is looked at, not 38 times
+    # per step.
+    def _sync_steps(self):
+        for st in self.state.values():
+            st["step"].fill_(float(self._t))
+
+    def state_dict(self):
+        self._sync_steps()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        """Accepts a torch.optim.Adam / FlatAdam state (reference checkpoints: mlp/train.py:84-106):
+        the moments are copied into the flat buffers, which the per-parameter state keeps aliasing."""
+        super().load_state_dict(state_dict)
+        m, steps = self.model, []
+        with torch.no_grad():
+            for i, p in enumerate(m._param_list):
+                off, n = m._offsets[i], p.numel()
+                st = self.state.get(p)
+                mv, vv = self._m[off:off + n].view(p.shape), self._v[off:off + n].view(p.shape)
+                if st is None or "exp_avg" not in st:      # fresh parameter (no step taken when saved)
+                    mv.zero_(), vv.zero_()
+                    step = 0.0
+                else:
+                    mv.copy_(st["exp_avg"]), vv.copy_(st["exp_avg_sq"])
+                    step = float(st["step"])
+                steps.append(step)
+                self.state[p] = {"step": torch.tensor(step), "exp_avg": mv, "exp_avg_sq": vv}
+        if len(set(steps)) > 1:
+            raise RuntimeError("FlatAdam needs one common step count for all parameters, got %s" % sorted(set(steps)))
+        self._t = int(steps[0]) if steps else 0
 
 
 def create_model(n_classes, n_rels=0):

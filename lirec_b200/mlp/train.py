@@ -15,6 +15,8 @@ import torch
 
 from lirec_b200 import dp
 from lirec_b200.mixed_utils.classification_dataloader import packed_loader
+from lirec_b200.mlp.model import _FusedLoss, _HotPath
+from lirec_b200.mlp.model import train_step as native_train_step
 from lirec_b200.mlp.test import testing
 from lirec_b200.utils.arg_pars import opt
 from lirec_b200.utils.model_saver import ModelSaver
@@ -23,11 +25,17 @@ from lirec_b200.utils.util_functions import Averaging, dir_check
 
 def train_step(model, loss, optimizer, pb, world=1, fused=None):
     """One optimisation step on a device PackedBatch; returns the (device) loss tensor.  `fused`: the
-    in-switch reduce+Adam of dp.SwitchReduceAdam.attach (None: NCCL all_reduce, then the optimizer)."""
-    output = model(pb)
-    loss_values = loss(output, {})
-    optimizer.zero_grad()
-    loss_values.backward()
+    in-switch reduce+Adam of dp.SwitchReduceAdam.attach (None: NCCL all_reduce, then the optimizer).
+    With lirec_b200's own model and loss the forward, loss and backward run as three native calls
+    without the autograd engine (`mlp.model.train_step`, `--native_step 1`, the default); any other
+    combination takes the reference's four-call sequence (mlp/train.py:57-63)."""
+    if int(getattr(opt, "native_step", 1)) and isinstance(model, _HotPath) and isinstance(loss, _FusedLoss):
+        loss_values = native_train_step(model, loss, pb)
+    else:
+        output = model(pb)
+        loss_values = loss(output, {})
+        optimizer.zero_grad()
+        loss_values.backward()
     local = global_clips = None
     if world > 1:
         local = pb.B

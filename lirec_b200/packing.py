@@ -44,6 +44,43 @@ def _csr_inverse(col, n_unique):
     return off, order
 
 
+class _DeviceTables(dict):
+    """name -> int32 device view into the staged arena, materialised on first use: a train step reads
+    a handful of the ~20 tables by tensor and the rest only by address (`PackedBatch.table_ptr`), so
+    building every view on every `to_device` was pure host overhead."""
+
+    def __init__(self, arena, layout):
+        super().__init__()
+        self._arena, self._layout = arena, layout
+
+    def __missing__(self, k):
+        off, n, shape = self._layout[k]
+        v = self._arena[off:off + n].view(*shape)
+        dict.__setitem__(self, k, v)
+        return v
+
+    def __contains__(self, k):
+        return k in self._layout
+
+    def __iter__(self):
+        return iter(self._layout)
+
+    def __len__(self):
+        return len(self._layout)
+
+    def keys(self):
+        return self._layout.keys()
+
+    def values(self):
+        return [self[k] for k in self._layout]
+
+    def items(self):
+        return [(k, self[k]) for k in self._layout]
+
+    def get(self, k, default=None):
+        return self[k] if k in self._layout else default
+
+
 class PackedBatch:
     """Host (numpy) or device (torch) packed batch. Build with `PackedBatch.from_tables`."""
 
@@ -65,11 +102,15 @@ class PackedBatch:
     # ---- sizes -----------------------------------------------------------------------------
     @property
     def n_cand(self):
-        return int(self.tables["cand_rows"].shape[0])
+        n = self.__dict__.get("_n_cand")
+        return int(self.tables["cand_rows"].shape[0]) if n is None else n
 
     @property
     def n_ctx_rows(self):
-        return int(self.tables["ctx_rows"].shape[0]) if self.has_ctx else 0
+        if not self.has_ctx:
+            return 0
+        n = self.__dict__.get("_n_ctx_rows")
+        return int(self.tables["ctx_rows"].shape[0]) if n is None else n
 
     @property
     def n_clip(self):
@@ -81,6 +122,13 @@ class PackedBatch:
 
     def __getitem__(self, k):
         return self.tables[k]
+
+    def table_ptr(self, k):
+        """Device address of integer table `k` (device batches only) without building a tensor view."""
+        t = self.tables
+        if isinstance(t, _DeviceTables):
+            return t._arena.data_ptr() + 4 * t._layout[k][0]
+        return t[k].data_ptr()
 
     # ---- construction ----------------------------------------------------------------------
     @staticmethod
@@ -171,8 +219,10 @@ class PackedBatch:
             d.clip_bank = self.clip_bank.to(device, non_blocking=non_blocking)
             d.track_bank = self.track_bank.to(device, non_blocking=non_blocking)
         d.multilab = self.multilab.to(device, non_blocking=non_blocking)
-        for k, (off, n, shape) in self._layout.items():
-            d.tables[k] = arena[off:off + n].view(*shape)
+        d.tables = _DeviceTables(arena, self._layout)
+        d._n_cand = int(self._layout["cand_rows"][2][0])
+        if self.has_ctx:
+            d._n_ctx_rows = int(self._layout["ctx_rows"][2][0])
         d._arena_dev = arena
         d.host = self
         return d

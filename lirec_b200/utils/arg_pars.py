@@ -104,6 +104,9 @@ _FLAGS = [
     ("--dp_switch_reduce", dict(default=1, type=int, help="1: with --dp and --fused_adam, reduce gradients inside the "
                                                           "NVSwitch fused with Adam (falls back to NCCL without multicast)")),
     ("--fused_adam", dict(default=0, type=int, help="1: flat fused Adam kernel instead of torch.optim.Adam")),
+    ("--native_step", dict(default=1, type=int, help="1: forward + loss + backward of a training iteration as three "
+                                                     "native calls (no autograd engine round trip); 0: the "
+                                                     "reference's model()/loss()/backward() sequence")),
     ("--max_n_tripl", dict(default=20, type=int, help="candidate slots per clip (reference hard-codes 20)")),
     ("--synthetic", dict(default=0, type=int, help="1: independent synthetic MovieGraphs-shaped clips; 2: synthetic "
                                                    "annotation world through the index-only dataset")),

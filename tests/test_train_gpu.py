@@ -66,3 +66,84 @@ def test_torch_adam_and_fused_adam_agree(opt_preset):
     for k in finals[0]:
         tol = 1e-4 if k == "__next_logits" else 2e-6      # logits see the bf16 re-rounding of the weights
         assert float((finals[0][k] - finals[1][k]).abs().max()) < tol, k
+
+
+def test_flat_adam_state_roundtrip_and_torch_adam_interop(opt_preset):
+    """optimizer.state_dict() / load_state_dict() in torch.optim.Adam's layout (reference checkpoints,
+    mlp/train.py:84-106): a FlatAdam resumed from its own state, and one resumed from a torch.optim.Adam
+    state, continue exactly like the optimizer that kept running."""
+    import copy
+    from lirec_b200.mixed_utils import synthetic
+    from helpers import make_model
+    import lirec_b200.mlp.model as M
+    pbs = [synthetic.make_batch(8, seed=s).to_device("cuda") for s in (4, 5, 6)]
+
+    def run(model, loss, optimizer, pb, seed):
+        lv = loss(model(pb, seed=seed), {})
+        optimizer.zero_grad()
+        lv.backward()
+        optimizer.step()
+
+    finals = {}
+    for src in ("flat", "torch"):
+        opt_preset("int_rel_ch", fused_adam=1 if src == "flat" else 0, lr=1e-3)
+        model, loss, optimizer = make_model(seed=3)
+        model.train()
+        run(model, loss, optimizer, pbs[0], 60)
+        run(model, loss, optimizer, pbs[1], 61)
+        sd_m, sd_o = copy.deepcopy(model.state_dict()), copy.deepcopy(optimizer.state_dict())
+        assert len(sd_o["state"]) == 38
+        assert all(float(st["step"]) == 2.0 for st in sd_o["state"].values())
+        if src == "flat":                                   # the run that simply keeps going
+            run(model, loss, optimizer, pbs[2], 62)
+            finals["continued"] = {k: v.clone() for k, v in model.state_dict().items()}
+        # resume into a fresh model + FlatAdam
+        opt_preset("int_rel_ch", fused_adam=1, lr=1e-3)
+        model2, loss2, optimizer2 = make_model(seed=11)
+        assert isinstance(optimizer2, M.FlatAdam)
+        model2.load_state_dict(sd_m)
+        optimizer2.load_state_dict(sd_o)
+        assert optimizer2._t == 2
+        assert optimizer2.state[model2._param_list[0]]["exp_avg"].data_ptr() == optimizer2._m.data_ptr()
+        model2.train()
+        run(model2, loss2, optimizer2, pbs[2], 62)
+        finals[src] = {k: v.clone() for k, v in model2.state_dict().items()}
+        assert float(optimizer2.state_dict()["state"][0]["step"]) == 3.0
+    for k in finals["continued"]:
+        assert torch.equal(finals["continued"][k], finals["flat"][k]), k
+        # torch.optim.Adam's first two steps differ from the fused kernel's in the last bits (test above)
+        assert float((finals["continued"][k] - finals["torch"][k]).abs().max()) < 4e-6, k
+
+
+@pytest.mark.parametrize("preset", ["modalities", "int_rels", "int_ch", "int_rel_ch"])
+def test_native_train_step_equals_autograd_path(opt_preset, preset):
+    """mlp.model.train_step (forward + loss + backward as three native calls, no autograd engine) leaves the
+    same loss and bit-identical gradients as loss(model(x), x).backward() — for every model / loss pair."""
+    from lirec_b200.mixed_utils import synthetic
+    from helpers import make_model
+    import lirec_b200.mlp.model as M
+    opt_preset(preset, fused_adam=1, lr=1e-3)
+    pb = synthetic.make_batch(12, seed=9, preset=preset).to_device("cuda")
+    model, loss, optimizer = make_model(seed=5)
+    model.train()
+    lv = loss(model(pb, seed=77), {})
+    optimizer.zero_grad()
+    lv.backward()
+    ref = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model._flat_grad.fill_(float("nan"))                       # the native step must rewrite every gradient
+    lv2 = M.train_step(model, loss, pb, seed=77)
+    assert not lv2.requires_grad and torch.equal(lv.detach(), lv2)
+    for k, p in model.named_parameters():
+        assert p.grad is not None and torch.equal(p.grad, ref[k]), k
+    # and the loop helper takes the same step either way
+    import lirec_b200.mlp.train as TR
+    finals = []
+    for native in (0, 1):
+        o = opt_preset(preset, fused_adam=1, lr=1e-3, native_step=native)
+        model, loss, optimizer = make_model(seed=5)
+        model.train()
+        for s in range(2):
+            TR.train_step(model, loss, optimizer, pb)
+        finals.append({k: v.clone() for k, v in model.state_dict().items()})
+    for k in finals[0]:
+        assert torch.equal(finals[0][k], finals[1][k]), k

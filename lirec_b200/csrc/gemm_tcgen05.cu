@@ -89,6 +89,7 @@ struct DevProblem {
   DevEpi epi;
 };
 
+constexpr int EPI_STAGE_BYTES = 4096;   // per epilogue warp: a 32 x 32 chunk as bf16 hi + lo (pair kernel)
 constexpr int MAX_ORDERED_TILES = 6144;
 constexpr uint16_t NO_TILE = 0xFFFF;
 
@@ -310,12 +311,21 @@ __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* p, bool vec, f
   }
 }
 
-__device__ __forceinline__ void epilogue_chunk(const DevEpi& e, int M, int N, int m, int n0,
-                                               const uint32_t (&acc)[32], int64_t slice_off) {
-  if (m >= M || n0 >= N) return;
+// `stage`: this warp's 4 KB shared-memory staging area (or nullptr): the transposed split output goes
+// through it so that the warp stores 16-byte pieces of eight consecutive rows instead of 2-byte elements.
+__device__ __forceinline__ void epilogue_chunk(const DevEpi& e, int M, int N, int m_true, int n0,
+                                               const uint32_t (&acc)[32], int64_t slice_off,
+                                               bool first_slice, uint8_t* stage, int lane) {
+  if (n0 >= N) return;                                     // warp-uniform
+  const bool staged_t = (e.out_kind == LIREC_OUT_SPLIT_BF16_T) && stage != nullptr;
+  if (m_true >= M && !staged_t) return;
+  // a staged store is a warp-cooperative step: rows beyond M tag along on the last valid row's
+  // inputs (their values are never stored)
+  const int m = min(m_true, M - 1);
   const int nvalid = min(32, N - n0);
   const bool full = nvalid == 32;
-  const bool bias_on = e.bias != nullptr && (e.row_flag == nullptr || e.row_flag[m] != 0);
+  // split-K: the partial sums are added up afterwards, so the bias goes into slice 0 only
+  const bool bias_on = first_slice && e.bias != nullptr && (e.row_flag == nullptr || e.row_flag[m] != 0);
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = e.alpha * __uint_as_float(acc[j]);
@@ -406,6 +416,47 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpi& e, int M, int N, in
         }
       }
     }
+  } else if (staged_t) {
+    // transposed hi/lo split through shared memory: element (m, n) -> out[(col_off + n) * ld + m].
+    // The warp holds 32 consecutive m (lanes) x 32 n (registers).  It writes the chunk as [n][m] into
+    // its staging area, then every lane moves 16 bytes = eight consecutive m of one n: a store
+    // instruction covers 8 columns x 64 contiguous bytes (direct 2-byte stores: one column x 64 B).
+    __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(stage);
+    __nv_bfloat16* sl = sh + 32 * 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      __nv_bfloat16 h, l;
+      split_bf16(v[j], h, l);
+      sh[j * 32 + lane] = h;
+      sl[j * 32 + lane] = l;
+    }
+    __syncwarp();
+    const int part = lane & 3;
+    const int mrow = (m_true - lane) + part * 8;            // first of this lane's eight rows
+    const bool rows_ok = mrow + 8 <= M;
+    const int64_t lo_off = static_cast<int64_t>(e.out_lo_off) * e.out_ld_m;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int col = it * 8 + (lane >> 2);
+      if (col < nvalid && mrow < M) {
+        __nv_bfloat16* g = reinterpret_cast<__nv_bfloat16*>(e.out) +
+                           static_cast<int64_t>(e.out_col_off + n0 + col) * e.out_ld_m + mrow;
+        const __nv_bfloat16* ph = sh + col * 32 + part * 8;
+        const __nv_bfloat16* pl = sl + col * 32 + part * 8;
+        if (e.vec_ok && rows_ok) {
+          *reinterpret_cast<uint4*>(g) = *reinterpret_cast<const uint4*>(ph);
+          *reinterpret_cast<uint4*>(g + lo_off) = *reinterpret_cast<const uint4*>(pl);
+        } else {
+          for (int q = 0; q < 8; ++q) {
+            if (mrow + q < M) {
+              g[q] = ph[q];
+              g[q + lo_off] = pl[q];
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();                                           // the next chunk reuses the staging area
   } else if (e.out_kind == LIREC_OUT_SPLIT_BF16_T) {
     // transposed hi/lo split: element (m, n) -> out[(col_off + n) * ld + m].  The 32 lanes of a warp
     // hold 32 consecutive m, so every store instruction writes 64 contiguous bytes.
@@ -629,7 +680,7 @@ lirec_gemm_tcgen05_kernel(const __grid_constant__ GemmParams P) {
                                static_cast<uint32_t>(acc * BN + c * 32);
         tmem_ld_32x32(taddr, r);
         epilogue_chunk(pr.epi, pr.M, pr.N, m0 + quarter * 32 + lane, n0 + c * 32, r,
-                       static_cast<int64_t>(slice) * pr.split_stride);
+                       static_cast<int64_t>(slice) * pr.split_stride, slice == 0, nullptr, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -813,6 +864,7 @@ lirec_gemm_tcgen05_pair_kernel(const __grid_constant__ GemmParams P) {
     // ===================== epilogue warps (0..7), both CTAs =====================
     const int quarter = warp & 3;
     const int half = warp >> 2;
+    uint8_t* epi_stage = smem + STAGES * STAGE_BYTES + 256 + warp * EPI_STAGE_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int slot = cluster_id; slot < P.num_slots; slot += num_clusters) {
@@ -835,7 +887,7 @@ lirec_gemm_tcgen05_pair_kernel(const __grid_constant__ GemmParams P) {
                                static_cast<uint32_t>(acc) * ACC_COLS + static_cast<uint32_t>(c * 32);
         tmem_ld_32x32(taddr, r);
         epilogue_chunk(pr.epi, pr.M, pr.N, m0 + quarter * 32 + lane, n0 + c * 32, r,
-                       static_cast<int64_t>(slice) * pr.split_stride);
+                       static_cast<int64_t>(slice) * pr.split_stride, slice == 0, epi_stage, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -1014,7 +1066,8 @@ static int launch(const GemmParams& P, cudaStream_t stream) {
 // CTA-pair launch: one cluster of two CTAs per TPC, persistent over the pair tiles.
 template <int STAGES>
 static int launch_pair(const GemmParams& P, cudaStream_t stream) {
-  constexpr size_t smem = STAGES * (BM * BK * 2 + 128 * BK * 2) + 1024 /*align*/ + 256 /*barriers*/;
+  constexpr size_t smem = STAGES * (BM * BK * 2 + 128 * BK * 2) + 1024 /*align*/ + 256 /*barriers*/ +
+                          NUM_EPI_WARPS * EPI_STAGE_BYTES /*epilogue staging*/;
   static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   static int max_clusters = 0;
@@ -1050,20 +1103,40 @@ static int launch_pair(const GemmParams& P, cudaStream_t stream) {
   return LIREC_OK;
 }
 
-// LIREC_GEMM_PAIR=0 selects the single-CTA 128x128 kernel (kept for A/B measurements).
-static bool use_pair_kernel() {
-  static int v = -1;
-  if (v < 0) {
+// Which kernel runs a launch.  LIREC_GEMM_PAIR=1 / 0 forces the CTA-pair (256-row tiles over two SMs) or
+// the single-CTA 128x128 kernel; unset = choose per launch.  The pair kernel is the fast one per tile,
+// but at small row counts (the reference's 64-clip batches: ~530 candidate rows = 3 pair tiles per
+// column of tiles) its tiles cover under 60 % of the 74 clusters while the same launch cut into
+// 128x128 tiles still fits one wave of the 148 SMs: then the single-CTA kernel finishes sooner.
+static int pair_mode() {
+  static int v = -2;
+  if (v == -2) {
     const char* e = getenv("LIREC_GEMM_PAIR");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = (e == nullptr || e[0] == '\0') ? -1 : (e[0] == '0' ? 0 : 1);
   }
-  return v != 0;
+  return v;
+}
+static bool choose_pair_kernel(const lirec_gemm_problem* probs, int nprobs) {
+  const int mode = pair_mode();
+  if (mode >= 0) return mode != 0;
+  long pair_tiles = 0, single_tiles = 0;
+  for (int i = 0; i < nprobs; ++i) {
+    const lirec_gemm_problem& g = probs[i];
+    if (g.M <= 0 || g.N <= 0) continue;
+    int max_kb = 0;
+    for (int ps = 0; ps < g.num_passes; ++ps) max_kb = std::max(max_kb, (g.pass[ps].k_len + BK - 1) / BK);
+    const int split = std::max(1, std::min(g.split_k, max_kb));
+    const int bn = g.N > 128 ? 256 : 128;
+    pair_tiles += (long)((g.M + 2 * BM - 1) / (2 * BM)) * ((g.N + bn - 1) / bn) * split;
+    single_tiles += (long)((g.M + BM - 1) / BM) * ((g.N + 127) / 128) * split;
+  }
+  return !(pair_tiles * 10 <= 74 * 6 && single_tiles <= 148);
 }
 
 int run_grouped(const lirec_gemm_problem* probs, int nprobs, cudaStream_t stream) {
   LIREC_REQUIRE(nprobs >= 0 && nprobs <= MAX_PROBLEMS, "too many GEMM problems (%d > %d)", nprobs,
                 MAX_PROBLEMS);
-  const bool pair = use_pair_kernel();
+  const bool pair = choose_pair_kernel(probs, nprobs);
   const int tile_m = pair ? 2 * BM : BM;
   static thread_local GemmParams P;  // 16 KB: keep it off the stack
   std::vector<MapKey> keys;
@@ -1107,6 +1180,8 @@ int run_grouped(const lirec_gemm_problem* probs, int nprobs, cudaStream_t stream
     for (int ps = 0; ps < g.num_passes; ++ps) max_kb = std::max(max_kb, (g.pass[ps].k_len + BK - 1) / BK);
     int split = std::max(1, std::min(g.split_k, max_kb));
     LIREC_REQUIRE(split == 1 || g.epi.out_kind == LIREC_OUT_F32, "problem %d: split-K needs an fp32 output", idx);
+    LIREC_REQUIRE(split == 1 || (g.epi.act == LIREC_ACT_NONE && g.epi.post == LIREC_POST_NONE && !g.epi.accumulate),
+                  "problem %d: split-K partial sums cannot carry an activation, post op or accumulate", idx);
     LIREC_REQUIRE(g.epi.out_kind == LIREC_OUT_F32 || g.epi.out_kind == LIREC_OUT_SPLIT_BF16 ||
                       g.epi.out_kind == LIREC_OUT_SPLIT_BF16_T,
                   "problem %d: out_kind=%d", idx, g.epi.out_kind);
@@ -1154,8 +1229,8 @@ int run_grouped(const lirec_gemm_problem* probs, int nprobs, cudaStream_t stream
     const uintptr_t ob = reinterpret_cast<uintptr_t>(e.out);
     if (e.out_kind == LIREC_OUT_F32)
       de.vec_ok = (e.out_ld_n == 1 && (ob & 15) == 0 && (e.out_ld_m % 4) == 0) ? 1 : 0;
-    else if (e.out_kind == LIREC_OUT_SPLIT_BF16_T)
-      de.vec_ok = 0;
+    else if (e.out_kind == LIREC_OUT_SPLIT_BF16_T)   // 16-byte pieces of eight consecutive m (staged store)
+      de.vec_ok = ((ob & 15) == 0 && (e.out_ld_m % 8) == 0) ? 1 : 0;
     else
       de.vec_ok = ((ob & 15) == 0 && (e.out_ld_m % 8) == 0 && (e.out_col_off % 8) == 0 &&
                    (e.out_lo_off % 8) == 0)

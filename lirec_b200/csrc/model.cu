@@ -119,6 +119,12 @@ static int split_factor(int out_f, int in_f, int passes, int rows) {
   if (tiles >= 64 || kb < 128) return 1;
   return std::max(1, std::min(std::min(8, kb / 64), (74 + tiles - 1) / tiles));
 }
+// K-slices of the interaction head's forward GEMM ([Ni, C <= 128] output: one pair tile per 256 rows)
+static int head_split(int Ni, int width) {
+  const int tiles = (Ni + 255) / 256;
+  const int kb = (width + 63) / 64;
+  return std::max(1, std::min(std::min(8, kb / 8), 74 / std::max(1, tiles)));
+}
 static size_t split_pool_floats(const Dims& d) {
   size_t n = 0;
   auto add = [&](int out_f, int in_f, int passes, int rows) {
@@ -138,6 +144,9 @@ static size_t split_pool_floats(const Dims& d) {
       add(d.J, d.inw[s], 2, nu); add(d.J, 1, 2, nu);
     }
   }
+  // forward reuses the pool for the split interaction head (backward starts after forward has drained it)
+  const int hs = head_split(d.Ni, hw);
+  if (hs > 1) n = std::max(n, (size_t)hs * d.Ni * d.C);
   return n;
 }
 
@@ -434,9 +443,32 @@ int forward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lirec
     add_pass(g, mk_pass(a, 0, width, wo, 0, 0, width));
     g.epi.bias = P.out_ints.bias;
     out_f32(g, out_ints, d.C);
+    // One column of 256-row tiles (C <= 128) leaves most clusters idle and every busy SM pulling its
+    // 2 x width K-range at per-SM bandwidth: split K so the launch covers the machine, and add the
+    // partial [Ni, C] outputs up afterwards (bias rides in slice 0).
+    const int S = head_split(d.Ni, width);
+    ReduceJobs jobs;
+    jobs.n = 0;
+    if (S > 1 && (size_t)S * d.Ni * d.C <= w.pool_floats) {
+      const int kb = (width + 63) / 64, chunk = (kb + S - 1) / S;
+      ReduceJob& j = jobs.job[jobs.n++];
+      j.dst = out_ints; j.dst_ld = d.C; j.src = w.pool; j.M = d.Ni; j.N = d.C;
+      j.S = (kb + chunk - 1) / chunk;
+      g.split_k = S;
+      g.split_stride = (int64_t)d.Ni * d.C;
+      g.epi.out = w.pool;
+    }
     pr.push_back(g);
+    if ((rc = gemm::run_grouped(pr.data(), (int)pr.size(), stream)) != LIREC_OK) return rc;
+    if (jobs.n > 0) {
+      const int64_t total = (int64_t)d.Ni * d.C;
+      dim3 grid((unsigned)((total + 1023) / 1024), jobs.n);
+      reduce_partials_kernel<<<grid, 256, 0, stream>>>(jobs);
+      LIREC_CUDA_OK(cudaGetLastError());
+      note_launch();
+    }
   }
-  return gemm::run_grouped(pr.data(), (int)pr.size(), stream);
+  return LIREC_OK;
 }
 
 // ---------------------------------------------------------------------------

@@ -253,7 +253,8 @@ class _HotPath(nn.Module):
         cfg.slot_mask = int(self._slot_mask)
         self._params_c, self._cfg_c = P, cfg
         self._grad_views = [self._grad_view(i) for i in range(len(self._param_list))]
-        self._anchor = next((p for p in self._param_list if p.requires_grad), self._param_list[0])
+        # index, not the Parameter itself: assigning a Parameter to a module attribute would register it
+        self._anchor_idx = next((i for i, p in enumerate(self._param_list) if p.requires_grad), 0)
 
     def _batch_struct(self, pb, training, seed):
         """lirec_batch of `pb`; the pointer part is built once per (batch, branch set) and cached on the
@@ -348,9 +349,10 @@ class _HotPath(nn.Module):
         training = self.training and self.dropout.p > 0
         if seed is None:
             seed = self.next_seed() if training else 0
-        anchor = self._anchor
+        anchor = self._param_list[self._anchor_idx]
         if not anchor.requires_grad:             # parameters frozen since the structs were built
-            anchor = self._anchor = next((p for p in self._param_list if p.requires_grad), anchor)
+            self._anchor_idx = next((i for i, p in enumerate(self._param_list) if p.requires_grad), self._anchor_idx)
+            anchor = self._param_list[self._anchor_idx]
         inters, rels = _ModelFn.apply(self, pb, training, seed, anchor)
         return ModelOutput(pb, inters, rels if self._ctx else None, dense_tracks=(self.kind == "maxtracks"))
 

@@ -188,3 +188,28 @@ def test_transposed_gradient_forms():
                                                   (o_dyT, 256, 0, _ext.operand(ones[:, :rows]), 0, 0, rows)],
                                        out=db, out_ld_m=1)])
     assert _rel(db, dy.double().sum(0)) < 2e-5
+
+
+@pytest.mark.parametrize("rows,in_f,pitch", [(997, 328, 1024), (1000, 96, 1004), (61, 40, 64), (300, 256, 304)])
+def test_transposed_split_store_edges(rows, in_f, pitch):
+    """The shared-memory staged transposed hi/lo store (16-byte pieces of eight consecutive rows) at its
+    edges: a row count that is not a multiple of 8, partial column chunks, a pitch that forbids vector
+    stores — bit-identical values to the split of the fp32 product and nothing written outside."""
+    from lirec_b200 import _ext, ops
+    out_f = 128
+    torch.manual_seed(rows)
+    dy = torch.randn(rows, out_f, device="cuda")
+    kp = (rows + 63) // 64 * 64
+    dyT = torch.zeros(out_f, kp, device="cuda", dtype=torch.bfloat16)
+    dyT[:, :rows] = dy.to(torch.bfloat16).t()
+    w = _rnd(out_f, in_f)
+    wT = w.t().contiguous()
+    in_p = (in_f + 7) // 8 * 8 + 8
+    dxT = torch.full((2 * in_p, pitch), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_grouped([ops.gemm_problem(rows, in_f, [(_ext.operand(dyT[:, :rows]), 0, 0, _ext.operand(wT), 0, 0, out_f)],
+                                       a_mn_major=True, out=dxT, out_kind=ops.OUT_SPLIT_T, out_ld_m=pitch,
+                                       out_lo_off=in_p)])
+    ref = dy.to(torch.bfloat16).double() @ w.double()                     # [rows, in_f]
+    got = (dxT[:in_f, :rows].double() + dxT[in_p:in_p + in_f, :rows].double()).t()
+    assert _rel(got, ref) < 2e-5
+    assert (dxT[:, rows:] == 7).all() and (dxT[in_f:in_p] == 7).all() and (dxT[in_p + in_f:] == 7).all()

@@ -94,9 +94,8 @@ def test_flat_adam_state_roundtrip_and_torch_adam_interop(opt_preset):
         sd_m, sd_o = copy.deepcopy(model.state_dict()), copy.deepcopy(optimizer.state_dict())
         assert len(sd_o["state"]) == 38
         assert all(float(st["step"]) == 2.0 for st in sd_o["state"].values())
-        if src == "flat":                                   # the run that simply keeps going
-            run(model, loss, optimizer, pbs[2], 62)
-            finals["continued"] = {k: v.clone() for k, v in model.state_dict().items()}
+        run(model, loss, optimizer, pbs[2], 62)             # the run that simply keeps going
+        finals[src + "_continued"] = {k: v.clone() for k, v in model.state_dict().items()}
         # resume into a fresh model + FlatAdam
         opt_preset("int_rel_ch", fused_adam=1, lr=1e-3)
         model2, loss2, optimizer2 = make_model(seed=11)
@@ -109,10 +108,15 @@ def test_flat_adam_state_roundtrip_and_torch_adam_interop(opt_preset):
         run(model2, loss2, optimizer2, pbs[2], 62)
         finals[src] = {k: v.clone() for k, v in model2.state_dict().items()}
         assert float(optimizer2.state_dict()["state"][0]["step"]) == 3.0
-    for k in finals["continued"]:
-        assert torch.equal(finals["continued"][k], finals["flat"][k]), k
-        # torch.optim.Adam's first two steps differ from the fused kernel's in the last bits (test above)
-        assert float((finals["continued"][k] - finals["torch"][k]).abs().max()) < 4e-6, k
+    for k in finals["flat_continued"]:
+        d_flat = float((finals["flat_continued"][k] - finals["flat"][k]).abs().max())
+        d_torch = float((finals["torch_continued"][k] - finals["torch"][k]).abs().max())
+        assert d_flat == 0.0, (k, d_flat)
+        # third step from torch.optim.Adam's state, taken by FlatAdam vs by torch.optim.Adam itself: the two
+        # implementations agree to ~2e-6 per step (test above); a lost moment or step count would show as
+        # ~lr = 1e-3.  (Whole trajectories are not comparable: Adam normalises, so a last-bit difference
+        # in a near-zero gradient moves that element by a full lr.)
+        assert d_torch < 4e-6, (k, d_torch)
 
 
 @pytest.mark.parametrize("preset", ["modalities", "int_rels", "int_ch", "int_rel_ch"])

@@ -49,7 +49,17 @@ class TimedLib(object):
 phase = collections.defaultdict(float)
 
 
+import lirec_b200.mlp.train as TR
+NATIVE = os.environ.get("PROBE_NATIVE", "0") == "1"
+
+
 def step(pb, timed):
+    if NATIVE:
+        t0 = time.perf_counter()
+        TR.train_step(model, loss_fn, optimizer, pb)
+        if timed:
+            phase["native train_step"] += time.perf_counter() - t0
+        return
     t0 = time.perf_counter()
     out = model(pb)
     t1 = time.perf_counter()

@@ -234,11 +234,16 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceJobs j
     const int m = (int)(i / j.N), n = (int)(i - (int64_t)m * j.N);
     *reinterpret_cast<float4*>(j.dst + (int64_t)m * j.dst_ld + n) = acc;
   } else {
+    const bool contiguous = j.dst_ld == j.N;     // no (m, n) decomposition: 64-bit divisions dominate otherwise
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
       float acc = 0.f;
       for (int s = 0; s < j.S; ++s) acc += j.src[(int64_t)s * total + i];
-      const int m = (int)(i / j.N), n = (int)(i - (int64_t)m * j.N);
-      j.dst[(int64_t)m * j.dst_ld + n] = acc;
+      if (contiguous) {
+        j.dst[i] = acc;
+      } else {
+        const int m = (int)(i / j.N), n = (int)(i - (int64_t)m * j.N);
+        j.dst[(int64_t)m * j.dst_ld + n] = acc;
+      }
     }
   }
 }

@@ -85,6 +85,7 @@ struct DevProblem {
   int64_t split_stride;        // elements between the partial outputs of consecutive slices
   int32_t num_passes;
   int32_t a_mn_major, b_mn_major;
+  int32_t kb_major;            // 1: all passes cover the same k-blocks and are interleaved per k-block
   DevPass pass[MAX_PASSES];
   DevEpi epi;
 };
@@ -572,34 +573,41 @@ lirec_gemm_tcgen05_kernel(const __grid_constant__ GemmParams P) {
         const int slice = local / pr.tiles_mn, rem = local - slice * pr.tiles_mn;
         const int m0 = (rem / pr.tiles_n) * BM;
         const int n0 = (rem % pr.tiles_n) * BN;
-        for (int ps = 0; ps < pr.num_passes; ++ps) {
+        auto issue = [&](int ps, int kb) {
           const DevPass& pa = pr.pass[ps];
           const CUtensorMap* amap = &P.maps[pa.a_map];
           const CUtensorMap* bmap = &P.maps[pa.b_map];
-          const int kb_end = min(pa.k_blocks, (slice + 1) * pr.split_chunk);
-          for (int kb = slice * pr.split_chunk; kb < kb_end; ++kb) {
-            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-            const uint32_t fb = smem_u32(&full_bar[stage]);
-            mbar_expect_tx(fb, STAGE_BYTES);
-            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-            const uint32_t sb = sa + A_BYTES;
-            if (!pr.a_mn_major) {
-              tma_load_2d(sa, amap, fb, pa.a_k_off + kb * BK, pa.a_mn_off + m0);
-            } else {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          if (!pr.a_mn_major) {
+            tma_load_2d(sa, amap, fb, pa.a_k_off + kb * BK, pa.a_mn_off + m0);
+          } else {
 #pragma unroll
-              for (int h = 0; h < BM / 64; ++h)
-                tma_load_2d(sa + h * (BK * 128), amap, fb, pa.a_mn_off + m0 + h * 64,
-                            pa.a_k_off + kb * BK);
-            }
-            if (!pr.b_mn_major) {
-              tma_load_2d(sb, bmap, fb, pa.b_k_off + kb * BK, pa.b_mn_off + n0);
-            } else {
+            for (int h = 0; h < BM / 64; ++h)
+              tma_load_2d(sa + h * (BK * 128), amap, fb, pa.a_mn_off + m0 + h * 64,
+                          pa.a_k_off + kb * BK);
+          }
+          if (!pr.b_mn_major) {
+            tma_load_2d(sb, bmap, fb, pa.b_k_off + kb * BK, pa.b_mn_off + n0);
+          } else {
 #pragma unroll
-              for (int h = 0; h < BN / 64; ++h)
-                tma_load_2d(sb + h * (BK * 128), bmap, fb, pa.b_mn_off + n0 + h * 64,
-                            pa.b_k_off + kb * BK);
-            }
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            for (int h = 0; h < BN / 64; ++h)
+              tma_load_2d(sb + h * (BK * 128), bmap, fb, pa.b_mn_off + n0 + h * 64,
+                          pa.b_k_off + kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        };
+        if (pr.kb_major) {   // passes share their k range: visit them k-block by k-block (operand reuse in L2)
+          const int kb_end = min(pr.pass[0].k_blocks, (slice + 1) * pr.split_chunk);
+          for (int kb = slice * pr.split_chunk; kb < kb_end; ++kb)
+            for (int ps = 0; ps < pr.num_passes; ++ps) issue(ps, kb);
+        } else {
+          for (int ps = 0; ps < pr.num_passes; ++ps) {
+            const int kb_end = min(pr.pass[ps].k_blocks, (slice + 1) * pr.split_chunk);
+            for (int kb = slice * pr.split_chunk; kb < kb_end; ++kb) issue(ps, kb);
           }
         }
       }
@@ -778,34 +786,41 @@ lirec_gemm_tcgen05_pair_kernel(const __grid_constant__ GemmParams P) {
         const int m0 = (rem / pr.tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
         const int n0 = (rem % pr.tiles_n) * pr.bn + static_cast<int>(rank) * bhalf;
         const uint32_t cta_bytes = A_BYTES + static_cast<uint32_t>(bhalf) * (BK * 2);
-        for (int ps = 0; ps < pr.num_passes; ++ps) {
+        auto issue = [&](int ps, int kb) {
           const DevPass& pa = pr.pass[ps];
           const CUtensorMap* amap = &P.maps[pa.a_map];
           const CUtensorMap* bmap = &P.maps[pa.b_map];
-          const int kb_end = min(pa.k_blocks, (slice + 1) * pr.split_chunk);
-          for (int kb = slice * pr.split_chunk; kb < kb_end; ++kb) {
-            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-            const uint32_t fb_local = smem_u32(&full_bar[stage]);
-            if (rank == 0) mbar_expect_tx(fb_local, 2 * cta_bytes);   // both CTAs' bytes land here
-            const uint32_t fb = mapa_rank(fb_local, 0);
-            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-            const uint32_t sb = sa + A_BYTES;
-            if (!pr.a_mn_major) {
-              tma_load_2d_pair(sa, amap, fb, pa.a_k_off + kb * BK, pa.a_mn_off + m0);
-            } else {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb_local = smem_u32(&full_bar[stage]);
+          if (rank == 0) mbar_expect_tx(fb_local, 2 * cta_bytes);   // both CTAs' bytes land here
+          const uint32_t fb = mapa_rank(fb_local, 0);
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          if (!pr.a_mn_major) {
+            tma_load_2d_pair(sa, amap, fb, pa.a_k_off + kb * BK, pa.a_mn_off + m0);
+          } else {
 #pragma unroll
-              for (int h = 0; h < BM / 64; ++h)
-                tma_load_2d_pair(sa + h * (BK * 128), amap, fb, pa.a_mn_off + m0 + h * 64,
-                                 pa.a_k_off + kb * BK);
-            }
-            if (!pr.b_mn_major) {
-              tma_load_2d_pair(sb, bmap, fb, pa.b_k_off + kb * BK, pa.b_mn_off + n0);
-            } else {
-              for (int h = 0; h < bhalf / 64; ++h)
-                tma_load_2d_pair(sb + h * (BK * 128), bmap, fb, pa.b_mn_off + n0 + h * 64,
-                                 pa.b_k_off + kb * BK);
-            }
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            for (int h = 0; h < BM / 64; ++h)
+              tma_load_2d_pair(sa + h * (BK * 128), amap, fb, pa.a_mn_off + m0 + h * 64,
+                               pa.a_k_off + kb * BK);
+          }
+          if (!pr.b_mn_major) {
+            tma_load_2d_pair(sb, bmap, fb, pa.b_k_off + kb * BK, pa.b_mn_off + n0);
+          } else {
+            for (int h = 0; h < bhalf / 64; ++h)
+              tma_load_2d_pair(sb + h * (BK * 128), bmap, fb, pa.b_mn_off + n0 + h * 64,
+                               pa.b_k_off + kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        };
+        if (pr.kb_major) {   // passes share their k range: visit them k-block by k-block (operand reuse in L2)
+          const int kb_end = min(pr.pass[0].k_blocks, (slice + 1) * pr.split_chunk);
+          for (int kb = slice * pr.split_chunk; kb < kb_end; ++kb)
+            for (int ps = 0; ps < pr.num_passes; ++ps) issue(ps, kb);
+        } else {
+          for (int ps = 0; ps < pr.num_passes; ++ps) {
+            const int kb_end = min(pr.pass[ps].k_blocks, (slice + 1) * pr.split_chunk);
+            for (int kb = slice * pr.split_chunk; kb < kb_end; ++kb) issue(ps, kb);
           }
         }
       }
@@ -1116,6 +1131,14 @@ static int pair_mode() {
   }
   return v;
 }
+static bool kb_major_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LIREC_GEMM_KB_MAJOR");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
 static bool choose_pair_kernel(const lirec_gemm_problem* probs, int nprobs) {
   const int mode = pair_mode();
   if (mode >= 0) return mode != 0;
@@ -1199,6 +1222,17 @@ int run_grouped(const lirec_gemm_problem* probs, int nprobs, cudaStream_t stream
       if (ia < 0 || ib < 0) return fail(LIREC_ERR_LIMIT, "more than %d tensor maps in one launch", MAX_MAPS);
       d.pass[ps] = DevPass{(int16_t)ia, (int16_t)ib, s.a_mn_off, s.a_k_off, s.b_mn_off, s.b_k_off,
                            (s.k_len + BK - 1) / BK};
+    }
+    // Optional (LIREC_GEMM_KB_MAJOR=1): passes over the same k range (hi/lo splits of one operand pair)
+    // interleaved k-block by k-block, so the operand tile two passes share (x_hi in x_hi*dy_hi and
+    // x_hi*dy_lo) is re-read while it is still in L2.  Measured on B200 it LOSES to the pass-major
+    // default: gate backward 0.67 -> 0.70 ms, first-layer wgrad 0.311 -> 0.329 ms, heads backward
+    // unchanged (the long sequential K sweep per operand is what the TMA/HBM path likes), so it is off.
+    d.kb_major = 0;
+    if (g.num_passes > 1 && kb_major_enabled()) {
+      d.kb_major = 1;
+      for (int ps = 1; ps < g.num_passes; ++ps)
+        if (d.pass[ps].k_blocks != d.pass[0].k_blocks) d.kb_major = 0;
     }
     const lirec_epilogue& e = g.epi;
     LIREC_REQUIRE(e.out != nullptr, "problem %d: null output", idx);

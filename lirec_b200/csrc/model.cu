@@ -520,6 +520,23 @@ static void add_dgrad_passes(lirec_gemm_problem& g, const TGrad& dy, int rows, c
   add_pass(g, mk_pass(a, 0, dy.hi, b, w_row_off, 0, k_len));
   add_pass(g, mk_pass(a, 0, dy.lo, b, w_row_off, 0, k_len));
 }
+// The same passes against the weight IN PLACE: B = W [out_f, in_total] read MN-major (columns
+// [in_off, in_off + N) of W are the problem's N).  Slower per tile than the K-major W^T copy, but it needs
+// no per-step transposes (28 us for the 11 M second-layer / gate / head weights): what small batches
+// want.  Rows of dY^T beyond out_f are zero (split_f32_t pads) and rows of W beyond out_f are TMA zero fill.
+static void add_dgrad_passes_inplace(lirec_gemm_problem& g, const TGrad& dy, int rows, const void* w_bf16, int out_f,
+                                     int in_total, int in_off) {
+  const lirec_operand a = op(dy.ptr, dy.buf_rows, rows, dy.pitch);
+  const lirec_operand b = op(w_bf16, out_f, in_total, in_total);
+  g.b_mn_major = 1;
+  add_pass(g, mk_pass(a, 0, dy.hi, b, in_off, 0, out_f));
+  add_pass(g, mk_pass(a, 0, dy.lo, b, in_off, 0, out_f));
+}
+// Below this many candidate rows backward multiplies by the weights in place instead of transposing them.
+static bool dgrad_in_place(int Ni) {
+  const char* e = getenv("LIREC_DGRAD_INPLACE_ROWS");   // read per call: the tests switch it
+  return Ni < (e ? atoi(e) : 1536);
+}
 static void out_split_t(lirec_gemm_problem& g, bf16* out, int64_t pitch, int row_off, int lo_off) {
   g.epi.out_kind = LIREC_OUT_SPLIT_BF16_T;
   g.epi.out = out; g.epi.out_ld_m = pitch; g.epi.out_col_off = row_off; g.epi.out_lo_off = lo_off;
@@ -569,7 +586,8 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
   const bf16* hx = d.gates ? w.g2 : w.f2[0];
 
   // ---- [in, out] copies of the weights the data gradients multiply by ---------------------------
-  {
+  const bool inplace = dgrad_in_place(Ni);
+  if (!inplace) {
     rows::TransposeJobs tj;
     tj.n = 0;
     auto add = [&](const void* src, int out_f, int in_f, bf16* dst, int out_p) {
@@ -607,7 +625,8 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
   }
   {
     lirec_gemm_problem g = mk_problem(Ni, hw, true, false);
-    add_dgrad_passes(g, dli, Ni, w.out_intsT, hw, CP, 0, CP);
+    if (inplace) add_dgrad_passes_inplace(g, dli, Ni, P.out_ints.w_bf16, d.C, hw, 0);
+    else add_dgrad_passes(g, dli, Ni, w.out_intsT, hw, CP, 0, CP);
     if (d.gates) {
       g.epi.post = LIREC_POST_DRELU;  // through dropout(relu(.)) of the gate: model.py:353
       g.epi.post_scale = keep_scale;
@@ -623,7 +642,8 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
   }
   if (d.ctx && !d.gates) {
     lirec_gemm_problem g = mk_problem(Ni, F, true, false);
-    add_dgrad_passes(g, dlr, Ni, w.out_ctxT, F, RP, 0, RP);
+    if (inplace) add_dgrad_passes_inplace(g, dlr, Ni, P.out_ctx.w_bf16, d.R, F, 0);
+    else add_dgrad_passes(g, dlr, Ni, w.out_ctxT, F, RP, 0, RP);
     g.epi.post = LIREC_POST_DTANH;
     g.epi.drop = mk_drop(p, B.seed, DS_CAT_CTX, 0);
     g.epi.aux = w.f2[1]; g.epi.aux_ld = 2 * F; g.epi.aux_col_off = 0; g.epi.aux_lo_off = F;
@@ -642,9 +662,12 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
     for (int h = 0; h < 2; ++h) {
       const int br = h ? 0 : 1;
       lirec_gemm_problem g = mk_problem(Ni, F, true, false);
-      add_dgrad_passes(g, dpg, Ni, w.gateT, 2 * F, Gd, h * F, Gd);
-      if (br == 1)  // the context feature also feeds the relationship head
-        add_dgrad_passes(g, dlr, Ni, w.out_ctxT, F, RP, 0, RP);
+      if (inplace) add_dgrad_passes_inplace(g, dpg, Ni, P.gate.w_bf16, Gd, 2 * F, h * F);
+      else add_dgrad_passes(g, dpg, Ni, w.gateT, 2 * F, Gd, h * F, Gd);
+      if (br == 1) {  // the context feature also feeds the relationship head
+        if (inplace) add_dgrad_passes_inplace(g, dlr, Ni, P.out_ctx.w_bf16, d.R, F, 0);
+        else add_dgrad_passes(g, dlr, Ni, w.out_ctxT, F, RP, 0, RP);
+      }
       g.epi.post = LIREC_POST_DTANH;
       g.epi.drop = mk_drop(p, B.seed, br ? DS_CAT_CTX : DS_CAT_INTS, 0);
       g.epi.aux = w.f2[br]; g.epi.aux_ld = 2 * F; g.epi.aux_col_off = 0; g.epi.aux_lo_off = F;
@@ -666,7 +689,8 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
       push_reduction(pr, bgrad_t(d.outw[s], dz, br ? w.flagT : w.onesT, Ni, enc.l2[s].grad_b), d.outw[s], 1, Ni,
                      false, sc);
       lirec_gemm_problem g = mk_problem(Ni, J, true, false);
-      add_dgrad_passes(g, dz, Ni, w.l2T[br][s], J, d.outw[s], 0, d.outw[s]);
+      if (inplace) add_dgrad_passes_inplace(g, dz, Ni, enc.l2[s].w_bf16, d.outw[s], J, 0);
+      else add_dgrad_passes(g, dz, Ni, w.l2T[br][s], J, d.outw[s], 0, d.outw[s]);
       g.epi.alpha = keep_scale;
       out_f32(g, w.da2[br] + s * J, 4 * J);
       pr.push_back(g);

@@ -353,7 +353,10 @@ class _HotPath(nn.Module):
         if not anchor.requires_grad:             # parameters frozen since the structs were built
             self._anchor_idx = next((i for i, p in enumerate(self._param_list) if p.requires_grad), self._anchor_idx)
             anchor = self._param_list[self._anchor_idx]
-        inters, rels = _ModelFn.apply(self, pb, training, seed, anchor)
+        if torch.is_grad_enabled() and anchor.requires_grad:
+            inters, rels = _ModelFn.apply(self, pb, training, seed, anchor)
+        else:                                    # inference (mlp/test.py runs under no_grad): no autograd node
+            _, _, inters, rels = self._run_forward(pb, training, seed)
         return ModelOutput(pb, inters, rels if self._ctx else None, dense_tracks=(self.kind == "maxtracks"))
 
 

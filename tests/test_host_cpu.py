@@ -102,3 +102,24 @@ def test_shard_range_partitions():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_device_tables_are_lazy_views_of_the_arena():
+    """PackedBatch.to_device exposes the integer tables as views built on first use; the dict protocol the
+    rest of the code relies on (in / iter / len / keys / values / items / get) still sees every table."""
+    import torch
+    from lirec_b200.packing import PackedBatch, _DeviceTables
+    arena = torch.arange(40, dtype=torch.int32)
+    layout = {"cand_off": (0, 5, (5,)), "cand_rows": (5, 12, (4, 3)), "labels": (17, 4, (4,))}
+    t = _DeviceTables(arena, layout)
+    assert dict.__len__(t) == 0 and len(t) == 3 and "cand_rows" in t and "ctx_rows" not in t
+    assert list(t) == list(layout) and list(t.keys()) == list(layout)
+    assert t["cand_rows"].shape == (4, 3) and t["cand_rows"][1].tolist() == [8, 9, 10]
+    assert t["cand_rows"] is t["cand_rows"] and dict.__len__(t) == 1          # materialised once
+    assert t.get("labels").tolist() == [17, 18, 19, 20] and t.get("nope") is None
+    assert [v.numel() for v in t.values()] == [5, 12, 4] and [k for k, _ in t.items()] == list(layout)
+    with pytest.raises(KeyError):
+        t["nope"]
+    pb = PackedBatch()
+    pb.tables = t
+    assert pb.table_ptr("labels") == arena.data_ptr() + 4 * 17 == pb["labels"].data_ptr()

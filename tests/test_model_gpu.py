@@ -251,3 +251,20 @@ def test_edge_case_batches(case, opt_preset):
     if case == "no_relationships":
         assert pb.n_ctx_rows == pb.n_cand
     _check_all(model, loss_fn, out, lv, sd, ragged, l, extra)
+
+
+@pytest.mark.parametrize("preset", ["int_ch", "int_rel_ch", "int_rels"])
+def test_backward_with_transposed_weight_copies(preset, opt_preset, monkeypatch):
+    """Backward multiplies by the weights in place below 1536 candidate rows (every other test here) and by
+    per-step K-major W^T copies above (the bench sizes).  Force the W^T form on a small batch: same parity
+    against the oracle, and gradients equal to the in-place form within summation order."""
+    opt = opt_preset(preset)
+    monkeypatch.setenv("LIREC_DGRAD_INPLACE_ROWS", "0")
+    model, loss_fn, out, lv, sd, ragged, l, extra, tape = _run(preset, opt, 6, 21, True)
+    worst = max(rel_err(p.grad, sd[k].grad) for k, p in model.named_parameters())
+    assert worst < TOL
+    g_t = {k: p.grad.clone() for k, p in model.named_parameters()}
+    monkeypatch.setenv("LIREC_DGRAD_INPLACE_ROWS", "1000000")
+    model2, loss_fn2, out2, lv2, sd2, *_ = _run(preset, opt, 6, 21, True)
+    for k, p in model2.named_parameters():
+        assert rel_err(p.grad, g_t[k]) < 1e-5, k

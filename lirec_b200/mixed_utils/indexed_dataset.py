@@ -207,7 +207,8 @@ class IndexedMixedFeaturesDataset(Dataset):
         if L <= n:
             return rows, (None if classes is None else classes[key])
         if self.mode == "train":
-            sel = np.random.choice(np.arange(L), n, replace=False)
+            # = np.random.choice(np.arange(L), n, replace=False) (reference :387), same global RNG stream
+            sel = np.random.permutation(L)[:n]
         else:
             sel = eval_idxs[key]
         return rows[sel], (None if classes is None else classes[key][sel])
@@ -325,6 +326,10 @@ class IndexedMixedFeaturesDataset(Dataset):
         rec["cand_rows"] = np.asarray(cand, dtype=np.int32).reshape(-1, 3)
         if opt.rels_multitask and opt.rels_multi_clip:
             rec["ctx_rows"] = ctx
+            # the same blocks back to back + their lengths: what collate needs (one concatenate per item
+            # here instead of thousands of small array ops per batch there)
+            rec["ctx_counts"] = np.fromiter((len(x) for x in ctx), dtype=np.int64, count=len(ctx))
+            rec["ctx_cat"] = np.concatenate(ctx).astype(np.int64, copy=False) if ctx else np.zeros((0, 3), np.int64)
             rec["ctx_tiled"] = tiled
             rec["ctx_labels"] = ctx_lab
         if opt.rels_multitask and self.triplets:
@@ -441,31 +446,44 @@ def collate_indexed(records, dataset, resident=False):
         cand_t[:, c] = np.where(cand[:, c] == 0, ZERO, cand[:, c])
     ctx_t = ctx_off = None
     if has_ctx:
-        per = [np.asarray(x, dtype=np.int64).reshape(-1, 3) for r in records for x in r["ctx_rows"]]
-        ctx_counts = np.array([len(x) for x in per])
+        if "ctx_cat" in records[0]:
+            ctx_counts = np.concatenate([r["ctx_counts"] for r in records])
+            ctx_t = np.concatenate([r["ctx_cat"] for r in records]).astype(np.int64)     # fresh copy, edited below
+        else:                                                   # records built by hand (tests, tools)
+            per = [np.asarray(x, dtype=np.int64).reshape(-1, 3) for r in records for x in r["ctx_rows"]]
+            ctx_counts = np.array([len(x) for x in per])
+            ctx_t = np.concatenate(per) if len(per) else np.zeros((0, 3), dtype=np.int64)
         ctx_off = np.concatenate(([0], np.cumsum(ctx_counts)))
-        ctx_t = np.concatenate(per) if len(per) else np.zeros((0, 3), dtype=np.int64)
         owner_clip = np.repeat(cand_clip_of, ctx_counts)
         ctx_t[:, 0] = np.where(ctx_t[:, 0] == zc, -1 - owner_clip, ctx_t[:, 0])
         for c in (1, 2):
             ctx_t[:, c] = np.where(ctx_t[:, c] == 0, -1 - owner_clip, ctx_t[:, c])
 
-    def remap(cols_ints, cols_ctx):
-        u_ints = np.unique(cols_ints)
-        extra = np.setdiff1d(np.unique(cols_ctx), u_ints) if cols_ctx is not None else np.zeros(0, dtype=np.int64)
-        order = np.concatenate((u_ints, extra))
-        sorter = np.argsort(order, kind="stable")
-        return order, len(u_ints), (order[sorter], sorter)
+    # Bank rows are small non-negative integers and the private zero rows are -1 - clip in [-B, -1]: the
+    # unique / set-difference / lookup steps are marks and gathers over a table of n_rows + B entries
+    # (same order as np.unique + np.setdiff1d: ints rows ascending, then the context-only rows ascending).
+    def remap(cols_ints, cols_ctx, n_rows):
+        size = n_rows + B
+        seen = np.zeros(size, dtype=bool)
+        seen[cols_ints + B] = True
+        u_ints = np.flatnonzero(seen)
+        if cols_ctx is not None:
+            seen_ctx = np.zeros(size, dtype=bool)
+            seen_ctx[cols_ctx + B] = True
+            seen_ctx[u_ints] = False
+            order = np.concatenate((u_ints, np.flatnonzero(seen_ctx)))
+        else:
+            order = u_ints
+        lut = np.empty(size, dtype=np.int64)
+        lut[order] = np.arange(len(order))
+        return order - B, len(u_ints), lut
 
-    c_order, n_clip_ints, c_lut = remap(cand_t[:, 0], ctx_t[:, 0] if has_ctx else None)
-    t_order, n_track_ints, t_lut = remap(cand_t[:, 1:].reshape(-1), ctx_t[:, 1:].reshape(-1) if has_ctx else None)
-
-    def look(lut, col):
-        keys, sorter = lut
-        return sorter[np.searchsorted(keys, col)]
+    c_order, n_clip_ints, c_lut = remap(cand_t[:, 0], ctx_t[:, 0] if has_ctx else None, len(dataset.clip_bank))
+    t_order, n_track_ints, t_lut = remap(cand_t[:, 1:].reshape(-1), ctx_t[:, 1:].reshape(-1) if has_ctx else None,
+                                         len(dataset.track_bank))
 
     def apply(tbl):
-        return np.stack((look(c_lut, tbl[:, 0]), look(t_lut, tbl[:, 1]), look(t_lut, tbl[:, 2])), axis=1)
+        return np.stack((c_lut[tbl[:, 0] + B], t_lut[tbl[:, 1] + B], t_lut[tbl[:, 2] + B]), axis=1)
 
     clip_src = np.where(c_order < 0, zc, c_order)
     track_src = np.where(t_order < 0, 0, t_order)               # private zero rows read the zero row

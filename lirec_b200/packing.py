@@ -37,7 +37,9 @@ _INT_TABLES = ["cand_off", "cand_rows", "ctx_off", "ctx_rows", "ctx_owner", "lab
 def _csr_inverse(col, n_unique):
     """CSR (off [n_unique+1], idx) listing, for every unique id, the positions where it occurs."""
     col = np.asarray(col, dtype=np.int64)
-    order = np.argsort(col, kind="stable").astype(np.int32)
+    # numpy's stable sort is a radix sort for 16-bit keys (5x faster than the merge sort of wider ints)
+    key = col.astype(np.uint16) if 0 < n_unique <= 65536 and col.size and col.min() >= 0 else col
+    order = np.argsort(key, kind="stable").astype(np.int32)
     counts = np.bincount(col, minlength=n_unique)
     off = np.zeros(n_unique + 1, dtype=np.int32)
     np.cumsum(counts, out=off[1:])

@@ -50,8 +50,11 @@ class Relationship:
         self._scene2rel[scene_idx].append(self.rels_name)
 
     def scene2rel(self, scene_idx):
-        if scene_idx in self._scene2rel:
-            return np.random.choice(self._scene2rel[scene_idx])
+        names = self._scene2rel.get(scene_idx)
+        if names:
+            # np.random.choice(names) (reference :71-73) = names[randint(0, len)] on the same global RNG
+            # stream (checked draw for draw), without building a string array per call
+            return names[np.random.randint(0, len(names))]
         return "None"
 
 

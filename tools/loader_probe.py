@@ -1,0 +1,24 @@
+import sys, time; sys.argv=['x']
+sys.path.insert(0,'/root/repo')
+import numpy as np, torch
+from lirec_b200.utils.arg_pars import opt
+for k, v in dict(tr_maximize=True, tracks=True, ints=1, ctx=1, gates=1, rels_multitask=True, rels_multi_clip=True,
+                 rels_n_clips=18, mod_check=False, synthetic=2, world_movies=6, world_scenes=40).items():
+    setattr(opt, k, v)
+from lirec_b200.mixed_utils import classification_dataloader as cd, indexed_dataset as ix
+ds = cd.MixedFeaturesDataset("train")
+ds = ds.cache().init_relships() if hasattr(ds, "cache") else ds
+print(type(ds).__name__, len(ds))
+for B in (64, 256):
+    idx = list(range(min(B, len(ds))))
+    t0 = time.perf_counter(); recs = [ds[i] for i in idx]; t1 = time.perf_counter()
+    for resident in (False, True):
+        t2 = time.perf_counter()
+        for _ in range(3): pb = ix.collate_indexed(recs, ds, resident=resident)
+        t3 = time.perf_counter()
+        print("B=%d getitem %.2f ms/clip  collate(resident=%s) %.1f ms/batch -> %.0f clips/s/core (getitem+collate)" % (
+            len(idx), 1e3*(t1-t0)/len(idx), resident, 1e3*(t3-t2)/3, len(idx)/((t1-t0)+(t3-t2)/3)))
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable()
+recs = [ds[i] for i in range(min(256, len(ds)))]; pb = ix.collate_indexed(recs, ds, resident=True)
+pr.disable(); pstats.Stats(pr).sort_stats("cumulative").print_stats(18)

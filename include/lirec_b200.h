@@ -128,12 +128,15 @@ typedef struct lirec_gemm_problem {
   lirec_epilogue epi;
   /* split-K: when split_k > 1 the reduction range of every pass is cut into split_k slices of whole
    * 64-element k-blocks; slice s runs as its own tiles and writes its partial result to
-   * out + s * split_stride (elements).  The caller sums the slices (fixed order = deterministic). */
+   * out + s * split_stride (elements).  The caller sums the slices (fixed order = deterministic).
+   * Needs an F32 output without activation, post op or accumulate; a bias is added in slice 0 only. */
   int32_t split_k;
   int64_t split_stride;
 } lirec_gemm_problem;
 
-/* One persistent launch over all tiles of all problems (host array). */
+/* One persistent launch over all tiles of all problems (host array).  Kernel choice per launch: the
+ * CTA-pair kernel (256-row tiles, tcgen05 cta_group::2) unless the launch is too small to fill 60 % of
+ * the clusters and fits one wave of 128x128 tiles (single-CTA kernel); LIREC_GEMM_PAIR=1/0 forces one. */
 int lirec_gemm_grouped(const lirec_gemm_problem* problems_host, int num_problems,
                        void* stream);
 /* Per-launch timing of the GEMM kernel (CUDA events on the launching stream), for bench.py's

@@ -142,10 +142,13 @@ class _HotPath(nn.Module):
         """(Re)build the flat fp32 / grad / bf16 buffers and point every parameter into them."""
         pl = self._param_list
         if pl is not None and not self._dirty and self._flat is not None:
-            # fast path (every step): nn.Module._apply (.to / .cuda / .float) marks the model dirty;
-            # the two end-point checks catch a parameter re-pointed by hand
-            if pl[0].data_ptr() == self._flat.data_ptr() and \
-                    pl[-1].data_ptr() == self._flat.data_ptr() + 4 * self._offsets[-1]:
+            # fast path (every step, ~6 us): nn.Module._apply (.to / .cuda / .float) marks the model dirty;
+            # the pointer walk over the cached list catches a parameter re-pointed by hand (p.data = ...)
+            base = self._flat.data_ptr()
+            for p, off in zip(pl, self._offsets):
+                if p.data_ptr() != base + 4 * off:
+                    break
+            else:
                 return
         params = [p for p in self.parameters()]
         dev = params[0].device
@@ -260,7 +263,8 @@ class _HotPath(nn.Module):
         """lirec_batch of `pb`; the pointer part is built once per (batch, branch set) and cached on the
         batch — per step only the dropout seed and the training flag change."""
         cache = pb.__dict__.setdefault("_c_batch", {})
-        b = cache.get(self._ctx)
+        key = (self._ctx, pb.clip_bank.data_ptr(), pb.track_bank.data_ptr())   # banks may be swapped (resident staging)
+        b = cache.get(key)
         if b is None:
             b = _ext.Batch()
             b.clip_bank, b.clip_ld = pb.clip_bank.data_ptr(), pb.clip_bank.stride(0)
@@ -282,7 +286,7 @@ class _HotPath(nn.Module):
                 if self._ctx:
                     b.inv_ctx_off[s] = pb.table_ptr("inv_ctx_off%d" % s)
                     b.inv_ctx_idx[s] = pb.table_ptr("inv_ctx_idx%d" % s)
-            cache[self._ctx] = b
+            cache[key] = b
         b = _ext.Batch.from_buffer_copy(b)       # backward keeps this step's copy (its dropout seed)
         b.seed, b.training = int(seed) & 0xFFFFFFFF, int(bool(training))
         return b

@@ -289,9 +289,21 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 // the exp-based tanh, one dropout hash word per column pair, and 128-bit loads of the auxiliary tensor.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float tanh_fast(float x) {
-  // tanh(x) = (e^{2x} - 1) / (e^{2x} + 1); |x| clamped so e^{2x} stays finite. abs err ~1e-7.
-  const float t = __expf(2.0f * fminf(fmaxf(x, -15.f), 15.f));
-  return __fdividef(t - 1.0f, t + 1.0f);
+  // tanh(x) = 1 - 2 / (e^{2x} + 1): four instructions (mul, ex2, add+rcp, fma), no clamp needed —
+  // e^{2x} = inf gives 1 - 0 and e^{2x} = 0 gives 1 - 2.  abs err ~1e-7, like (t - 1) / (t + 1).
+  const float t = __expf(2.0f * x);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));   // 1 ulp; rcp(inf) = 0
+  return fmaf(-2.0f, r, 1.0f);
+}
+// hi/lo split of two values at once: hi2 / lo2 = packed bf16 pairs (a in the low half).  Two packed
+// converts instead of four scalar ones, and the hi parts come back as floats by shift / mask.
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi2 = *reinterpret_cast<const uint32_t*>(&h);
+  const float ha = __uint_as_float(hi2 << 16), hb = __uint_as_float(hi2 & 0xFFFF0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+  lo2 = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* p, bool vec, float (&out)[32]) {
@@ -424,12 +436,16 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpi& e, int M, int N, in
     // instruction covers 8 columns x 64 contiguous bytes (direct 2-byte stores: one column x 64 B).
     __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(stage);
     __nv_bfloat16* sl = sh + 32 * 32;
+    unsigned short* shu = reinterpret_cast<unsigned short*>(sh);
+    unsigned short* slu = reinterpret_cast<unsigned short*>(sl);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      __nv_bfloat16 h, l;
-      split_bf16(v[j], h, l);
-      sh[j * 32 + lane] = h;
-      sl[j * 32 + lane] = l;
+    for (int j = 0; j < 32; j += 2) {
+      uint32_t h2, l2;
+      split_bf16x2(v[j], v[j + 1], h2, l2);
+      shu[j * 32 + lane] = static_cast<unsigned short>(h2);
+      shu[(j + 1) * 32 + lane] = static_cast<unsigned short>(h2 >> 16);
+      slu[j * 32 + lane] = static_cast<unsigned short>(l2);
+      slu[(j + 1) * 32 + lane] = static_cast<unsigned short>(l2 >> 16);
     }
     __syncwarp();
     const int part = lane & 3;
@@ -483,15 +499,7 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpi& e, int M, int N, in
       for (int j = 0; j < 4; ++j) {
         uint32_t h[4], l[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(v[8 * j + 2 * q], h0, l0);
-          split_bf16(v[8 * j + 2 * q + 1], h1, l1);
-          h[q] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
-                 (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-          l[q] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
-                 (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
-        }
+        for (int q = 0; q < 4; ++q) split_bf16x2(v[8 * j + 2 * q], v[8 * j + 2 * q + 1], h[q], l[q]);
         ohi[j] = make_uint4(h[0], h[1], h[2], h[3]);
         olo[j] = make_uint4(l[0], l[1], l[2], l[3]);
       }

@@ -250,7 +250,9 @@ expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
   __shared__ float ref_w[EBT_REFS];         // 1 / segment length (1 for the ints branch)
   const int J = jb.J;
   const int lr = threadIdx.x >> 2;            // local unique row
-  const int cq = (threadIdx.x & 3) * 16;      // first of this thread's 16 columns inside the chunk
+  // this thread's 16 columns of a 64-column chunk: float4 number (t & 3) of each 16-column group, so the
+  // four lanes of a row read 64 contiguous bytes per load instruction (two full sectors)
+  const int q4 = (threadIdx.x & 3) * 4;
   const int u = u0 + lr;
   const bool live = u < jb.n_unique;
   // The references of 64 consecutive unique rows are one contiguous span of the CSR: resolve
@@ -279,7 +281,7 @@ expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
     float acc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.f;
-    const int j = c0 + cq;
+    const int j = c0 + q4;
     for (int q = beg; q < end; ++q) {
       int i, o;
       float w;
@@ -293,13 +295,13 @@ expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
         }
       }
       const float* gp = jb.d_in + static_cast<int64_t>(o) * jb.d_ld + j;
-      float4 g[4] = {ld4(gp), ld4(gp + 4), ld4(gp + 8), ld4(gp + 12)};
+      float4 g[4] = {ld4(gp), ld4(gp + 16), ld4(gp + 32), ld4(gp + 48)};
       if (jb.drop.p > 0.f) {
         const uint32_t rkey = drop_row_key(jb.drop.seed, jb.drop.stream_id, static_cast<uint32_t>(i));
-        const uint32_t cp = static_cast<uint32_t>(jb.drop.col_off + jb.slot * J + j) >> 1;   // j % 16 == 0
+        const uint32_t cp = static_cast<uint32_t>(jb.drop.col_off + jb.slot * J + j) >> 1;   // j % 4 == 0
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint32_t w0 = drop_word(rkey, cp + 2 * k), w1 = drop_word(rkey, cp + 2 * k + 1);
+          const uint32_t w0 = drop_word(rkey, cp + 8 * k), w1 = drop_word(rkey, cp + 8 * k + 1);
           if ((w0 & 0xFFFFu) < thr) g[k].x = 0.f;
           if ((w0 >> 16) < thr) g[k].y = 0.f;
           if ((w1 & 0xFFFFu) < thr) g[k].z = 0.f;
@@ -316,7 +318,7 @@ expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
       const float* rp = jb.r1 + static_cast<int64_t>(u) * J + j;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float4 r = ld4(rp + 4 * k);
+        const float4 r = ld4(rp + 16 * k);
         if (!(r.x > 0.f)) acc[4 * k] = 0.f;
         if (!(r.y > 0.f)) acc[4 * k + 1] = 0.f;
         if (!(r.z > 0.f)) acc[4 * k + 2] = 0.f;
@@ -327,8 +329,9 @@ expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
     for (int k = 0; k < 16; ++k) {
       __nv_bfloat16 h, l;
       split_bf16(acc[k], h, l);
-      tile[0][cq + k][lr] = h;
-      tile[1][cq + k][lr] = l;
+      const int col = 16 * (k >> 2) + q4 + (k & 3);      // acc[4 * kk + e] is column 16 * kk + q4 + e
+      tile[0][col][lr] = h;
+      tile[1][col][lr] = l;
     }
     __syncthreads();
     // write-out: thread t -> column t/4, 16 rows (32 bytes) of hi and of lo

@@ -38,6 +38,25 @@ class _PairScenes:
         self.scenes2inters = defaultdict(list)
 
 
+class _Blocks:
+    """Read-only sequence of the context blocks of one record: block i = rows [off[i], off[i+1]) of `cat`."""
+
+    def __init__(self, cat, counts):
+        self._cat = cat
+        self._off = np.concatenate(([0], np.cumsum(counts)))
+
+    def __len__(self):
+        return len(self._off) - 1
+
+    def __getitem__(self, i):
+        if i < 0:
+            i += len(self)
+        return self._cat[self._off[i]:self._off[i + 1]]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
 class IndexedMixedFeaturesDataset(Dataset):
     """source: dict with `interactions`, `rels`, `rels_list`, `rels_opp`, `clip_vec`, `track_vec`
     (see synthetic_world.subset) and `vocab`: object with `inter2idx`, `inter2mgd`, `mgd2idx`,
@@ -265,6 +284,8 @@ class IndexedMixedFeaturesDataset(Dataset):
                 tiled.append(len(trip) != 2)
                 ctx.append(np.asarray(rows, dtype=np.int32).reshape(-1, 3))
                 ctx_lab = np.asarray(cls, dtype=int)
+                # from here on a context block is either a table slice (ndarray [L, 3]) or ONE row, kept as
+                # the tuple it is: the blocks are laid out back to back once, below
                 rels_labs.append(gt_rel)
 
         if self.triplets:
@@ -284,7 +305,7 @@ class IndexedMixedFeaturesDataset(Dataset):
                 if len(cand) >= T:
                     continue
                 if opt.rels_multitask:
-                    rel_name, rows = NONE, [r]
+                    rel_name, rows = NONE, r
                     if (a, b) in self.rels[movie]:
                         rel_name = self.rels[movie][(a, b)].scene2rel(scene)
                         if rel_name != NONE:
@@ -293,7 +314,7 @@ class IndexedMixedFeaturesDataset(Dataset):
                             # the reference fills rows 1.. of this candidate's block and leaves row 0 — the
                             # row its interaction branch reads — all zero (:461-476); kept
                             r = (self.zero_clip, 0, 0)
-                    ctx.append(np.asarray(rows, dtype=np.int32).reshape(-1, 3))
+                    ctx.append(rows)
                     tiled.append(rel_name == NONE)
                     rels_labs.append(self.rels2idx[rel_name])
                 cand.append(r)
@@ -306,7 +327,7 @@ class IndexedMixedFeaturesDataset(Dataset):
                     if inter.bi:
                         gt_tracks[1] = len(cand)
                     if opt.rels_multitask:
-                        ctx.append(np.asarray([r], dtype=np.int32))
+                        ctx.append(r)
                         tiled.append(True)
                         rels_labs.append(self.rels2idx[NONE])
                     cand.append(r)
@@ -316,7 +337,7 @@ class IndexedMixedFeaturesDataset(Dataset):
                 if len(cand) < T - 1:
                     for r in (row(a, None), row(None, a)):
                         if opt.rels_multitask:
-                            ctx.append(np.asarray([r], dtype=np.int32))
+                            ctx.append(r)
                             tiled.append(True)
                             rels_labs.append(self.rels2idx[NONE])
                         cand.append(r)
@@ -325,11 +346,20 @@ class IndexedMixedFeaturesDataset(Dataset):
             rec["n_names"] = len(inter.id2names)
         rec["cand_rows"] = np.asarray(cand, dtype=np.int32).reshape(-1, 3)
         if opt.rels_multitask and opt.rels_multi_clip:
-            rec["ctx_rows"] = ctx
-            # the same blocks back to back + their lengths: what collate needs (one concatenate per item
-            # here instead of thousands of small array ops per batch there)
-            rec["ctx_counts"] = np.fromiter((len(x) for x in ctx), dtype=np.int64, count=len(ctx))
-            rec["ctx_cat"] = np.concatenate(ctx).astype(np.int64, copy=False) if ctx else np.zeros((0, 3), np.int64)
+            # the blocks back to back + their lengths: what collate needs (one pass per item here instead
+            # of thousands of small array ops per batch there); `ctx_rows` indexes into it block by block
+            counts = np.fromiter((1 if type(x) is tuple else len(x) for x in ctx), dtype=np.int64, count=len(ctx))
+            cat = np.empty((int(counts.sum()), 3), dtype=np.int64)
+            pos = 0
+            for x in ctx:
+                if type(x) is tuple:
+                    cat[pos] = x
+                    pos += 1
+                else:
+                    cat[pos:pos + len(x)] = x
+                    pos += len(x)
+            rec["ctx_counts"], rec["ctx_cat"] = counts, cat
+            rec["ctx_rows"] = _Blocks(cat, counts)
             rec["ctx_tiled"] = tiled
             rec["ctx_labels"] = ctx_lab
         if opt.rels_multitask and self.triplets:

@@ -110,7 +110,9 @@ _FLAGS = [
     ("--max_n_tripl", dict(default=20, type=int, help="candidate slots per clip (reference hard-codes 20)")),
     ("--synthetic", dict(default=0, type=int, help="1: independent synthetic MovieGraphs-shaped clips; 2: synthetic "
                                                    "annotation world through the index-only dataset")),
-    ("--resident_banks", dict(default=0, type=int, help="1: pooled feature banks stay in HBM, batches ship indices")),
+    ("--resident_banks", dict(default=1, type=int, help="1 (default): the split's pooled feature banks stay in HBM "
+                                                        "(< 1 GB for MovieGraphs) and batches ship index tables; "
+                                                        "0: every batch carries its feature rows host -> device")),
     ("--world_movies", dict(default=6, type=int)),
     ("--world_scenes", dict(default=40, type=int)),
 ]

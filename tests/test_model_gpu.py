@@ -268,3 +268,35 @@ def test_backward_with_transposed_weight_copies(preset, opt_preset, monkeypatch)
     model2, loss_fn2, out2, lv2, sd2, *_ = _run(preset, opt, 6, 21, True)
     for k, p in model2.named_parameters():
         assert rel_err(p.grad, g_t[k]) < 1e-5, k
+
+
+def test_full_size_batch_is_the_weighted_mean_of_its_halves(opt_preset):
+    """Size-independent property at the BENCH size (1024 clips: CTA-pair kernel over hundreds of tiles, LPT
+    schedule, split-K reductions, K-major W^T data gradients — paths the 6-clip oracle cases do not reach):
+    every loss is a mean over clips of per-clip terms, so without dropout the loss and every parameter gradient
+    of the full batch equal the clip-count-weighted mean of its two halves' — which run through different tile
+    counts, split factors and (second half) the in-place data-gradient form."""
+    from lirec_b200.mixed_utils import synthetic
+    opt = opt_preset("int_rel_ch")
+    B, cut = 1024, 160                                  # 160 clips ~ 1.3 k candidate rows: the in-place dgrad form
+    clips = [synthetic.make_clip(7 * 1000003 + i, preset="int_rel_ch") for i in range(B)]
+    model, loss_fn, _ = make_model(seed=2)
+    model.eval()                                        # no dropout: the masks are keyed by row position
+    outs = []
+    for part in (clips, clips[:cut], clips[cut:]):
+        pb = synthetic.pack_clips(part).to_device("cuda")
+        for p in model.parameters():
+            p.grad = None
+        lv = loss_fn(model(pb), {})
+        lv.backward()
+        outs.append((float(lv.detach()), {k: p.grad.double().clone() for k, p in model.named_parameters()}))
+    (l, g), (l1, g1), (l2, g2) = outs
+    w1, w2 = cut / B, (B - cut) / B
+    assert abs(l - (w1 * l1 + w2 * l2)) / abs(l) < 1e-5
+    for k in g:
+        ref = w1 * g1[k] + w2 * g2[k]
+        err = float((g[k] - ref).abs().max() / (ref.abs().max() + 1e-30))
+        # fp32 summation order only (~1e-6) — unless one of the ~10^6 hinge terms sits within 1e-7 of its
+        # kink and lands on the other side in the half batch (the head's K-split differs with the row count):
+        # one such term moves a head gradient by ~1e-3 of its max-norm, a lost tile or row block by > 3e-2
+        assert err < 2e-3, (k, err)

@@ -1,5 +1,10 @@
-import sys, time; sys.argv=['x']
-sys.path.insert(0,'/root/repo')
+"""Host-side batch assembly throughput of the index-only dataset (no GPU needed):
+__getitem__ per clip and collate_indexed per batch on the synthetic annotation world.
+
+    python tools/loader_probe.py
+"""
+import os, sys, time; sys.argv=['x']
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from lirec_b200.utils.arg_pars import opt
 for k, v in dict(tr_maximize=True, tracks=True, ints=1, ctx=1, gates=1, rels_multitask=True, rels_multi_clip=True,

@@ -111,6 +111,8 @@ def packed_loader(dataset, batch_size, shuffle, num_workers=0, device="cuda", ra
         a, b = dp.shard_range(len(idx), rank, world)
         if b > a:
             batches.append((idx[a:b], len(idx)))
+    if int(num_workers) > 0 and hasattr(dataset, "warm_records"):
+        dataset.warm_records()              # workers fork with the record cache already built
     loader = torch.utils.data.DataLoader(_IndexView(dataset, batches), batch_size=None, shuffle=False,
                                          num_workers=int(num_workers), collate_fn=None)
     copy_stream = torch.cuda.Stream(device=device)

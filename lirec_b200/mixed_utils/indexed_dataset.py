@@ -38,6 +38,26 @@ class _PairScenes:
         self.scenes2inters = defaultdict(list)
 
 
+def _mt_words(s0, s1, max_regen=64):
+    """32-bit words the global MT19937 produced between two `np.random.get_state()` snapshots (None if that
+    cannot be told): the position difference while the key is unchanged, else whole regenerations are
+    stepped through on a scratch generator."""
+    k0, p0, k1, p1 = s0[1], int(s0[2]), s1[1], int(s1[2])
+    if s0[3] != s1[3]:                      # a gaussian was drawn / cached: not a stream we account for
+        return None
+    if np.array_equal(k0, k1):
+        return p1 - p0 if p1 >= p0 else None
+    rs, words, key = np.random.RandomState(), 624 - p0, k0
+    for _ in range(max_regen):
+        rs.set_state(("MT19937", key, 624, 0, 0.0))
+        rs.bytes(4)                         # one word: regenerates the key, position 1
+        key = rs.get_state()[1]
+        if np.array_equal(key, k1):
+            return words + p1
+        words += 624
+    return None
+
+
 class _Blocks:
     """Read-only sequence of the context blocks of one record: block i = rows [off[i], off[i+1]) of `cat`."""
 
@@ -77,6 +97,7 @@ class IndexedMixedFeaturesDataset(Dataset):
         self.test_rels_multi_clip = False
         self._max_n_tripl = 0
         self.rels_n_clips = 0
+        self._plans, self._plan_sig, self._trace, self._trace_blk = {}, None, None, 0
         self.interactions = source["interactions"]
         with_rels = bool(opt.rels or opt.rels_multitask)
         self.rels = source["rels"] if with_rels else {}
@@ -227,12 +248,84 @@ class IndexedMixedFeaturesDataset(Dataset):
             return rows, (None if classes is None else classes[key])
         if self.mode == "train":
             # = np.random.choice(np.arange(L), n, replace=False) (reference :387), same global RNG stream
-            sel = np.random.permutation(L)[:n]
+            if self._trace is not None:              # first build of an item: account for the words drawn
+                pre = np.random.get_state()
+                sel = np.random.permutation(L)[:n]
+                self._trace.append((self._trace_blk, rows, None if classes is None else classes[key], n,
+                                    _mt_words(pre, np.random.get_state())))
+            else:
+                sel = np.random.permutation(L)[:n]
         else:
             sel = eval_idxs[key]
         return rows[sel], (None if classes is None else classes[key][sel])
 
+    # ---- record cache -----------------------------------------------------------------------------------
+    # An item is a deterministic function of the annotations except for (a) the train-mode context
+    # subsampling above and (b) `scene2rel` on a scene that carries several relationship names.  Items
+    # without (b) are built once; later accesses copy the cached record and redo only the (a) draws, in
+    # the original order, so the global numpy RNG stream stays the reference's (single-name `scene2rel`
+    # calls consume no random numbers).  Records are shared between accesses: treat them as read-only.
+    def _signature(self):
+        return (self.mode, self.rels_n_clips, self._max_n_tripl, bool(self.triplets), opt.inter_class, bool(opt.merged),
+                bool(opt.rels_multi_clip), bool(opt.tracks), bool(opt.rels_multitask), bool(opt.multilab_weights),
+                bool(opt.soft_gt))
+
     def __getitem__(self, idx_pair):
+        sig = self._signature()
+        if sig != self._plan_sig:
+            self._plans, self._plan_sig = {}, sig
+        plan = self._plans.get(idx_pair)
+        if plan is False:                            # known to draw other random numbers: always rebuilt
+            return self._build_record(idx_pair)
+        if plan is not None:
+            rec0, ops = plan
+            rec = dict(rec0)
+            if ops:
+                cat, off = rec0["ctx_cat"].copy(), rec0["ctx_rows"]._off
+                for blk, rows_all, cls_all, n, _ in ops:
+                    sel = np.random.permutation(len(rows_all))[:n]
+                    cat[off[blk]:off[blk] + n] = rows_all[sel]
+                    if cls_all is not None:
+                        rec["ctx_labels"] = np.asarray(cls_all[sel], dtype=int)
+                rec["ctx_cat"], rec["ctx_rows"] = cat, _Blocks(cat, rec0["ctx_counts"])
+            return rec
+        if not int(getattr(opt, "cache_records", 1)):
+            return self._build_record(idx_pair)
+        # first access: build, and find out whether the traced subsampling draws were the ONLY random
+        # numbers the build consumed (annotation objects draw too: `get_relship_by_id`, `scene2rel` with
+        # several names — at least one generator word per real choice): words produced by the global
+        # generator over the whole build against the words the traced draws account for
+        s0 = np.random.get_state()
+        self._trace, self._trace_blk = [], 0
+        try:
+            rec = self._build_record(idx_pair)
+            ops = self._trace
+        finally:
+            self._trace = None
+        total = _mt_words(s0, np.random.get_state())
+        traced = [op[4] for op in ops]
+        if total is not None and None not in traced and total == sum(traced):
+            self._plans[idx_pair] = (rec, ops)
+            rec = dict(rec)
+        else:
+            self._plans[idx_pair] = False
+        return rec
+
+    def warm_records(self):
+        """Build every cacheable record once (global RNG state preserved): DataLoader workers forked
+        afterwards share the cache copy-on-write instead of each rebuilding it every epoch."""
+        if not int(getattr(opt, "cache_records", 1)):
+            return self
+        state = np.random.get_state()
+        try:
+            for i in range(len(self)):
+                if self._plans.get(i) is None or self._plan_sig != self._signature():
+                    self[i]
+        finally:
+            np.random.set_state(state)
+        return self
+
+    def _build_record(self, idx_pair):
         i_id, t_idx = self.idxs_with_triplets[idx_pair]
         inter = self.interactions[i_id]
         movie, scene = inter.video_descr["movie"], inter.video_descr["scene"][0]
@@ -309,6 +402,7 @@ class IndexedMixedFeaturesDataset(Dataset):
                     if (a, b) in self.rels[movie]:
                         rel_name = self.rels[movie][(a, b)].scene2rel(scene)
                         if rel_name != NONE:
+                            self._trace_blk = len(ctx)
                             rows, _ = self._context(self.movie_ch1_ch2_rel, None, self.context_idxs,
                                                     (movie, a, b, rel_name))
                             # the reference fills rows 1.. of this candidate's block and leaves row 0 — the

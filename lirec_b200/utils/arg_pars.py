@@ -107,6 +107,9 @@ _FLAGS = [
     ("--native_step", dict(default=1, type=int, help="1: forward + loss + backward of a training iteration as three "
                                                      "native calls (no autograd engine round trip); 0: the "
                                                      "reference's model()/loss()/backward() sequence")),
+    ("--cache_records", dict(default=1, type=int, help="1: the index-only dataset keeps every deterministic item it has "
+                                                       "built and redoes only the train-mode context subsampling per "
+                                                       "access (same items, same numpy RNG stream); 0: rebuild always")),
     ("--max_n_tripl", dict(default=20, type=int, help="candidate slots per clip (reference hard-codes 20)")),
     ("--synthetic", dict(default=0, type=int, help="1: independent synthetic MovieGraphs-shaped clips; 2: synthetic "
                                                    "annotation world through the index-only dataset")),

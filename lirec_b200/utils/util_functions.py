@@ -53,8 +53,9 @@ class Relationship:
         names = self._scene2rel.get(scene_idx)
         if names:
             # np.random.choice(names) (reference :71-73) = names[randint(0, len)] on the same global RNG
-            # stream (checked draw for draw), without building a string array per call
-            return names[np.random.randint(0, len(names))]
+            # stream (checked draw for draw), without building a string array per call; a single name
+            # consumes no random number at all (numpy returns the lower bound for an empty range)
+            return names[0] if len(names) == 1 else names[np.random.randint(0, len(names))]
         return "None"
 
 

@@ -16,7 +16,9 @@ ds = ds.cache().init_relships() if hasattr(ds, "cache") else ds
 print(type(ds).__name__, len(ds))
 for B in (64, 256):
     idx = list(range(min(B, len(ds))))
+    c0 = time.perf_counter(); recs = [ds[i] for i in idx]; c1 = time.perf_counter()      # first access: builds the cache
     t0 = time.perf_counter(); recs = [ds[i] for i in idx]; t1 = time.perf_counter()
+    print("B=%d getitem first access %.2f ms/clip, cached %.3f ms/clip" % (len(idx), 1e3*(c1-c0)/len(idx), 1e3*(t1-t0)/len(idx)))
     for resident in (False, True):
         t2 = time.perf_counter()
         for _ in range(3): pb = ix.collate_indexed(recs, ds, resident=resident)

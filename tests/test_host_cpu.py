@@ -123,3 +123,36 @@ def test_device_tables_are_lazy_views_of_the_arena():
     pb = PackedBatch()
     pb.tables = t
     assert pb.table_ptr("labels") == arena.data_ptr() + 4 * 17 == pb["labels"].data_ptr()
+
+
+def test_install_aliases_exposes_the_reference_module_surface(monkeypatch):
+    """`lirec_b200.install_aliases()` lets code written against the reference (`from utils.arg_pars import
+    opt`, `import mlp.model`, `resume.int_rel_ch`) run on this package: same module objects, one `opt`,
+    the reference's class and entry-point names."""
+    import importlib
+    import sys
+    import lirec_b200
+    names = ("utils", "utils.arg_pars", "utils.util_functions", "utils.model_saver", "mlp", "mlp.model", "mlp.train",
+             "mlp.test", "mixed_utils", "mixed_utils.update_arg_pars", "mixed_utils.classification_dataloader",
+             "mixed_utils.mixed_features", "resume", "resume.modalties", "resume.int_rels", "resume.int_ch",
+             "resume.int_rel_ch")
+    for n in names:                                   # restored by monkeypatch afterwards
+        monkeypatch.setitem(sys.modules, n, sys.modules.get(n, None))
+    lirec_b200.install_aliases()
+    from utils.arg_pars import opt
+    from lirec_b200.utils.arg_pars import opt as opt2
+    assert opt is opt2
+    model = importlib.import_module("mlp.model")
+    for cls in ("Modalities", "MidFusionMultiClip", "MidFusionMultiClipMaxTracks", "GatingUnit",
+                "MaxMarginCrossEntropyLoss", "MultiTaskMaxMargin", "MarginLoss", "MarginTrackRelsLoss",
+                "MultiTaskCrossEntropyLoss", "create_model"):
+        assert hasattr(model, cls), cls
+    assert callable(importlib.import_module("mlp.train").training)
+    assert callable(importlib.import_module("mlp.test").testing)
+    assert callable(importlib.import_module("mixed_utils.classification_dataloader").MixedFeaturesDataset)
+    assert callable(importlib.import_module("mixed_utils.update_arg_pars").update)
+    for mod, fn in (("resume.modalties", "resume_modalities"), ("resume.int_rels", None), ("resume.int_ch", None),
+                    ("resume.int_rel_ch", "resume_max_tracks")):
+        m = importlib.import_module(mod)
+        if fn is not None:
+            assert callable(getattr(m, fn)), (mod, fn)

@@ -157,4 +157,8 @@ def reduce_and_step(model, optimizer, fused=None, local_clips=None, global_clips
             allreduce_flat_grad(model._flat_grad, local_clips, global_clips, average_in_place=True)
             optimizer.step()
     else:
-        optimizer.step()
+        step = getattr(optimizer, "_step_impl", None)       # FlatAdam: skip the Optimizer.step hook wrapper
+        if step is not None:
+            step()
+        else:
+            optimizer.step()

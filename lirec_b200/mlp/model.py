@@ -609,14 +609,18 @@ class FlatAdam(torch.optim.Optimizer):
             self.state[p] = {"step": torch.tensor(0.0), "exp_avg": self._m[off:off + n].view(p.shape),
                              "exp_avg_sq": self._v[off:off + n].view(p.shape)}
 
-    @torch.no_grad()
-    def step(self, closure=None, grad_scale=1.0):
+    def _step_impl(self, grad_scale=1.0):
+        """The step itself, without torch.optim.Optimizer's per-call hook / profiler wrapper (lirec_b200's
+        own loop calls this directly: ~25 us of host time per step at 64-clip batches)."""
         m = self.model
         g = self.param_groups[0]
         self._t += 1
         ops.adam_flat(m._flat, m._flat_grad, self._m, self._v, m._flat_bf16, g["lr"], g["betas"][0],
                       g["betas"][1], g["eps"], g["weight_decay"], self._t, grad_scale)
         m.mark_bf16_fresh()
+
+    def step(self, closure=None, grad_scale=1.0):
+        self._step_impl(grad_scale)
 
     def zero_grad(self, set_to_none=True):
         # backward overwrites the flat gradient buffer; p.grad keeps aliasing it

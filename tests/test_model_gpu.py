@@ -296,7 +296,9 @@ def test_full_size_batch_is_the_weighted_mean_of_its_halves(opt_preset):
     for k in g:
         ref = w1 * g1[k] + w2 * g2[k]
         err = float((g[k] - ref).abs().max() / (ref.abs().max() + 1e-30))
+        err2 = float((g[k] - ref).norm() / (ref.norm() + 1e-30))
         # fp32 summation order only (~1e-6) — unless one of the ~10^6 hinge terms sits within 1e-7 of its
         # kink and lands on the other side in the half batch (the head's K-split differs with the row count):
-        # one such term moves a head gradient by ~1e-3 of its max-norm, a lost tile or row block by > 3e-2
-        assert err < 2e-3, (k, err)
+        # one such term moves a head gradient by ~1e-3 of its max-norm but ~1e-5 of its 2-norm; a lost tile
+        # or row block shows as > 3e-2 in either
+        assert err < 2e-3 and err2 < 2e-4, (k, err, err2)

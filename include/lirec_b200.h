@@ -370,6 +370,29 @@ int lirec_model_backward(const lirec_model_cfg* cfg, const lirec_model_params* p
 int lirec_model_workspace_layout(const lirec_model_cfg* cfg, const lirec_batch* batch_host,
                                  int64_t* offsets, int max_entries);
 
+/* ---- host-side batch assembly (no GPU work) ---------------------------------
+ * Replaces the np.tile / hstack / vstack assembly of cached 6912-d rows in the reference's DataLoader
+ * workers (mixed_utils/classification_dataloader.py:329-334, 393-416, 474-497, mixed_features.py:115-125)
+ * and the default collate (mlp/train.py:33-37): a record carries only (clip, track1, track2) index triples
+ * into the DATASET banks; this call turns the concatenated triples of a batch into every integer table of
+ * a lirec_batch, in one int32 arena that crosses PCIe in one copy.  All pointers are HOST pointers.
+ *   cand_host [Ni,3] / cand_counts_host [B]: candidate triples per clip (reference slot order);
+ *   ctx_host [Nx,3] / ctx_counts_host [Ni]: context triples per candidate (both NULL: no context branch);
+ *   zero_clip: the dataset's all-zero clip row; track row 0 is the all-zero track.  References to either
+ *   are redirected to one private zero row per clip.
+ * Batch bank rows: rows the candidates use (ascending dataset row, private zero rows first), then the rows
+ * only context uses.  layout_host [24][2] = (offset, length) in arena_host of cand_off, cand_rows, ctx_off,
+ * ctx_rows, ctx_owner, labels, rels_label, gt_tracks, inv_cand_off0, inv_cand_idx0, .._off1, .._idx1, .._off2,
+ * .._idx2, inv_ctx_off0 .. inv_ctx_idx2, cand_clip, cand_slot, clip_src, track_src (length -1 = absent;
+ * labels / rels_label / gt_tracks are reserved for the caller to fill; clip_src / track_src = dataset-bank
+ * row behind every batch bank row).  sizes_host [4] = n_clip, n_clip_ints, n_track, n_track_ints.          */
+#define LIREC_COLLATE_NUM_TABLES 24
+int64_t lirec_collate_arena_bound(int64_t B, int64_t n_cand, int64_t n_ctx, int32_t has_ctx);
+int lirec_collate_tables(const int32_t* cand_host, const int32_t* cand_counts_host, int32_t B,
+                         const int32_t* ctx_host, const int32_t* ctx_counts_host, int32_t zero_clip,
+                         int32_t n_clip_rows, int32_t n_track_rows, int32_t max_slots,
+                         int32_t* arena_host, int64_t arena_cap, int64_t* layout_host, int32_t* sizes_host);
+
 /* ---- optimizer -----------------------------------------------------------
  * torch.optim.Adam with coupled L2 (reference mlp/model.py:599-601) over one
  * flat buffer; also refreshes the bf16 shadow of the weights.                */

@@ -157,6 +157,11 @@ def lib():
                                       C.c_void_p, C.c_void_p, C.c_void_p]
     L.lirec_model_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lirec_collate_arena_bound.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int32]
+    L.lirec_collate_arena_bound.restype = C.c_int64
+    L.lirec_collate_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                       C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
+                                       C.c_void_p]
     if L.lirec_abi_version() != 1:
         raise RuntimeError("liblirec_b200.so ABI version mismatch; rebuild it")
     _lib = L
@@ -168,6 +173,7 @@ EXPORTED_SYMBOLS = [
     "lirec_gemm_grouped", "lirec_profile_begin", "lirec_profile_end", "lirec_seg_reduce_f32", "lirec_seg_reduce_gather_f32", "lirec_rows_expand_fwd", "lirec_rows_expand_bwd",
     "lirec_split_f32", "lirec_cast_bf16", "lirec_gather_rows", "lirec_roi_max_pool_f32", "lirec_loss_track_fwd_bwd", "lirec_loss_rowmargin_fwd_bwd", "lirec_loss_ce_fwd_bwd", "lirec_predict_tracks",
     "lirec_model_workspace_bytes", "lirec_model_workspace_layout", "lirec_model_forward", "lirec_model_backward", "lirec_adam_flat", "lirec_dp_grid_size", "lirec_dp_allreduce_adam",
+    "lirec_collate_arena_bound", "lirec_collate_tables",
 ]
 
 # kernels launched through this binding since import (bench.py reports it as gpu_launches)

@@ -25,6 +25,8 @@ objects those loaders return (`source`), e.g. from mixed_utils/synthetic_world.p
 from collections import defaultdict
 from itertools import permutations
 
+import os
+
 import numpy as np
 import torch
 from torch.utils.data import Dataset
@@ -549,12 +551,90 @@ class IndexedMixedFeaturesDataset(Dataset):
         return out
 
 
+def _banks_bf16(dataset):
+    """bf16 torch copies of the dataset's two feature banks (what a batch ships), made once per bank array:
+    rounding a row before or after gathering it is the same row."""
+    key = (id(dataset.clip_bank), id(dataset.track_bank))
+    cached = dataset.__dict__.get("_bf16_banks")
+    if cached is None or cached[0] != key:
+        cached = (key, torch.from_numpy(np.ascontiguousarray(dataset.clip_bank, dtype=np.float32)).to(torch.bfloat16),
+                  torch.from_numpy(np.ascontiguousarray(dataset.track_bank, dtype=np.float32)).to(torch.bfloat16))
+        dataset.__dict__["_bf16_banks"] = cached
+    return cached[1], cached[2]
+
+
 def collate_indexed(records, dataset, resident=False):
     """records -> host PackedBatch.  The batch banks hold every referenced bank row ONCE: rows used by
     candidates first (the ints-branch prefix), then the rows only context refers to; references to the
     shared all-zero track row are redirected to one private zero row per clip (a single row referenced by
     thousands of table rows serialises the backward scatter-reduce).  With `resident=True` the banks are
-    left out and `pb.extras['bank_rows']` lists the dataset-bank rows to gather on the device."""
+    left out and `pb.extras['bank_rows']` lists the dataset-bank rows to gather on the device.
+
+    The integer tables are built by the native `lirec_collate_tables` (csrc/collate.cu; host code, safe in
+    DataLoader workers) straight into one int32 arena; `LIREC_NATIVE_COLLATE=0` selects the numpy
+    statement of the same tables (`collate_indexed_numpy`, which the tests hold the native one to)."""
+    if os.environ.get("LIREC_NATIVE_COLLATE", "1") == "0":
+        return collate_indexed_numpy(records, dataset, resident=resident)
+    from lirec_b200 import _ext
+    L = _ext.lib()
+    B = len(records)
+    has_ctx = "ctx_rows" in records[0]
+    track_models = "gt_tracks" in records[0]
+    cand = np.ascontiguousarray(np.concatenate([r["cand_rows"] for r in records]), dtype=np.int32).reshape(-1, 3)
+    counts = np.fromiter((len(r["cand_rows"]) for r in records), dtype=np.int32, count=B)
+    Ni = int(cand.shape[0])
+    ctx = ctx_counts = None
+    Nx = 0
+    if has_ctx:
+        if "ctx_cat" in records[0]:
+            ctx_counts = np.concatenate([r["ctx_counts"] for r in records])
+            ctx = np.concatenate([r["ctx_cat"] for r in records])
+        else:                                                   # records built by hand (tests, tools)
+            per = [np.asarray(x, dtype=np.int32).reshape(-1, 3) for r in records for x in r["ctx_rows"]]
+            ctx_counts = np.array([len(x) for x in per])
+            ctx = np.concatenate(per) if len(per) else np.zeros((0, 3), dtype=np.int32)
+        ctx_counts = np.ascontiguousarray(ctx_counts, dtype=np.int32)
+        ctx = np.ascontiguousarray(ctx, dtype=np.int32).reshape(-1, 3)
+        Nx = int(ctx.shape[0])
+        if len(ctx_counts) != Ni or int(ctx_counts.sum()) != Nx:
+            raise ValueError("collate_indexed: context blocks do not match the candidate rows")
+    T = dataset._max_n_tripl if track_models else 1
+    arena = np.empty(int(L.lirec_collate_arena_bound(B, Ni, Nx, int(has_ctx))), dtype=np.int32)
+    layout = np.empty((24, 2), dtype=np.int64)
+    sizes = np.empty(4, dtype=np.int32)
+    _ext.check(L.lirec_collate_tables(
+        cand.ctypes.data, counts.ctypes.data, B, ctx.ctypes.data if has_ctx else None,
+        ctx_counts.ctypes.data if has_ctx else None, int(dataset.zero_clip), len(dataset.clip_bank),
+        len(dataset.track_bank), int(T), arena.ctypes.data, arena.size, layout.ctypes.data, sizes.ctypes.data))
+    n_clip, n_clip_ints, n_track, n_track_ints = (int(v) for v in sizes)
+    clip_src = arena[layout[22, 0]:layout[22, 0] + n_clip].copy()
+    track_src = arena[layout[23, 0]:layout[23, 0] + n_track].copy()
+    if resident:                                                # banks are gathered on the device
+        clip_bank = torch.empty((n_clip, 0), dtype=torch.bfloat16)
+        track_bank = torch.empty((n_track, 0), dtype=torch.bfloat16)
+    else:                                                       # gather the rows from the bf16 copy of the banks
+        clip16, track16 = _banks_bf16(dataset)
+        clip_bank = clip16.index_select(0, torch.from_numpy(clip_src).long())
+        track_bank = track16.index_select(0, torch.from_numpy(track_src).long())
+    rels_label = None
+    if has_ctx and track_models:
+        rels_label = np.concatenate([np.asarray(r["rels_label"]).reshape(-1) for r in records])
+    elif has_ctx:
+        rels_label = np.array([r["rels_label"] for r in records])
+    gt = np.stack([r["gt_tracks"] for r in records]) if track_models else np.zeros((B, 2), dtype=np.int64)
+    mw = np.stack([r["multilab_weights"] for r in records]) if "multilab_weights" in records[0] else \
+        np.ones((B, dataset.n_classes))
+    extras = {k: np.array([r[k] for r in records]) for k in ("just_zeros", "n_names", "hash_rel") if k in records[0]}
+    pb = PackedBatch.from_arena(
+        arena, layout[:22], clip_bank, track_bank, n_clip_ints, n_track_ints, B, Ni, Nx if has_ctx else None,
+        [r["labels"] for r in records], rels_label, gt, mw, n_slots=T,
+        n_ctx_slots=records[0]["n_ctx_slots"], extras=extras)
+    pb.extras["bank_rows"] = (clip_src, track_src)
+    return pb
+
+
+def collate_indexed_numpy(records, dataset, resident=False):
+    """The numpy statement of `collate_indexed` (same tables, bit for bit)."""
     B = len(records)
     has_ctx = "ctx_rows" in records[0]
     track_models = "gt_tracks" in records[0]

@@ -181,6 +181,55 @@ class PackedBatch:
         pb.extras = dict(extras or {})
         return pb
 
+    @staticmethod
+    def from_arena(arena, layout, clip_bank, track_bank, n_clip_ints, n_track_ints, B, Ni, Nx, labels, rels_label,
+                   gt_tracks, multilab, n_slots=20, n_ctx_slots=18, extras=None):
+        """A host batch whose integer tables already lie in one int32 arena in `_INT_TABLES` order
+        (`lirec_collate_tables`, csrc/collate.cu): `layout[i] = (offset, length)` of table i, length -1 =
+        absent.  The tables are views into the arena, so `pin()` is a single copy.  Nx is None without a
+        context branch.  labels / rels_label / gt_tracks are written into their reserved slots here."""
+        pb = PackedBatch()
+        pb.B, pb.n_slots, pb.n_ctx_slots = int(B), int(n_slots), int(n_ctx_slots)
+        pb.clip_bank, pb.track_bank = _as_bf16(clip_bank), _as_bf16(track_bank)
+        pb.n_clip_ints, pb.n_track_ints = int(n_clip_ints), int(n_track_ints)
+        pb.multilab = torch.as_tensor(np.ascontiguousarray(np.asarray(multilab) != 0).astype(np.uint8))
+        pb.n_classes = int(pb.multilab.shape[1])
+        pb.has_ctx = Nx is not None
+        shapes = {"cand_rows": (Ni, 3), "ctx_rows": (Nx, 3), "gt_tracks": (B, 2)}
+        end = 0
+        host_layout = {}
+        for k, (off, n) in zip(_INT_TABLES, np.asarray(layout).tolist()):
+            if n < 0:
+                continue
+            assert off == end, "arena tables must be contiguous in _INT_TABLES order"
+            shape = shapes.get(k, (n,))
+            pb.tables[k] = arena[off:off + n].reshape(shape)
+            host_layout[k] = (off, n, shape)
+            end = off + n
+        t = pb.tables
+        t["labels"][:] = np.asarray(labels).reshape(B)
+        t["gt_tracks"][:] = np.asarray(gt_tracks).reshape(B, 2)
+        if pb.has_ctx:
+            t["rels_label"][:] = np.asarray(rels_label).reshape(Ni)
+        pb._host_arena, pb._host_layout = arena[:end], host_layout
+        pb.extras = dict(extras or {})
+        return pb
+
+    # A natively collated batch crosses the DataLoader worker -> main process pipe as its arena alone: the
+    # table views are rebuilt on arrival (pickling them would ship every table twice).
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        if st.get("_host_arena") is not None and st.get("device") is None:
+            st["tables"] = None
+            st.pop("_arena", None)
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        if self.tables is None:
+            self.tables = {k: self._host_arena[off:off + n].reshape(shape)
+                           for k, (off, n, shape) in self._host_layout.items()}
+
     # ---- device staging --------------------------------------------------------------------
     def h2d_bytes(self):
         n = self.clip_bank.numel() * 2 + self.track_bank.numel() * 2 + self.multilab.numel()
@@ -191,6 +240,13 @@ class PackedBatch:
     def pin(self):
         """Move the host copy into pinned memory (one int32 arena + the two banks + multilab)."""
         assert self.device is None
+        if getattr(self, "_host_arena", None) is not None and not hasattr(self, "_arena"):
+            self._arena = torch.from_numpy(self._host_arena).pin_memory()        # one copy: tables are arena views
+            self._layout = self._host_layout
+            self.clip_bank = self.clip_bank.pin_memory()
+            self.track_bank = self.track_bank.pin_memory()
+            self.multilab = self.multilab.pin_memory()
+            return self
         names = [k for k in _INT_TABLES if k in self.tables]
         sizes = [int(self.tables[k].size) for k in names]
         arena = torch.empty(sum(sizes), dtype=torch.int32).pin_memory()
@@ -239,6 +295,8 @@ class PackedBatch:
                   "tables"):
             setattr(d, k, getattr(self, k))
         d.extras = dict(self.extras)
+        if getattr(self, "_host_arena", None) is not None:
+            d._host_arena, d._host_layout = self._host_arena, self._host_layout
         d.clip_bank = torch.empty((self.n_clip, 0), dtype=torch.bfloat16)
         d.track_bank = torch.empty((self.n_track, 0), dtype=torch.bfloat16)
         d.extras["bank_rows"] = (np.ascontiguousarray(clip_rows, dtype=np.int32),

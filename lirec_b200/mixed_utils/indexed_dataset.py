@@ -63,9 +63,9 @@ def _mt_words(s0, s1, max_regen=64):
 class _Blocks:
     """Read-only sequence of the context blocks of one record: block i = rows [off[i], off[i+1]) of `cat`."""
 
-    def __init__(self, cat, counts):
+    def __init__(self, cat, counts, off=None):
         self._cat = cat
-        self._off = np.concatenate(([0], np.cumsum(counts)))
+        self._off = np.concatenate(([0], np.cumsum(counts))) if off is None else off
 
     def __len__(self):
         return len(self._off) - 1
@@ -99,7 +99,7 @@ class IndexedMixedFeaturesDataset(Dataset):
         self.test_rels_multi_clip = False
         self._max_n_tripl = 0
         self.rels_n_clips = 0
-        self._plans, self._plan_sig, self._trace, self._trace_blk = {}, None, None, 0
+        self._plans, self._plan_sig, self._trace, self._trace_blk, self._forced = {}, None, None, 0, None
         self.interactions = source["interactions"]
         with_rels = bool(opt.rels or opt.rels_multitask)
         self.rels = source["rels"] if with_rels else {}
@@ -250,23 +250,50 @@ class IndexedMixedFeaturesDataset(Dataset):
             return rows, (None if classes is None else classes[key])
         if self.mode == "train":
             # = np.random.choice(np.arange(L), n, replace=False) (reference :387), same global RNG stream
-            if self._trace is not None:              # first build of an item: account for the words drawn
-                pre = np.random.get_state()
-                sel = np.random.permutation(L)[:n]
-                self._trace.append((self._trace_blk, rows, None if classes is None else classes[key], n,
-                                    _mt_words(pre, np.random.get_state())))
+            if self._trace is not None:              # cached mode: a replayed prefix is forced, the rest accounted for
+                if self._forced:
+                    sel, words = self._forced.pop(0), 0
+                else:
+                    pre = np.random.get_state()
+                    sel = np.random.permutation(L)[:n]
+                    words = _mt_words(pre, np.random.get_state())
+                self._trace.append(("p", self._trace_blk, rows, None if classes is None else classes[key], n, words))
             else:
                 sel = np.random.permutation(L)[:n]
         else:
             sel = eval_idxs[key]
         return rows[sel], (None if classes is None else classes[key][sel])
 
+    def _choose(self, names):
+        """`np.random.choice(names)` of the annotation objects (`AnnotatedInter.get_relship_by_id`, reference
+        utils/util_functions.py:234-236; `Relationship.scene2rel`, :70-73) = names[randint(0, len)] on the
+        same global RNG stream (a single name consumes no random number), as a traced / replayable draw."""
+        k = len(names)
+        if k == 1:
+            return names[0]
+        if self._trace is None:
+            return names[np.random.randint(0, k)]
+        if self._forced:
+            o, words = self._forced.pop(0), 0
+        else:
+            pre = np.random.get_state()
+            o = int(np.random.randint(0, k))
+            words = _mt_words(pre, np.random.get_state())
+        self._trace.append(("c", k, o, words))
+        return names[o]
+
     # ---- record cache -----------------------------------------------------------------------------------
-    # An item is a deterministic function of the annotations except for (a) the train-mode context
-    # subsampling above and (b) `scene2rel` on a scene that carries several relationship names.  Items
-    # without (b) are built once; later accesses copy the cached record and redo only the (a) draws, in
-    # the original order, so the global numpy RNG stream stays the reference's (single-name `scene2rel`
-    # calls consume no random numbers).  Records are shared between accesses: treat them as read-only.
+    # An item is a deterministic function of the annotations and of the random numbers it draws: (a) the
+    # train-mode context subsampling above and (b) the choice among several relationship names of a pair
+    # (`_choose`).  (a) changes rows, (b) changes what is built next.  Per item the cache keeps the DECISION
+    # TREE of its draws: ["c", k, {outcome: node}] for a choice among k names, ["p", block, rows, classes, n,
+    # node] for a subsampling of `rows` to n, ["l", record] at the end.  An access walks the tree making the
+    # same draws, in the same order, on the global numpy RNG — so the stream stays the reference's — then
+    # copies the leaf's record and lays the freshly drawn context rows into it; an outcome met for the first
+    # time builds the record with the draws made so far forced and hangs the new branch into the tree.
+    # Whether a build drew anything the tree does not account for is decided by exact accounting of the
+    # generator words it consumed; such items are rebuilt on every access.  Records are shared between
+    # accesses: treat them as read-only.
     def _signature(self):
         return (self.mode, self.rels_n_clips, self._max_n_tripl, bool(self.triplets), opt.inter_class, bool(opt.merged),
                 bool(opt.rels_multi_clip), bool(opt.tracks), bool(opt.rels_multitask), bool(opt.multilab_weights),
@@ -276,46 +303,72 @@ class IndexedMixedFeaturesDataset(Dataset):
         sig = self._signature()
         if sig != self._plan_sig:
             self._plans, self._plan_sig = {}, sig
-        plan = self._plans.get(idx_pair)
-        if plan is False:                            # known to draw other random numbers: always rebuilt
+        node = self._plans.get(idx_pair)
+        if node is False:                            # draws random numbers the tree cannot account for
             return self._build_record(idx_pair)
-        if plan is not None:
-            rec0, ops = plan
-            rec = dict(rec0)
-            if ops:
-                cat, off = rec0["ctx_cat"].copy(), rec0["ctx_rows"]._off
-                for blk, rows_all, cls_all, n, _ in ops:
-                    sel = np.random.permutation(len(rows_all))[:n]
-                    cat[off[blk]:off[blk] + n] = rows_all[sel]
-                    if cls_all is not None:
-                        rec["ctx_labels"] = np.asarray(cls_all[sel], dtype=int)
-                rec["ctx_cat"], rec["ctx_rows"] = cat, _Blocks(cat, rec0["ctx_counts"])
-            return rec
-        if not int(getattr(opt, "cache_records", 1)):
-            return self._build_record(idx_pair)
-        # first access: build, and find out whether the traced subsampling draws were the ONLY random
-        # numbers the build consumed (annotation objects draw too: `get_relship_by_id`, `scene2rel` with
-        # several names — at least one generator word per real choice): words produced by the global
-        # generator over the whole build against the words the traced draws account for
-        s0 = np.random.get_state()
-        self._trace, self._trace_blk = [], 0
-        try:
-            rec = self._build_record(idx_pair)
-            ops = self._trace
-        finally:
-            self._trace = None
-        total = _mt_words(s0, np.random.get_state())
-        traced = [op[4] for op in ops]
-        if total is not None and None not in traced and total == sum(traced):
-            self._plans[idx_pair] = (rec, ops)
-            rec = dict(rec)
-        else:
-            self._plans[idx_pair] = False
+        if node is None:
+            if not int(getattr(opt, "cache_records", 1)):
+                return self._build_record(idx_pair)
+            return self._explore(idx_pair, None, None, [])
+        drawn, perms = [], None
+        while True:
+            tag = node[0]
+            if tag == "l":
+                break
+            if tag == "p":
+                sel = np.random.permutation(len(node[2]))[:node[4]]
+                if perms is None:
+                    perms = []
+                perms.append((node, sel))
+                drawn.append(sel)
+                node = node[5]
+            else:
+                o = int(np.random.randint(0, node[1]))
+                drawn.append(o)
+                nxt = node[2].get(o)
+                if nxt is None:
+                    return self._explore(idx_pair, node, o, drawn)
+                node = nxt
+        rec0 = node[1]
+        rec = dict(rec0)
+        if perms:
+            cat, off = rec0["ctx_cat"].copy(), rec0["ctx_rows"]._off
+            for (_, blk, rows_all, cls_all, n, _), sel in perms:
+                cat[off[blk]:off[blk] + n] = rows_all[sel]
+                if cls_all is not None:
+                    rec["ctx_labels"] = np.asarray(cls_all[sel], dtype=int)
+            rec["ctx_cat"], rec["ctx_rows"] = cat, _Blocks(cat, None, off)
         return rec
 
-    def warm_records(self):
-        """Build every cacheable record once (global RNG state preserved): DataLoader workers forked
-        afterwards share the cache copy-on-write instead of each rebuilding it every epoch."""
+    def _explore(self, idx_pair, parent, outcome, drawn):
+        """Build the record with the draws already made (`drawn`) forced, account for every generator word
+        the rest of the build consumes, and hang the new branch under `parent[outcome]` (or as the root)."""
+        s0 = np.random.get_state()
+        self._trace, self._trace_blk, self._forced = [], 0, list(drawn)
+        try:
+            rec = self._build_record(idx_pair)
+            events, leftover = self._trace, len(self._forced)
+        finally:
+            self._trace, self._forced = None, None
+        total = _mt_words(s0, np.random.get_state())
+        new = events[len(drawn):]
+        words = [e[-1] for e in new]
+        if leftover or len(events) < len(drawn) or total is None or None in words or total != sum(words):
+            self._plans[idx_pair] = False
+            return rec
+        tail = ["l", rec]
+        for e in reversed(new):
+            tail = ["c", e[1], {e[2]: tail}] if e[0] == "c" else ["p", e[1], e[2], e[3], e[4], tail]
+        if parent is None:
+            self._plans[idx_pair] = tail
+        else:
+            parent[2][outcome] = tail
+        return dict(rec)
+
+    def warm_records(self, max_branches=32):
+        """Build every item's decision tree ahead of use (global RNG state preserved): the path a first access
+        takes, then the outcomes not met yet, up to `max_branches` per item.  DataLoader workers forked
+        afterwards share the trees copy-on-write instead of each exploring them again."""
         if not int(getattr(opt, "cache_records", 1)):
             return self
         state = np.random.get_state()
@@ -323,6 +376,19 @@ class IndexedMixedFeaturesDataset(Dataset):
             for i in range(len(self)):
                 if self._plans.get(i) is None or self._plan_sig != self._signature():
                     self[i]
+                budget = int(max_branches)
+                stack = [(self._plans.get(i), [])]
+                while stack and budget > 0 and self._plans.get(i):
+                    node, drawn = stack.pop()
+                    if node[0] == "p":                       # any subsample does: an access lays its own rows in
+                        stack.append((node[5], drawn + [np.arange(node[4])]))
+                    elif node[0] == "c":
+                        for o in range(node[1]):
+                            if o not in node[2] and budget > 0:
+                                budget -= 1
+                                self._explore(i, node, o, drawn + [o])
+                            if self._plans.get(i) and o in node[2]:
+                                stack.append((node[2][o], drawn + [o]))
         finally:
             np.random.set_state(state)
         return self
@@ -354,7 +420,8 @@ class IndexedMixedFeaturesDataset(Dataset):
         tiled = []              # per candidate: context block is an np.tile of the candidate's own row
 
         if opt.rels_multitask:
-            gt_rel = self.rels2idx[inter.get_relship_by_id(t_idx)]
+            rel_opts = inter.relships.get(t_idx)         # = inter.get_relship_by_id(t_idx), as a replayable draw
+            gt_rel = self.rels2idx[self._choose(rel_opts) if rel_opts else NONE]
             rec["rels_label"] = gt_rel
             if opt.rels_multi_clip:
                 if len(trip) == 2:
@@ -402,7 +469,8 @@ class IndexedMixedFeaturesDataset(Dataset):
                 if opt.rels_multitask:
                     rel_name, rows = NONE, r
                     if (a, b) in self.rels[movie]:
-                        rel_name = self.rels[movie][(a, b)].scene2rel(scene)
+                        rel_opts = self.rels[movie][(a, b)]._scene2rel.get(scene)  # = .scene2rel(scene)
+                        rel_name = self._choose(rel_opts) if rel_opts else NONE
                         if rel_name != NONE:
                             self._trace_blk = len(ctx)
                             rows, _ = self._context(self.movie_ch1_ch2_rel, None, self.context_idxs,

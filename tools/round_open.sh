@@ -26,4 +26,5 @@ timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --cloc
 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -c 40 \
   -o $out/${tag}_step_full -f python bench.py --steps 1 --warmup 3 --ncu_window --no_cpu_baseline > $out/${tag}_ncu_full.log 2>&1
 python tools/loader_probe.py > $out/${tag}_loader_probe.txt 2>&1
+timeout 600 python tools/e2e_loader_probe.py > $out/${tag}_e2e_loader_probe.json 2> $out/${tag}_e2e_loader_probe.err; tail -c 700 $out/${tag}_e2e_loader_probe.json
 ls -la $out | tail -20

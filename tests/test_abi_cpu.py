@@ -75,3 +75,22 @@ def test_product_never_imports_oracle():
                 with open(os.path.join(dirpath, fn)) as f:
                     src = f.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, fn)
+
+
+def test_integration_stubs_match_the_binding():
+    """INTEGRATION.md's ctypes stubs: every python block parses, and the struct it declares has the fields of
+    the real binding (a by-value struct with missing tail fields would pass garbage)."""
+    from lirec_b200 import _ext
+    with open(os.path.join(ROOT, "INTEGRATION.md")) as f:
+        blocks = re.findall(r"```python\n(.*?)```", f.read(), flags=re.S)
+    assert len(blocks) >= 3
+    for b in blocks:
+        compile(b, "INTEGRATION.md", "exec")
+    stub = [b for b in blocks if "class TrackLossCfg" in b][0]
+    fields = re.findall(r'\("(\w+)", ctypes\.c_(\w+)\)', stub.split("def margin_track_rels")[0])
+    real = list(_ext.TrackLossCfg._fields_)
+    assert [(n, getattr(ctypes, "c_" + t)) for n, t in fields] == real, (fields, real)
+    with open(os.path.join(ROOT, "include", "lirec_b200.h")) as f:
+        header = f.read()
+    body = header[header.index("typedef struct lirec_track_loss_cfg"):header.index("} lirec_track_loss_cfg;")]
+    assert re.findall(r"\b(?:float|int32_t|uint32_t)\s+(\w+);", body) == [n for n, _ in real]

@@ -94,3 +94,50 @@ def test_integration_stubs_match_the_binding():
         header = f.read()
     body = header[header.index("typedef struct lirec_track_loss_cfg"):header.index("} lirec_track_loss_cfg;")]
     assert re.findall(r"\b(?:float|int32_t|uint32_t)\s+(\w+);", body) == [n for n, _ in real]
+
+
+def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
+    """include/lirec_b200.h compiles as C (gcc, no CUDA headers), and every struct the ctypes binding passes
+    has the size and the field offsets the C compiler gives it."""
+    import shutil
+    import subprocess
+    from lirec_b200 import _ext
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    pairs = {"lirec_dropout": _ext.Dropout, "lirec_operand": _ext.Operand, "lirec_gemm_pass": _ext.GemmPass,
+             "lirec_epilogue": _ext.Epilogue, "lirec_gemm_problem": _ext.GemmProblem,
+             "lirec_track_loss_cfg": _ext.TrackLossCfg, "lirec_linear": _ext.Linear, "lirec_encoder": _ext.Encoder,
+             "lirec_model_params": _ext.ModelParams, "lirec_model_cfg": _ext.ModelCfg, "lirec_batch": _ext.Batch}
+    with open(os.path.join(ROOT, "include", "lirec_b200.h")) as f:
+        header = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "lirec_b200.h"', "int main(void) {"]
+    expect = []
+    for cname, ct in pairs.items():
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), header, flags=re.S).group(1)
+        # `a, b` declarations: the first name is the last token of the part before the first comma
+        cfields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            parts = [x.strip() for x in decl.split(",")]
+            names = [parts[0].split()[-1]] + parts[1:]
+            cfields += [re.sub(r"\[.*", "", n).lstrip("*") for n in names]
+        pfields = [n for n, _ in ct._fields_]
+        assert len(cfields) == len(pfields), (cname, cfields, pfields)
+        lines.append('printf("%%zu\\n", sizeof(%s));' % cname)
+        expect.append((cname, "sizeof", ctypes.sizeof(ct)))
+        for cf, pf in zip(cfields, pfields):
+            lines.append('printf("%%zu\\n", offsetof(%s, %s));' % (cname, cf))
+            expect.append((cname, cf, getattr(ct, pf).offset))
+    lines += ["return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert len(out) == len(expect)
+    for got, (cname, what, want) in zip(out, expect):
+        assert int(got) == want, (cname, what, got, want)

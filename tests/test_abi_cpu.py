@@ -141,3 +141,37 @@ def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
     assert len(out) == len(expect)
     for got, (cname, what, want) in zip(out, expect):
         assert int(got) == want, (cname, what, got, want)
+
+
+def test_argtypes_arity_matches_the_header(built_lib):
+    """Every entry point the binding types has as many `argtypes` as the header declares parameters, with
+    pointers / 64-bit / 32-bit / float / by-value-struct parameters in the same positions."""
+    from lirec_b200 import _ext
+    L = _ext.lib()
+    with open(os.path.join(ROOT, "include", "lirec_b200.h")) as f:
+        header = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    decls = re.findall(r"\b(lirec_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", header)
+    assert len(decls) >= 25
+    checked = 0
+    for name, params in decls:
+        params = [p.strip() for p in params.split(",")] if params.strip() not in ("", "void") else []
+        fn = getattr(L, name)
+        if fn.argtypes is None:
+            assert not params or name in ("lirec_profile_begin", "lirec_dp_grid_size"), name
+            continue
+        assert len(fn.argtypes) == len(params), (name, len(fn.argtypes), params)
+        for at, p in zip(fn.argtypes, params):
+            if "*" in p:
+                kind = ctypes.c_void_p
+            elif re.match(r"(const\s+)?(int64_t|size_t)\b", p):
+                kind = (ctypes.c_int64, ctypes.c_size_t)
+            elif re.match(r"(const\s+)?(int32_t|int|uint32_t)\b", p):
+                kind = (ctypes.c_int32, ctypes.c_uint32, ctypes.c_int)
+            elif re.match(r"(const\s+)?float\b", p):
+                kind = ctypes.c_float
+            else:                                   # a struct by value
+                assert issubclass(at, ctypes.Structure), (name, p, at)
+                continue
+            assert at in (kind if isinstance(kind, tuple) else (kind,)), (name, p, at)
+        checked += 1
+    assert checked >= 20

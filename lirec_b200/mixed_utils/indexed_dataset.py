@@ -189,6 +189,7 @@ class IndexedMixedFeaturesDataset(Dataset):
         if opt.rels_multi_clip:
             self.rels_n_clips = opt.rels_n_clips
             self._cache_relationships()
+        self._plans, self._plan_sig = {}, None      # cached records point into the tables built above
         return self
 
     def _triple(self, inter_id, a, b):
@@ -622,13 +623,13 @@ class IndexedMixedFeaturesDataset(Dataset):
 def _banks_bf16(dataset):
     """bf16 torch copies of the dataset's two feature banks (what a batch ships), made once per bank array:
     rounding a row before or after gathering it is the same row."""
-    key = (id(dataset.clip_bank), id(dataset.track_bank))
     cached = dataset.__dict__.get("_bf16_banks")
-    if cached is None or cached[0] != key:
-        cached = (key, torch.from_numpy(np.ascontiguousarray(dataset.clip_bank, dtype=np.float32)).to(torch.bfloat16),
+    if cached is None or cached[0] is not dataset.clip_bank or cached[1] is not dataset.track_bank:
+        cached = (dataset.clip_bank, dataset.track_bank,
+                  torch.from_numpy(np.ascontiguousarray(dataset.clip_bank, dtype=np.float32)).to(torch.bfloat16),
                   torch.from_numpy(np.ascontiguousarray(dataset.track_bank, dtype=np.float32)).to(torch.bfloat16))
         dataset.__dict__["_bf16_banks"] = cached
-    return cached[1], cached[2]
+    return cached[2], cached[3]
 
 
 def collate_indexed(records, dataset, resident=False):

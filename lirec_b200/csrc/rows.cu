@@ -242,6 +242,15 @@ constexpr int EBT_ZSPLIT = LIREC_EBT_ZSPLIT;   // references cached in shared me
 #ifndef LIREC_EBT_MIN_BLOCKS
 #define LIREC_EBT_MIN_BLOCKS 4
 #endif
+// A/B knob (undefined = what ships): references of a unique row walked N at a time, so the row gathers of
+// consecutive references are in flight together (tools/build_variants.sh builds the alternatives)
+#define LIREC_PRAGMA_(x) _Pragma(#x)
+#define LIREC_PRAGMA_UNROLL(n) LIREC_PRAGMA_(unroll n)
+#ifdef LIREC_EBT_UNROLL
+#define LIREC_EBT_UNROLL_PRAGMA LIREC_PRAGMA_UNROLL(LIREC_EBT_UNROLL)
+#else
+#define LIREC_EBT_UNROLL_PRAGMA     /* default: the compiler's own choice, as shipped and measured */
+#endif
 __global__ void __launch_bounds__(256, LIREC_EBT_MIN_BLOCKS)
 expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
   const ExpandBwdJob& jb = jobs.job[blockIdx.y];
@@ -285,6 +294,7 @@ expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.f;
     const int j = c0 + q4;
+    LIREC_EBT_UNROLL_PRAGMA
     for (int q = beg; q < end; ++q) {
       int i, o;
       float w;

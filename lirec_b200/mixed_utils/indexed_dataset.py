@@ -513,8 +513,8 @@ class IndexedMixedFeaturesDataset(Dataset):
         if opt.rels_multitask and opt.rels_multi_clip:
             # the blocks back to back + their lengths: what collate needs (one pass per item here instead
             # of thousands of small array ops per batch there); `ctx_rows` indexes into it block by block
-            counts = np.fromiter((1 if type(x) is tuple else len(x) for x in ctx), dtype=np.int64, count=len(ctx))
-            cat = np.empty((int(counts.sum()), 3), dtype=np.int64)
+            counts = np.fromiter((1 if type(x) is tuple else len(x) for x in ctx), dtype=np.int32, count=len(ctx))
+            cat = np.empty((int(counts.sum()), 3), dtype=np.int32)
             pos = 0
             for x in ctx:
                 if type(x) is tuple:
@@ -690,9 +690,10 @@ def collate_indexed(records, dataset, resident=False):
         rels_label = np.concatenate([np.asarray(r["rels_label"]).reshape(-1) for r in records])
     elif has_ctx:
         rels_label = np.array([r["rels_label"] for r in records])
-    gt = np.stack([r["gt_tracks"] for r in records]) if track_models else np.zeros((B, 2), dtype=np.int64)
-    mw = np.stack([r["multilab_weights"] for r in records]) if "multilab_weights" in records[0] else \
-        np.ones((B, dataset.n_classes))
+    gt = np.concatenate([r["gt_tracks"] for r in records]).reshape(B, 2) if track_models else \
+        np.zeros((B, 2), dtype=np.int64)
+    mw = np.concatenate([r["multilab_weights"] for r in records]).reshape(B, -1) if "multilab_weights" in records[0] \
+        else np.ones((B, dataset.n_classes))
     extras = {k: np.array([r[k] for r in records]) for k in ("just_zeros", "n_names", "hash_rel") if k in records[0]}
     pb = PackedBatch.from_arena(
         arena, layout[:22], clip_bank, track_bank, n_clip_ints, n_track_ints, B, Ni, Nx if has_ctx else None,

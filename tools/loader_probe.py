@@ -18,17 +18,18 @@ t0 = time.perf_counter()
 if hasattr(ds, "warm_records"):
     ds.warm_records()          # what packed_loader does before forking workers: every item's decision tree
 print("warm_records %.1f ms (%.2f ms/clip, once)" % (1e3 * (time.perf_counter() - t0), 1e3 * (time.perf_counter() - t0) / len(ds)))
-for B in (64, 256):
-    idx = list(range(min(B, len(ds))))
-    c0 = time.perf_counter(); recs = [ds[i] for i in idx]; c1 = time.perf_counter()
-    t0 = time.perf_counter(); recs = [ds[i] for i in idx]; t1 = time.perf_counter()
-    print("B=%d getitem %.3f / %.3f ms/clip (two passes)" % (len(idx), 1e3*(c1-c0)/len(idx), 1e3*(t1-t0)/len(idx)))
+def best(f, n=7):
+    ts = []
+    for _ in range(n):
+        t0 = time.perf_counter(); r = f(); ts.append(time.perf_counter() - t0)
+    return min(ts), r
+for B in (64, 256, 1024):
+    idx = [i % len(ds) for i in range(B)]
+    tg, recs = best(lambda: [ds[i] for i in idx])
     for resident in (False, True):
-        t2 = time.perf_counter()
-        for _ in range(3): pb = ix.collate_indexed(recs, ds, resident=resident)
-        t3 = time.perf_counter()
-        print("B=%d getitem %.2f ms/clip  collate(resident=%s) %.1f ms/batch -> %.0f clips/s/core (getitem+collate)" % (
-            len(idx), 1e3*(t1-t0)/len(idx), resident, 1e3*(t3-t2)/3, len(idx)/((t1-t0)+(t3-t2)/3)))
+        tc, pb = best(lambda: ix.collate_indexed(recs, ds, resident=resident))
+        print("B=%d getitem %.1f us/clip  collate(resident=%s) %.2f ms/batch (%.1f us/clip) -> %.0f clips/s/core (best of 7)" % (
+            B, 1e6 * tg / B, resident, 1e3 * tc, 1e6 * tc / B, B / (tg + tc)))
 import cProfile, pstats
 pr = cProfile.Profile(); pr.enable()
 recs = [ds[i] for i in range(min(256, len(ds)))]; pb = ix.collate_indexed(recs, ds, resident=True)

@@ -113,6 +113,71 @@ def create_model(name, n_classes, n_rels, seed=0, **overrides):
     return model, loss
 
 
+class DropoutReplay(torch.nn.Module):
+    """Stand-in for the reference's `self.dropout` modules (mlp/model.py:52, 347): instead of drawing
+    from torch's global RNG it applies the NEXT mask of `queue` (0/1 tensors, any shape with the input's
+    element count) scaled by 1/(1-p) — nn.Dropout's own train-mode arithmetic.  The queue is filled in the
+    reference's call order (mlp/model.py:62-88, 155-196, 282-327, 353):
+        ints: txt, vis, tracks1, tracks2, cat   ctx: txt, vis, tracks1, tracks2, cat   gate
+    so the oracle's keyed masks and the unmodified reference forward see the same masks."""
+
+    def __init__(self, p, queue):
+        super().__init__()
+        self.p, self.queue = p, queue
+
+    def forward(self, x):
+        m = self.queue.pop(0)
+        assert m.numel() == x.numel(), (tuple(m.shape), tuple(x.shape))
+        return x * m.reshape(x.shape).to(x.dtype) / (1.0 - self.p)
+
+
+def mask_order(masks, modality="m", tracks=True):
+    """Keys of oracle/model.py's `masks` dict in the order the reference's forward calls dropout."""
+    slots = [s for s in ("txt", "vis", "tracks1", "tracks2")
+             if (s == "txt" and modality in ("m", "t")) or (s == "vis" and modality in ("m", "v"))
+             or (s.startswith("tracks") and tracks)]
+    order = []
+    for br in ("ints", "ctx"):
+        if ("cat", br) not in masks:
+            continue
+        order += [("l1", br, s) for s in slots] + [("cat", br)]
+    if ("gate",) in masks:
+        order.append(("gate",))
+    return order
+
+
+def replay_dropout(model, masks, p, modality="m", tracks=True):
+    """Put the reference model in train mode with its dropout modules replaced by DropoutReplay over
+    `masks` (oracle key -> 0/1 tensor).  Returns the queue (empty after one forward)."""
+    queue = [masks[k] for k in mask_order(masks, modality, tracks)]
+    model.train()
+    model.dropout = DropoutReplay(p, queue)
+    if hasattr(model, "gates_ints"):
+        model.gates_ints.dropout = DropoutReplay(p, queue)
+    return queue
+
+
+def random_masks(kind, rows, S, J, gate_dim, p, gen, ctx=True, gates=True, modality="m", tracks=True):
+    """Random 0/1 dropout masks in the layout of oracle/model.py's `masks` dict.  rows = encoder rows of
+    the ints branch (B, or B*T for the track models); context masks are [rows, S, J]."""
+    slots = [s for s in ("txt", "vis", "tracks1", "tracks2")
+             if (s == "txt" and modality in ("m", "t")) or (s == "vis" and modality in ("m", "v"))
+             or (s.startswith("tracks") and tracks)]
+    width = sum(J if s in ("txt", "vis") else J // 2 for s in slots)
+
+    def draw(*shape):
+        return torch.rand(*shape, generator=gen) >= p
+    masks = {("l1", "ints", s): draw(rows, J) for s in slots}
+    masks[("cat", "ints")] = draw(rows, width)
+    if ctx and kind != "modalities":
+        for s in slots:
+            masks[("l1", "ctx", s)] = draw(rows, S, J)
+        masks[("cat", "ctx")] = draw(rows, width)
+        if gates:
+            masks[("gate",)] = draw(rows, gate_dim)
+    return masks
+
+
 def run_loss(loss, output, batch):
     """Call a reference loss under torch-1.1 mask semantics."""
     with torch11_masks():

@@ -4,8 +4,11 @@
 
 For each preset / loss variant a small random model of the reference (reduced dims so the fixtures
 stay small) is built with the reference's own create_model, run forward + loss + backward on a
-random dense batch in eval mode, and inputs, parameters, outputs, loss, the in-place masked logits
-and all parameter gradients are stored.  tests/test_oracle_golden.py checks oracle/ against them
+random dense batch, and inputs, parameters, outputs, loss, the in-place masked logits and all
+parameter gradients are stored.  Twelve cases run in eval mode; four more (`*_train.npz`, one per
+preset) run the reference in TRAIN mode with its nn.Dropout modules replaced by a replayer
+(oracle/reference_shim.py:DropoutReplay) over random 0/1 masks that are stored with the case, which
+pins the dropout sites of the restatement.  tests/test_oracle_golden.py checks oracle/ against them
 everywhere (the GPU box has no /root/reference).
 """
 import os
@@ -29,6 +32,9 @@ CASES = [
     ("modalities", dict(tracks=False)), ("int_rels", {}), ("int_ch", {}), ("int_ch", dict(tr_correct=True)),
     ("int_ch", dict(tr_max_neg=True)), ("int_rel_ch", {}), ("int_rel_ch", dict(tr_correct=True)),
     ("int_rel_ch", dict(tr_max_neg=True)), ("int_rel_ch", dict(tr_correct=True, tr_max_neg=True)),
+    # train mode (dropout masks replayed): one per preset
+    ("modalities", dict(train=True)), ("int_rels", dict(train=True)), ("int_ch", dict(train=True)),
+    ("int_rel_ch", dict(train=True)),
 ]
 
 
@@ -78,11 +84,23 @@ def main():
             setattr(opt, k, v)
         opt.mlp_dim = D
         opt.modality, opt.tracks = "m", True
+        over = dict(over)
+        train = bool(over.pop("train", False))
         model, loss = rs.create_model(preset, C, R, seed=idx, **over)
         model.eval()
         batch = make_batch(preset, rng)
         inp = {k: v.clone() for k, v in batch.items()}
+        masks = None
+        if train:
+            kind = {"modalities": "modalities", "int_rels": "midfusion"}.get(preset, "maxtracks")
+            ctx = preset in ("int_rels", "int_rel_ch")
+            rows = B * T if kind == "maxtracks" else B
+            masks = rs.random_masks(kind, rows, S, DIMS["joint_dim"], DIMS["joint_dim"] * DIMS["mid_m_ints"], opt.dropout,
+                                    torch.Generator().manual_seed(1000 + idx), ctx=ctx, gates=ctx)
+            queue = rs.replay_dropout(model, masks, opt.dropout)
         out = model(batch)                     # MaxTracks reshapes batch['features'] in place
+        if train:
+            assert not queue
         lv = rs.run_loss(loss, out, batch)     # track losses overwrite out[...] with -inf in place
         lv.backward()
         rec = {"loss": np.float64(lv.item())}
@@ -95,6 +113,11 @@ def main():
         for k, v in out.items():
             if v is not None:
                 rec["out_" + k] = v.detach().numpy()
+        if train:
+            over["train"] = True
+            rec["dropout_p"] = np.float64(opt.dropout)
+            for k, m in masks.items():
+                rec["mask_" + "/".join(k)] = m.numpy()
         rec["meta"] = np.array([preset, repr(sorted(over.items()))])
         name = "%s%s.npz" % (preset, "".join("_" + (k if over[k] is True else "%s-%s" % (k, over[k])) for k in sorted(over)))
         np.savez_compressed(os.path.join(HERE, name), **rec)

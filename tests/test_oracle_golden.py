@@ -18,7 +18,7 @@ C, R = 11, 5
 
 
 def test_golden_files_present():
-    assert len(GOLDEN) == 12
+    assert len(GOLDEN) == 16          # 12 eval-mode cases + one train-mode (replayed dropout masks) case per preset
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -33,16 +33,21 @@ def test_oracle_reproduces_reference(path):
     ctx = preset in ("int_rels", "int_rel_ch")
     cfg = om.default_cfg(ctx=int(ctx), gates=int(ctx), modality=over.get("modality", "m"),
                          tracks=over.get("tracks", True), **DIMS)
+    masks = None
+    if over.get("train"):                      # the dropout masks the reference replayed (make_golden.py)
+        cfg.dropout = float(z["dropout_p"])
+        masks = {tuple(k[5:].split("/")): torch.from_numpy(z[k]) for k in z.files if k.startswith("mask_")}
+        assert ("cat", "ints") in masks
     masked = {}
     if kind == "modalities":
-        o = om.modalities_forward(sd, feats, cfg)
+        o = om.modalities_forward(sd, feats, cfg, masks)
         l = ol.max_margin_ce(o["inters"], inp["labels"], inp["multilab_weights"].float(), 0.101)
     elif kind == "midfusion":
-        o = om.midfusion_forward(sd, feats, inp["rels_mask"], cfg)
+        o = om.midfusion_forward(sd, feats, inp["rels_mask"], cfg, masks)
         l = ol.multitask_max_margin(o["inters"], o["rels"], inp["labels"], inp["rels_label"],
                                     inp["multilab_weights"].float(), 0.101, 1.0, R)
     else:
-        o = om.maxtracks_forward(sd, feats, inp.get("rels_mask"), cfg)
+        o = om.maxtracks_forward(sd, feats, inp.get("rels_mask"), cfg, masks)
         if ctx:
             l, ts, xi, xr = ol.margin_track_rels(o["inters"], o["rels"], inp["labels"], inp["rels_label"],
                                                  inp["mem_mask"].float(), inp["multilab_weights"].float(),

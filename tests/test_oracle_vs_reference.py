@@ -15,10 +15,15 @@ def _rel(a, b):
     return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))
 
 
+@pytest.mark.parametrize("train", [False, True], ids=["eval", "train"])
 @pytest.mark.parametrize("preset,over", [("int_rel_ch", {}), ("int_rel_ch", dict(tr_correct=True)),
                                          ("int_rel_ch", dict(tr_max_neg=True)), ("int_ch", {}),
                                          ("int_rels", {}), ("modalities", {})])
-def test_full_size_forward_loss_backward(preset, over):
+def test_full_size_forward_loss_backward(preset, over, train):
+    """eval: dropout off on both sides.  train: the UNMODIFIED reference forward runs in train mode with
+    its nn.Dropout modules (mlp/model.py:52, 347) replaced by a replayer that applies, in the reference's
+    call order, the very masks the oracle receives by key — this pins the oracle's dropout sites, their
+    order and the relu(dropout(.)) / dropout(tanh(.)) / dropout(relu(.)) placements (:62, 88, 353)."""
     from lirec_b200.mixed_utils import synthetic
     from oracle import losses as ol, model as om
     B = 3
@@ -26,6 +31,14 @@ def test_full_size_forward_loss_backward(preset, over):
     dense = pb.to_dense(np.float64)
     model, loss = rs.create_model(preset, 101, 15, seed=1, **over)
     model.eval()
+    masks = None
+    if train:
+        kind0 = synthetic.PRESETS[preset]["kind"]
+        ctx0 = preset in ("int_rels", "int_rel_ch")
+        rows = B * dense["features"].shape[1] if kind0 == "maxtracks" else B
+        masks = rs.random_masks(kind0, rows, 18, 512, 3072, 0.3, torch.Generator().manual_seed(77), ctx=ctx0,
+                                gates=ctx0)
+        queue = rs.replay_dropout(model, masks, 0.3)
     batch = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in dense.items()}
     kind = synthetic.PRESETS[preset]["kind"]
     if kind == "modalities":
@@ -37,27 +50,29 @@ def test_full_size_forward_loss_backward(preset, over):
         batch["labels"] = batch["labels"].reshape(B, 1, 1).expand(B, S1, 1).contiguous()
         batch["rels_label"] = batch["rels_label"].reshape(B)
     out = model(batch)
+    if train:
+        assert not queue, "the reference forward consumed %d masks fewer than the oracle has sites" % len(queue)
     lv = rs.run_loss(loss, out, batch)
     lv.backward()
 
     sd = {k: v.detach().clone().double().requires_grad_(True) for k, v in model.state_dict().items()}
     ctx = preset in ("int_rels", "int_rel_ch")
-    cfg = om.default_cfg(ctx=int(ctx), gates=int(ctx))
+    cfg = om.default_cfg(ctx=int(ctx), gates=int(ctx), dropout=0.3)
     f = dense["features"]
     if kind == "modalities":
-        o = om.modalities_forward(sd, f.reshape(B, 1, -1), cfg)
+        o = om.modalities_forward(sd, f.reshape(B, 1, -1), cfg, masks)
         l = ol.max_margin_ce(o["inters"], dense["labels"], dense["multilab_weights"], 0.101)
     elif kind == "midfusion":
-        o = om.midfusion_forward(sd, f.reshape(B, -1, f.shape[-1]), dense["rels_mask"].reshape(B, -1, 1), cfg)
+        o = om.midfusion_forward(sd, f.reshape(B, -1, f.shape[-1]), dense["rels_mask"].reshape(B, -1, 1), cfg, masks)
         l = ol.multitask_max_margin(o["inters"], o["rels"], dense["labels"].reshape(B, 1, 1),
                                     dense["rels_label"].reshape(B), dense["multilab_weights"], 0.101, 1.0, 15)
     elif ctx:
-        o = om.maxtracks_forward(sd, f, dense["rels_mask"], cfg)
+        o = om.maxtracks_forward(sd, f, dense["rels_mask"], cfg, masks)
         l = ol.margin_track_rels(o["inters"], o["rels"], dense["labels"], dense["rels_label"], dense["mem_mask"],
                                  dense["multilab_weights"], dense["gt_tracks"], 0.101, 1.0, 15,
                                  tr_correct=bool(over.get("tr_correct")), max_neg=bool(over.get("tr_max_neg")))[0]
     else:
-        o = om.maxtracks_forward(sd, f, None, cfg)
+        o = om.maxtracks_forward(sd, f, None, cfg, masks)
         l = ol.margin_loss(o["inters"], dense["labels"], dense["mem_mask"], dense["multilab_weights"],
                            dense["gt_tracks"], 0.101)[0]
     l.backward()

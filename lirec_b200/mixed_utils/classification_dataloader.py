@@ -92,25 +92,52 @@ def collate_packed(records):
     return synthetic.pack_clips(records)
 
 
-def packed_loader(dataset, batch_size, shuffle, num_workers=0, device="cuda", rank=0, world=1, drop_last=False,
-                  seed=0):
-    """Iterate device-resident PackedBatches with one-batch-ahead async H2D prefetch.
+class EmptyShard:
+    """A rank's share of a global batch that has fewer clips than ranks (the last batch of an epoch, e.g. 37
+    clips, batch 8, 8 ranks: 5 clips left).  The rank has no rows to compute on but MUST still take part in the
+    step's collectives — the loops zero its gradient and call the exchange with local_clips = 0 — otherwise
+    the other ranks' gradient reduction pairs up with this rank's NEXT collective (hang or corruption)."""
+    B = 0
+    device = None
 
-    Data parallel: every rank iterates the same shuffled order and takes its contiguous share of each
-    global batch (lirec_b200/dp.py:shard_range), so the global batch equals the single-GPU one."""
+    def __init__(self, global_clips):
+        self.global_clips = int(global_clips)
+        self.host = self
+
+    def pin(self):
+        return self
+
+    def record_stream(self, stream):
+        return self
+
+
+def plan_batches(n, batch_size, order, rank, world, drop_last=False):
+    """[(this rank's clip indices, global batch size)] for one epoch.  EVERY rank gets one entry per global
+    batch — an empty index list when the global batch is smaller than the world — so all ranks take the same
+    number of steps and their collectives stay paired."""
     from lirec_b200 import dp
-    g = torch.Generator()
-    g.manual_seed(int(seed) * 1000003 + int(getattr(dataset, "epoch", 0)))
-    n = len(dataset)
-    order = torch.randperm(n, generator=g).tolist() if shuffle else list(range(n))
     batches = []
     for s in range(0, n, batch_size):
         idx = order[s:s + batch_size]
         if drop_last and len(idx) < batch_size:
             break
         a, b = dp.shard_range(len(idx), rank, world)
-        if b > a:
-            batches.append((idx[a:b], len(idx)))
+        batches.append((idx[a:b], len(idx)))
+    return batches
+
+
+def packed_loader(dataset, batch_size, shuffle, num_workers=0, device="cuda", rank=0, world=1, drop_last=False,
+                  seed=0):
+    """Iterate device-resident PackedBatches with one-batch-ahead async H2D prefetch.
+
+    Data parallel: every rank iterates the same shuffled order and takes its contiguous share of each
+    global batch (lirec_b200/dp.py:shard_range), so the global batch equals the single-GPU one.  A rank whose
+    share is empty receives an `EmptyShard` for that step (see there)."""
+    g = torch.Generator()
+    g.manual_seed(int(seed) * 1000003 + int(getattr(dataset, "epoch", 0)))
+    n = len(dataset)
+    order = torch.randperm(n, generator=g).tolist() if shuffle else list(range(n))
+    batches = plan_batches(n, batch_size, order, rank, world, drop_last)
     if int(num_workers) > 0 and hasattr(dataset, "warm_records"):
         dataset.warm_records()              # workers fork with the record cache already built
     loader = torch.utils.data.DataLoader(_IndexView(dataset, batches), batch_size=None, shuffle=False,
@@ -124,18 +151,29 @@ def packed_loader(dataset, batch_size, shuffle, num_workers=0, device="cuda", ra
         dataset._resident = banks
         copy_stream.wait_stream(torch.cuda.current_stream())
     for host_pb in loader:
+        if isinstance(host_pb, EmptyShard):
+            dev_pb, ev = host_pb, None
+            if pending is not None:
+                prev, pev = pending
+                if pev is not None:
+                    torch.cuda.current_stream().wait_event(pev)
+                yield prev.record_stream(torch.cuda.current_stream())
+            pending = (dev_pb, ev)
+            continue
         with torch.cuda.stream(copy_stream):
             dev_pb = banks.stage(host_pb) if banks is not None else host_pb.pin().to_device(device, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         if pending is not None:
             prev, pev = pending
-            torch.cuda.current_stream().wait_event(pev)
+            if pev is not None:
+                torch.cuda.current_stream().wait_event(pev)
             yield prev.record_stream(torch.cuda.current_stream())
         pending = (dev_pb, ev)
     if pending is not None:
         prev, pev = pending
-        torch.cuda.current_stream().wait_event(pev)
+        if pev is not None:
+            torch.cuda.current_stream().wait_event(pev)
         yield prev.record_stream(torch.cuda.current_stream())
 
 
@@ -150,6 +188,8 @@ class _IndexView(Dataset):
 
     def __getitem__(self, i):
         idx, global_size = self.batches[i]
+        if not idx:
+            return EmptyShard(global_size)
         pb = self.dataset.collate([self.dataset[j] for j in idx])
         pb.global_clips = global_size
         return pb

@@ -342,9 +342,15 @@ class _HotPath(nn.Module):
                 x["packed"] = pb
         return pb
 
+    def set_rank(self, rank):
+        """Data parallel: mix the rank into the dropout seeds, so that row i of rank 0's shard and row i of rank
+        1's shard do not share their masks (the masks are keyed by local row position)."""
+        self._seed_rank = int(rank)
+
     def next_seed(self):
         self._step += 1
-        return (int(opt.seed) * 0x9E3779B1 + self._step * 0x85EBCA6B) & 0xFFFFFFFF
+        return (int(opt.seed) * 0x9E3779B1 + self._step * 0x85EBCA6B +
+                getattr(self, "_seed_rank", 0) * 0xC2B2AE3D) & 0xFFFFFFFF
 
     def forward(self, x, seed=None):
         self._sync_flat()
@@ -448,6 +454,38 @@ class _FusedLoss(nn.Module):
         return _LossFn.apply(terms, tuple(grads), *logits)
 
 
+def _rel_term(loss_mod, pb, n_sel, run):
+    """The relationship term of the multi-task losses: the mean over the rows whose label is not None
+    (reference mlp/model.py:404-418, 369-377).  `run(scale)` launches the fused kernel with the given row
+    scale and returns (terms, d_rels).  Single process: scale = 1 / n_sel.  Data parallel (the training loop
+    sets `loss_mod._dp_world`): the reference's mean runs over the non-None rows of the GLOBAL batch, while the
+    gradient exchange weights rank r by B_r / B — so the rank's term is computed unscaled and multiplied, on
+    the device, by (B / B_r) / sum_r n_sel_r (one 1-element all_reduce, no host sync); a rank without any
+    labelled row still takes part in that all_reduce."""
+    world = int(getattr(loss_mod, "_dp_world", 1) or 1)
+    if world <= 1:
+        return run(1.0 / n_sel) if n_sel else (None, None)
+    import torch.distributed as dist
+    dev = pb.device
+    cnt = torch.full((1,), float(n_sel), dtype=torch.float32, device=dev)
+    dist.all_reduce(cnt)
+    b_glob = float(getattr(pb.host, "global_clips", None) or pb.B * world)
+    scale = torch.where(cnt > 0, (b_glob / float(pb.B)) / cnt.clamp(min=1.0), torch.zeros_like(cnt))
+    if not n_sel:
+        return None, None
+    t, d = run(1.0)
+    return t * scale, d * scale
+
+
+def dp_empty_shard_collectives(loss_mod, device):
+    """The collectives a loss would have issued on a rank that holds an EmptyShard this step."""
+    if int(getattr(loss_mod, "_dp_world", 1) or 1) > 1 and isinstance(loss_mod, (MultiTaskMaxMargin,
+                                                                                 MultiTaskCrossEntropyLoss)):
+        if isinstance(loss_mod, MultiTaskCrossEntropyLoss) or opt.ctx == 1:
+            import torch.distributed as dist
+            dist.all_reduce(torch.zeros(1, dtype=torch.float32, device=device))
+
+
 class MaxMarginCrossEntropyLoss(_FusedLoss):
     """Reference: mlp/model.py:422-441."""
 
@@ -482,15 +520,21 @@ class MultiTaskMaxMargin(_FusedLoss):
             host = pb.host if pb.device is not None else pb
             lab = host["rels_label"]
             n_sel = int((lab != self.n_rels).sum())
-            if n_sel:
+
+            def run(scale):
                 sel = pb["rels_label"].clone()
                 sel[sel == self.n_rels] = -1                     # rows labelled None are skipped (model.py:406)
-                t, d_r = ops.loss_rowmargin(lr, sel, None, self.m, 1.0 / n_sel)
+                return ops.loss_rowmargin(lr, sel, None, self.m, scale)
+            t, d_r = _rel_term(self, pb, n_sel, run)
+            if t is not None:
                 terms.append(t)
         return torch.cat(terms), d_i, d_r
 
 
 class _TrackLoss(_FusedLoss):
+    def set_rank(self, rank):
+        self._seed_rank = int(rank)            # tr_cat_distr draws differ per data-parallel rank
+
     def _run(self, x, args, n_rels, lymbda):
         assert opt.tr_maximize
         assert not (opt.tr_cat_distr and opt.tr_correct)                 # model.py:469, 539
@@ -501,7 +545,8 @@ class _TrackLoss(_FusedLoss):
             li, lr, pb["cand_off"], pb["labels"], pb["rels_label"] if n_rels else None, pb["gt_tracks"],
             pb.multilab, self.m, lymbda, n_rels, tr_correct=opt.tr_correct,
             max_neg=bool(opt.tr_max_neg and opt.tr_sum_max_flag), max_slots=pb.n_slots,
-            cat_distr=bool(opt.tr_cat_distr), seed=(int(opt.seed) * 0x9E3779B1 + self._draws * 0xC2B2AE35))
+            cat_distr=bool(opt.tr_cat_distr),
+            seed=(int(opt.seed) * 0x9E3779B1 + self._draws * 0xC2B2AE35 + getattr(self, "_seed_rank", 0) * 0x27D4EB2F))
         self.last_assignment = assign
         return terms, d_i, (d_r if n_rels else None)
 
@@ -553,10 +598,13 @@ class MultiTaskCrossEntropyLoss(_FusedLoss):
         if x.ragged_rels is not None:
             lab = host["rels_label"]
             n_sel = int((lab != self.n_rels).sum())
-            if n_sel:
+
+            def run(scale):
                 sel = pb["rels_label"].clone()
                 sel[sel == self.n_rels] = -1                     # rows labelled None are skipped (model.py:369)
-                t, d_r = ops.loss_ce(x.ragged_rels, sel, None, 1.0 / n_sel)
+                return ops.loss_ce(x.ragged_rels, sel, None, scale)
+            t, d_r = _rel_term(self, pb, n_sel, run)
+            if t is not None:
                 terms.append(t)
         return torch.cat(terms), d_i, d_r
 

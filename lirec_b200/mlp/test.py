@@ -51,6 +51,8 @@ def testing(test_dataset, model, loss, total_iter=1, mode="val", train_start_tim
                                 device=dev, rank=rank, world=world):
             if getattr(pb.host, "global_clips", pb.B) == 1:     # reference skips batches of one (:38-39)
                 continue
+            if pb.B == 0:                                        # EmptyShard: no per-batch collective in evaluation
+                continue
             out = model(pb)
             loss_sum += loss(out, {}) * pb.B
             n_batches += 1

@@ -15,7 +15,7 @@ import torch
 
 from lirec_b200 import dp
 from lirec_b200.mixed_utils.classification_dataloader import packed_loader
-from lirec_b200.mlp.model import _FusedLoss, _HotPath
+from lirec_b200.mlp.model import _FusedLoss, _HotPath, dp_empty_shard_collectives
 from lirec_b200.mlp.model import train_step as native_train_step
 from lirec_b200.mlp.test import testing
 from lirec_b200.utils.arg_pars import opt
@@ -29,6 +29,17 @@ def train_step(model, loss, optimizer, pb, world=1, fused=None):
     With lirec_b200's own model and loss the forward, loss and backward run as three native calls
     without the autograd engine (`mlp.model.train_step`, `--native_step 1`, the default); any other
     combination takes the reference's four-call sequence (mlp/train.py:57-63)."""
+    if pb.B == 0:
+        # EmptyShard: this rank has no clip of a global batch smaller than the world; it contributes a zero
+        # gradient with weight 0 but takes part in the exchange, so every rank runs the same collectives
+        model._sync_flat()
+        model._flat_grad.zero_()
+        loss._dp_world = world
+        dp_empty_shard_collectives(loss, model._flat.device)
+        loss._dp_world = 1
+        dp.reduce_and_step(model, optimizer, fused, 0, pb.global_clips)
+        return model._flat_grad.new_zeros(())
+    loss._dp_world = world                       # multi-task losses normalise their relationship term globally
     if int(getattr(opt, "native_step", 1)) and isinstance(model, _HotPath) and isinstance(loss, _FusedLoss):
         loss_values = native_train_step(model, loss, pb)
     else:
@@ -40,6 +51,7 @@ def train_step(model, loss, optimizer, pb, world=1, fused=None):
     if world > 1:
         local = pb.B
         global_clips = getattr(pb.host, "global_clips", None) if getattr(pb, "host", None) is not None else None
+    loss._dp_world = 1                           # evaluation (mlp/test.py) runs the losses without collectives
     dp.reduce_and_step(model, optimizer, fused, local, global_clips)
     return loss_values
 
@@ -53,6 +65,9 @@ def training(train_dataset, **kwargs):
         rank, world, _ = dp.init_from_env()
         model._sync_flat()
         dp.broadcast_params(model._flat)
+        model.set_rank(rank)                               # dropout / sampled-assignment streams differ per rank
+        if hasattr(loss, "set_rank"):
+            loss.set_rank(rank)
         if int(getattr(opt, "dp_switch_reduce", 1)):
             fused = dp.SwitchReduceAdam.attach(model, optimizer)     # None without NVSwitch multicast / FlatAdam
     batch_time, data_time, losses = Averaging(), Averaging(), Averaging()
@@ -78,7 +93,7 @@ def training(train_dataset, **kwargs):
                 continue
             loss_values = train_step(model, loss, optimizer, pb, world, fused)
             counter += pb.B
-            if i % 10 == 0:
+            if i % 10 == 0 and pb.B:
                 losses.update(loss_values.item(), pb.B)      # device->host sync only here
             batch_time.update(time.time() - end)
             end = time.time()
@@ -95,10 +110,18 @@ def training(train_dataset, **kwargs):
                 val_dataset = kwargs.get("val_dataset", kwargs.get("test_dataset"))
                 check_val = testing(val_dataset, model, loss, total_iter=epoch, train_start_time=train_start_time,
                                     mode="val")
-                if rank == 0 and model_saver_val.check(check_val):
-                    save_dict = {"epoch": epoch, "state_dict": copy.deepcopy(model.state_dict()),
-                                 "optimizer": copy.deepcopy(optimizer.state_dict().copy())}
+                # every rank keeps the same book (the metrics are reduced over ranks), rank 0 alone the payloads
+                model_saver_val_hit = model_saver_val.check(check_val)
+                if model_saver_val_hit:
+                    save_dict = None
+                    if rank == 0:
+                        save_dict = {"epoch": epoch, "state_dict": copy.deepcopy(model.state_dict()),
+                                     "optimizer": copy.deepcopy(optimizer.state_dict().copy())}
                     model_saver_val.update(check_val, save_dict, epoch)
+                if model_saver_val_hit and kwargs.get("test_dataset") is not None and \
+                        kwargs.get("test_dataset") is not val_dataset:
+                    testing(kwargs["test_dataset"], model, loss, total_iter=epoch,     # reference :91-92
+                            train_start_time=train_start_time, mode="test")
             print(opt.log_prefix)
         if opt.save_model and opt.save_model_often and epoch % 30 == 0 and rank == 0:
             model_saver_val.save()

@@ -9,6 +9,17 @@ import lirec_b200.mlp.test
 import lirec_b200.mlp.train
 
 
+def released_checkpoint(path):
+    """The reference's entry points set `opt.resume = True` and point `opt.resume_str` at the released
+    checkpoint (resume/int_rel_ch.py:92, 117-121): they EVALUATE it.  Same here, except that an explicit
+    `--resume_str` wins over the default path and `--scratch 1` (ours) turns the script into a training run
+    from random init — the released checkpoints are not available offline."""
+    if not opt.resume_str:
+        opt.resume_str = path
+    if int(getattr(opt, "scratch", 0)):
+        opt.resume = False
+
+
 def catch_inner():
     train_dataset = MixedFeaturesDataset(mode="train")
     train_dataset.cache()

@@ -1,10 +1,11 @@
 """Entry point: interaction + character-pair detection with the weakly supervised track-assignment
 loss (reference: resume/int_ch.py:77-117)."""
-from lirec_b200.resume._common import pipeline
+from lirec_b200.resume._common import pipeline, released_checkpoint
 from lirec_b200.utils.arg_pars import opt
 
 
 def resume_max_tracks():
+    opt.resume = True
     opt.test = True
     opt.visdom = False
     opt.tr_maximize = True
@@ -19,7 +20,7 @@ def resume_max_tracks():
     opt.inter_class = "m" if opt.sanity_check else "all"
     opt.log_prefix = ""
     name = "gt_int_ch_sum_max" if opt.tr_correct else "weak_int_ch_sum_max"
-    opt.resume_str = opt.data_root + "/models_release/%s.pth.tar" % name
+    released_checkpoint(opt.data_root + "/models_release/%s.pth.tar" % name)
     return pipeline("")
 
 

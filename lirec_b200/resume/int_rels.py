@@ -1,9 +1,10 @@
 """Entry point: multi-task interaction + relationship model (reference: resume/int_rels.py:88-115)."""
-from lirec_b200.resume._common import pipeline
+from lirec_b200.resume._common import pipeline, released_checkpoint
 from lirec_b200.utils.arg_pars import opt
 
 
 def resume_ints_rels():
+    opt.resume = True
     opt.test = True
     opt.feature_type = "m"
     opt.tracks = True
@@ -18,7 +19,7 @@ def resume_ints_rels():
     opt.lymbda = 1
     opt.inter_class = "m" if opt.sanity_check else "all"
     opt.log_prefix = ""
-    opt.resume_str = opt.data_root + "/models_release/int_rel.pth.tar"
+    released_checkpoint(opt.data_root + "/models_release/int_rel.pth.tar")
     return pipeline("")
 
 

@@ -1,9 +1,10 @@
 """Entry point: multimodal interaction model (reference: resume/modalties.py:79-100 flag preset)."""
-from lirec_b200.resume._common import pipeline
+from lirec_b200.resume._common import pipeline, released_checkpoint
 from lirec_b200.utils.arg_pars import opt
 
 
 def resume_modalities():
+    opt.resume = True
     opt.test = True
     opt.mod_check = True
     opt.ints = 1
@@ -13,7 +14,7 @@ def resume_modalities():
     opt.tr_maximize = False
     opt.inter_class = "m" if opt.sanity_check else "all"
     opt.log_prefix = ""
-    opt.resume_str = opt.data_root + "/models_release/mod_all.pth.tar"
+    released_checkpoint(opt.data_root + "/models_release/mod_all.pth.tar")
     return pipeline("")
 
 

@@ -100,6 +100,8 @@ _FLAGS = [
     ("--model_name", dict(default="")),
     ("--sanity_check", dict(default=False)),
     # ---- B200: flags added by this implementation (defaults keep reference behaviour) ----
+    ("--scratch", dict(default=0, type=int, help="1: the resume/*.py entry points train from random init instead of "
+                                                 "evaluating the released checkpoint (reference behaviour)")),
     ("--dp", dict(default=0, type=int, help="1: data-parallel over clips, NCCL gradient allreduce")),
     ("--dp_switch_reduce", dict(default=1, type=int, help="1: with --dp and --fused_adam, reduce gradients inside the "
                                                           "NVSwitch fused with Adam (falls back to NCCL without multicast)")),

@@ -46,6 +46,21 @@ def _drop(x, masks, key, p):
     return x * masks[key].to(x.dtype) / (1.0 - p)
 
 
+def _relu(cfg, name, z, dropped):
+    """relu(dropped) where dropped = dropout(z) (or z itself).  With cfg.relu_gate = {name: bool tensor}
+    the on/off decision of every unit whose pre-activation lies within cfg.relu_edge of zero is TAKEN FROM
+    THAT TENSOR instead of from the sign of z: a unit that close to zero is a knife-edge on which an fp32 and
+    an fp64 evaluation of the same formula may legitimately land on different sides (its activation is ~0
+    either way; only d relu/dz flips), so the large-batch parity tests replay the decisions of the path under
+    test there.  Everywhere else — and without cfg.relu_gate — this is torch.relu."""
+    gates = getattr(cfg, "relu_gate", None)
+    if not gates or name not in gates:
+        return torch.relu(dropped)
+    edge = z.detach().abs() < getattr(cfg, "relu_edge", 1e-5)
+    g = torch.where(edge, gates[name].reshape(z.shape), z.detach() > 0)
+    return dropped * g.to(dropped.dtype)
+
+
 def _tape(cfg, name, t):
     """Optional white-box tape (cfg.tape = {}) used by the stage-level parity tests."""
     tape = getattr(cfg, "tape", None)
@@ -64,14 +79,15 @@ def encode(sd, branch, x, cfg, masks, slots=SLOTS):
     outs = []
     for slot in slots:
         h = _tape(cfg, "z1_%s_%s" % (slot, branch), _lin(sd, "%s_%s" % (slot, branch), parts[slot]))
-        h = torch.relu(_drop(h, masks, ("l1", branch, slot), cfg.dropout))  # relu(dropout(.)): model.py:62
+        h = _relu(cfg, "z1_%s_%s" % (slot, branch), h, _drop(h, masks, ("l1", branch, slot), cfg.dropout))  # relu(dropout(.)): model.py:62
         outs.append(_lin(sd, "%s_%s" % (SECOND[slot], branch), h))
     return outs
 
 
 def gating_unit(sd, feat_ints, feat_ctx, cfg, masks):
     z = _tape(cfg, "gate_in", torch.cat((feat_ctx, feat_ints), dim=-1))   # (rels, inters) order: model.py:352
-    z = torch.relu(_tape(cfg, "pre_gate", _lin(sd, "gates_ints.fc_out", z)))
+    pre = _tape(cfg, "pre_gate", _lin(sd, "gates_ints.fc_out", z))
+    z = _relu(cfg, "pre_gate", pre, pre)
     return _drop(z, masks, ("gate",), cfg.dropout)             # dropout(relu(.)): model.py:353
 
 

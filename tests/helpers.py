@@ -33,7 +33,7 @@ def make_model(n_classes=N_CLASSES, n_rels=N_RELS, seed=0):
         return M.create_model(n_classes, n_rels=n_rels)
 
 
-def oracle_forward_loss(pb, sd, preset, opt, masks, tape=None):
+def oracle_forward_loss(pb, sd, preset, opt, masks, tape=None, relu_gate=None):
     """Dense fp64 oracle forward + loss for host PackedBatch `pb`. Returns (outputs, loss, extra)."""
     from lirec_b200.mixed_utils import synthetic
     from oracle import losses as ol, model as om
@@ -44,6 +44,8 @@ def oracle_forward_loss(pb, sd, preset, opt, masks, tape=None):
         cfg.modality, cfg.tracks = opt.modality, bool(opt.tracks)
     if tape is not None:
         cfg.tape = tape
+    if relu_gate is not None:
+        cfg.relu_gate = relu_gate
     B = pb.B
     f = dense["features"]
     extra = {"dense": dense}
@@ -73,3 +75,66 @@ def oracle_forward_loss(pb, sd, preset, opt, masks, tape=None):
             ragged = {"inters": o["inters"][mm]}
         extra["assignment"] = ts
     return ragged, l, extra
+
+
+def kernel_relu_gates(model, pb_host, pb_dev, seed, train):
+    """White-box: the on/off decision the CUDA path takes for every ReLU unit of one step, laid out like the
+    dense oracle's pre-activations (oracle/model.py `cfg.relu_gate`).  Runs lirec_model_forward once and reads
+    the workspace: r1 (relu(L1) of the unique bank rows, fp32 — backward gates on r1 > 0, csrc/rows.cu) and
+    the gate output g2 (hi bf16 — backward gates on g2 > 0, csrc/gemm_tcgen05.cu POST_DRELU).  The oracle uses
+    these ONLY for units whose fp64 pre-activation is within 1e-5 of zero (knife-edges)."""
+    import ctypes as C
+    from lirec_b200 import _ext
+    slots = ("txt", "vis", "tracks1", "tracks2")
+    training = bool(train) and model.dropout.p > 0
+    with torch.no_grad():
+        model._sync_flat()
+        model._refresh_bf16()
+        batch_c, ws, _, _ = model._run_forward(pb_dev, training, seed if training else 0)
+    torch.cuda.synchronize()
+    offs = (C.c_int64 * 40)()
+    n = _ext.lib().lirec_model_workspace_layout(C.byref(model._cfg_c), C.byref(batch_c), offs, 40)
+    assert n >= 31
+    off = list(offs)[:n]
+    t = pb_host.tables
+    T, S, J = pb_host.n_slots, pb_host.n_ctx_slots, 512
+    B, Ni = pb_host.B, pb_host.n_cand
+    dense_row = torch.from_numpy(t["cand_clip"].astype(np.int64) * T + t["cand_slot"].astype(np.int64))
+    col = (0, 0, 1, 2)
+    gates = {}
+
+    def r1(br, s, nu):
+        o = off[br * 4 + s]
+        if o < 0:
+            return None
+        return ws[o:o + nu * J * 4].view(torch.float32).view(nu, J).cpu() > 0
+
+    cand_rows = torch.from_numpy(np.asarray(t["cand_rows"]).astype(np.int64))
+    for s, name in enumerate(slots):
+        nu = batch_c.n_clip_ints if s < 2 else batch_c.n_track_ints
+        g = r1(0, s, nu)
+        if g is None:
+            continue
+        d = torch.ones(B * T, J, dtype=torch.bool)
+        d[dense_row] = g[cand_rows[:, col[s]]]
+        gates["z1_%s_ints" % name] = d
+    if model._ctx:
+        Nx = pb_host.n_ctx_rows
+        owner = torch.from_numpy(np.asarray(t["ctx_owner"]).astype(np.int64))
+        pos = torch.arange(Nx) - torch.from_numpy(np.asarray(t["ctx_off"]).astype(np.int64))[:-1][owner]
+        ctx_rows = torch.from_numpy(np.asarray(t["ctx_rows"]).astype(np.int64))
+        for s, name in enumerate(slots):
+            nu = batch_c.n_clip if s < 2 else batch_c.n_track
+            g = r1(1, s, nu)
+            d = torch.ones(B * T, S, J, dtype=torch.bool)
+            if Nx:
+                d[dense_row[owner], pos] = g[ctx_rows[:, col[s]]]
+            gates["z1_%s_ctx" % name] = d
+    if model._gates:
+        Gd = model._gate_dim
+        o = off[27]                                          # g2: [Ni, 2 * Gd] bf16, hi | lo
+        g2 = ws[o:o + Ni * 2 * Gd * 2].view(torch.bfloat16).view(Ni, 2 * Gd)[:, :Gd].float().cpu() > 0
+        d = torch.ones(B * T, Gd, dtype=torch.bool)
+        d[dense_row] = g2
+        gates["pre_gate"] = d
+    return gates

@@ -156,3 +156,53 @@ def test_install_aliases_exposes_the_reference_module_surface(monkeypatch):
         m = importlib.import_module(mod)
         if fn is not None:
             assert callable(getattr(m, fn)), (mod, fn)
+
+
+def test_model_saver_mirrors_the_reference_store(tmp_path):
+    """per-metric folders, v<value>_ep<epoch>.pth.tar names, evicted checkpoints removed from
+    disk, already-saved ones not rewritten, `ModelSaver(n=..., path=...)` — checked against the UNMODIFIED
+    reference class when /root/reference is mounted, else against the expected listing."""
+    import os
+    from lirec_b200.utils.model_saver import ModelSaver
+    seq = [(0, 0.50, 0.10), (1, 0.40, 0.30), (2, 0.60, 0.20), (3, 0.60, 0.05), (4, 0.10, 0.40), (5, 0.70, 0.40)]
+
+    def drive(cls, root):
+        ms = cls(n=2, path=str(root))
+        listing = []
+        for epoch, a, b in seq:
+            val = {"total": a, "ints": b}
+            if ms.check(val):
+                ms.update(val, {"epoch": epoch}, epoch)
+            if epoch % 2 == 1:
+                ms.save()
+                listing.append(sorted(os.path.relpath(os.path.join(d, f), str(root))
+                                      for d, _, fs in os.walk(str(root)) for f in fs))
+        return listing
+    ours = drive(ModelSaver, tmp_path / "ours")
+    # (update() books EVERY metric of a hit, so epoch 4 — a hit on 'ints' only — also enters 'total', evicting the
+    # later of the two 0.60s; the listing below is what the unmodified reference class produces)
+    assert ours[-1] == ["ints/v0.4000_ep4.pth.tar", "ints/v0.4000_ep5.pth.tar", "total/v0.6000_ep2.pth.tar",
+                        "total/v0.7000_ep5.pth.tar"]
+    assert all(len(l) <= 4 for l in ours)
+    from oracle import reference_shim as rs
+    if rs.available():
+        rs.load_dataloader()
+        ref_cls = rs._state["modules"]["utils.model_saver"].ModelSaver if "utils.model_saver" in rs._state["modules"] else None
+        if ref_cls is None:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_ref_model_saver", os.path.join(rs.REFERENCE_ROOT, "utils", "model_saver.py"))
+            import sys
+            saved = {k: sys.modules.get(k) for k in ("utils", "utils.util_functions")}
+            sys.modules["utils"] = rs._state["modules"]["utils"]
+            sys.modules["utils.util_functions"] = rs._state["modules"]["utils.util_functions"]
+            try:
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+            finally:
+                for k, v in saved.items():
+                    if v is None:
+                        sys.modules.pop(k, None)
+                    else:
+                        sys.modules[k] = v
+            ref_cls = mod.ModelSaver
+        assert drive(ref_cls, tmp_path / "ref") == ours

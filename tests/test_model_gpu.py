@@ -84,6 +84,94 @@ def test_forward_loss_backward_parity(preset, train, opt_preset):
             assert rel_err(p.grad, sd[k].grad) < TOL, (k, rel_err(p.grad, sd[k].grad))
 
 
+@pytest.mark.parametrize("preset", ["int_rel_ch", "int_rels", "int_ch", "modalities"])
+def test_reference_batch_size_parity_train_mode(preset, opt_preset):
+    """B = 64 — the reference's batch size (utils/arg_pars.py:150) and BASELINE.md's parity point — in TRAIN
+    mode with replayed dropout masks against the dense fp64 oracle: logits, loss, track assignment and every
+    parameter gradient within 1e-3.  Nothing is forced: kernel choice per launch (CTA-pair vs single-CTA),
+    LPT tile schedules, split-K factors and the data-gradient form are whatever the library picks at ~530
+    candidate / ~1.9 k context rows.  At this size a few dozen of the ~10^7 ReLU pre-activations lie within
+    1e-5 of zero; for exactly those units the oracle replays the CUDA path's on/off decision
+    (helpers.kernel_relu_gates, oracle/model.py:_relu) instead of nudging biases as the small cases do."""
+    from helpers import kernel_relu_gates
+    from lirec_b200.mixed_utils import synthetic
+    from oracle import dropout as odrop
+    opt = opt_preset(preset)
+    model, loss_fn, _ = make_model(seed=4)
+    model.train()
+    B, step_seed = 64, 4242
+    pb = synthetic.make_batch(B, seed=64, preset=preset)
+    pbd = pb.to_device("cuda")
+    gates = kernel_relu_gates(model, pb, pbd, step_seed, True)
+    out = model(pbd, seed=step_seed)
+    lv = loss_fn(out, {})
+    lv.backward()
+    torch.cuda.synchronize()
+    sd = rounded_state_dict(model)
+    cw = model.out_ints.in_features if model.kind == "modalities" else None
+    masks = odrop.dense_masks(pb, step_seed, opt.dropout, cat_width=cw)
+    tape = {}
+    ragged, l, extra = oracle_forward_loss(pb, sd, preset, opt, masks, tape=tape, relu_gate=gates)
+    l.backward()
+    n_edge = sum(int((z.detach().abs() < EDGE).sum()) for name, z in tape.items() if name in gates)
+    print("B=64 %s: %d candidate rows, %d context rows, %d knife-edge units replayed" % (
+        preset, pb.n_cand, pb.n_ctx_rows, n_edge))
+    _check_all(model, loss_fn, out, lv, sd, ragged, l, extra)
+
+
+def test_five_step_trajectory_against_oracle_adam(opt_preset):
+    """K = 5 optimisation steps (five different batches, train mode, fused flat Adam) against the fp64 oracle
+    driven by torch.optim.Adam: per-step losses and logits within 1e-3 — the oracle re-rounds its master
+    weights to bf16 before every forward, so a stale bf16 shadow after a fused step shows at once (lr is
+    raised to 1e-3 so that every step moves most weights by more than a bf16 ulp) — and the accumulated
+    parameter update, which depends on the step counter through Adam's bias corrections, within 2 % in
+    2-norm per tensor (coordinates whose gradient is ~1e-8 of the tensor's scale take lr-sized steps of
+    either sign in BOTH implementations; they are a vanishing part of the 2-norm)."""
+    from lirec_b200.mixed_utils import synthetic
+    from oracle import dropout as odrop
+    K, lr, wd = 5, 1e-3, 1e-5
+    opt = opt_preset("int_rel_ch", fused_adam=1, lr=lr, weight_decay=wd)
+    model, loss_fn, optimizer = make_model(seed=6)
+    import lirec_b200.mlp.model as M
+    assert isinstance(optimizer, M.FlatAdam)
+    model.train()
+    p0 = {k: v.detach().clone() for k, v in model.named_parameters()}
+    master = {k: v.detach().cpu().double().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    oadam = torch.optim.Adam(list(master.values()), lr=lr, weight_decay=wd)
+    for step in range(K):
+        pb = synthetic.make_batch(6, seed=300 + step, preset="int_rel_ch")
+        pbd = pb.to_device("cuda")
+        seed = 9000 + step
+        out = model(pbd, seed=seed)
+        lv = loss_fn(out, {})
+        optimizer.zero_grad()
+        lv.backward()
+        optimizer.step()
+        # oracle: forward on the bf16-rounded master weights, gradients passed straight through to the master
+        sd = {k: (v.detach().to(torch.float32).to(torch.bfloat16) if k.endswith("weight") else v.detach()).double()
+              .requires_grad_(True) for k, v in master.items()}
+        masks = odrop.dense_masks(pb, seed, opt.dropout)
+        ragged, l, extra = oracle_forward_loss(pb, sd, "int_rel_ch", opt, masks)
+        l.backward()
+        assert rel_err(out.ragged_inters, ragged["inters"]) < TOL, step
+        assert rel_err(out.ragged_rels, ragged["rels"]) < TOL, step
+        assert abs(lv.item() - l.item()) / abs(l.item()) < TOL, step
+        oadam.zero_grad()
+        for k, v in master.items():
+            v.grad = sd[k].grad.clone()
+        oadam.step()
+    worst = 0.0
+    for k, p in model.named_parameters():
+        du, dr = (p.detach() - p0[k]).double().cpu(), master[k].detach() - p0[k].double().cpu()
+        err = float((du - dr).norm() / (dr.norm() + 1e-30))
+        worst = max(worst, err)
+        assert err < 2e-2, (k, err)
+        assert 0.5 < float(du.abs().mean() / dr.abs().mean()) < 2.0, k
+    print("5-step trajectory: worst relative 2-norm error of the accumulated update %.2e" % worst)
+    st = optimizer.state_dict()["state"]
+    assert all(float(v["step"]) == K for v in st.values())
+
+
 @pytest.mark.parametrize("flags", [dict(tr_correct=True), dict(tr_max_neg=True), dict(tr_correct=True, tr_max_neg=True)])
 def test_track_loss_variants_end_to_end(flags, opt_preset):
     opt = opt_preset("int_rel_ch", **flags)

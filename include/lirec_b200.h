@@ -165,6 +165,25 @@ int lirec_seg_reduce_gather_f32(const float* x, const int32_t* row_idx, const in
                                 int32_t nseg, int32_t dim, int32_t mode, float* out_f32,
                                 int64_t out_f32_ld, void* out_bf16, int64_t out_bf16_ld, void* stream);
 
+/* Softmax-weighted member of the same family, forward and backward — PARITY UNPINNED BY CONSTRUCTION: the
+ * reference has no softmax / attention pooling (np.max at mixed_features.py:54, 61, 105; masked mean at
+ * mlp/model.py:301-304); BASELINE.json's north_star asks for it and SURVEY.md §0.1 frames it as the third
+ * member of {max, mean, softmax-weighted} over the same offset tables.
+ *     out[s, c] = sum_{r in seg s} w[r, c] x[r, c],   w[., c] = softmax_r(beta * score[r, c])
+ * score_mode 0: score = x (scores NULL; beta -> inf is the max, beta = 0 the mean); 1: per-element tensor
+ * `scores` [total, dim]; 2: one score per row `scores` [total] (attention pooling).  An empty segment gives zeros.
+ * lse: log-normaliser the backward needs, [nseg, lse_ld] (modes 0 / 1) or [nseg] (mode 2); may be NULL in fwd.
+ * bwd writes d_x [total, dim] for every row of every segment and, if not NULL, d_scores ([total, dim] in mode 1,
+ * [total] in mode 2; in mode 0 the score path is folded into d_x).                                            */
+int lirec_seg_softmax_pool_fwd(const float* x, const float* scores, int32_t score_mode,
+                               const int32_t* seg_off, int32_t nseg, int32_t dim, float beta,
+                               float* out, int64_t out_ld, float* lse, int64_t lse_ld, void* stream);
+int lirec_seg_softmax_pool_bwd(const float* x, const float* scores, int32_t score_mode,
+                               const int32_t* seg_off, int32_t nseg, int32_t dim, float beta,
+                               const float* out, int64_t out_ld, const float* lse, int64_t lse_ld,
+                               const float* d_out, int64_t d_out_ld, float* d_x, float* d_scores,
+                               void* stream);
+
 /* ---- ragged row kernels of the modality encoder --------------------------
  * Layer-1 outputs are computed once per UNIQUE bank row (clip text, clip
  * visual, person track).  These kernels expand them to encoder rows by the
@@ -366,6 +385,14 @@ int lirec_model_backward(const lirec_model_cfg* cfg, const lirec_model_params* p
                          const lirec_batch* batch, void* workspace, size_t workspace_bytes,
                          const float* d_ints, const float* d_rels, void* stream);
 
+/* Same, and records the CUDA event `heads_event` (a cudaEvent_t; may be NULL) on `stream` as soon as the
+ * gradients of the gate and of the two heads are final in the flat gradient buffer: a data-parallel caller
+ * starts the exchange + Adam of that range (53 % of the weights) on another stream while the encoder stages of
+ * backward still run (lirec_b200/dp.py).  Autograd runs backward as one opaque call (mlp/train.py:62). */
+int lirec_model_backward_ex(const lirec_model_cfg* cfg, const lirec_model_params* params,
+                            const lirec_batch* batch, void* workspace, size_t workspace_bytes,
+                            const float* d_ints, const float* d_rels, void* stream, void* heads_event);
+
 /* White-box test aid: byte offsets of the named workspace buffers (see csrc/model.cu). */
 int lirec_model_workspace_layout(const lirec_model_cfg* cfg, const lirec_batch* batch_host,
                                  int64_t* offsets, int max_entries);
@@ -400,22 +427,20 @@ int lirec_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_
                     void* param_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int32_t step, float grad_scale, void* stream);
 
-/* ---- data parallel: gradient sum over ranks fused with the Adam step ------
- * One launch per rank per step replaces ncclAllReduce(flat gradient) + lirec_adam_flat.  `grad` is this
- * rank's flat fp32 gradient buffer in SYMMETRIC memory and `grad_multicast` the NVSwitch multicast
- * address of the same buffer (lirec_b200/dp.py obtains both from torch.distributed._symmetric_memory).
- * Each rank reduces its 1/world shard inside the switch (multimem.ld_reduce.add) and broadcasts the sum
- * (multimem.st), so `grad` holds the SUM over ranks afterwards; then Adam runs with grad * grad_scale
- * (1/world for equal shards).  flag_ptrs_dev: device array [world] of every rank's peer-mapped flag
- * buffer (>= 2*world zero-initialised uint32); sync_ws: 3 zero-initialised local uint32; epoch = 1, 2, ...
- * per call.  The reference has no counterpart (single process); optimizer semantics are
- * torch.optim.Adam's (mlp/model.py:599-601).                                                   */
-int lirec_dp_grid_size(void);
-int lirec_dp_allreduce_adam(float* param, float* grad, void* grad_multicast, float* exp_avg,
-                            float* exp_avg_sq, void* param_bf16, int64_t n, float lr, float beta1,
-                            float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
-                            int32_t rank, int32_t world, const void* flag_ptrs_dev, void* sync_ws,
-                            uint32_t epoch, void* stream);
+/* ---- data parallel: in-switch gradient exchange, bucket by bucket --------
+ * Replaces ncclAllReduce(flat gradient) of a data-parallel step (the reference is single-process, SURVEY.md
+ * §2.3; the optimizer stays torch.optim.Adam's arithmetic, mlp/model.py:599-601, through lirec_adam_flat on the
+ * same range afterwards).  `grad_multicast` is the NVSwitch multicast address of the flat fp32 gradient buffer,
+ * which lives in SYMMETRIC memory on every rank (lirec_b200/dp.py obtains both from
+ * torch.distributed._symmetric_memory).  The call enqueues on `stream`: a cross-GPU barrier, this rank's 1/world
+ * shard of floats [offset, offset + n) reduced inside the switch (multimem.ld_reduce.add) and broadcast
+ * (multimem.st), and a second barrier — afterwards every rank holds the SUM over ranks in that range.
+ * flag_ptrs_dev: device array [world] of every rank's peer-mapped, zero-initialised flag buffer of
+ * lirec_dp_flag_words(world) uint32; `channel` (0..3) selects the flag slots, so chains for different buckets may
+ * be in flight on different streams at the same time (all ranks must use the same channel for the same bucket). */
+int lirec_dp_flag_words(int32_t world);
+int lirec_dp_exchange(void* grad_multicast, int64_t offset, int64_t n, int32_t rank, int32_t world,
+                      const void* flag_ptrs_dev, int32_t channel, void* stream);
 
 #ifdef __cplusplus
 }

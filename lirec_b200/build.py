@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblirec_b200.so")
 STAMP = os.path.join(HERE, ".liblirec_b200.stamp")
-SOURCES = ["abi.cu", "gemm_tcgen05.cu", "rows.cu", "loss.cu", "model.cu", "dp.cu", "collate.cu"]
+SOURCES = ["abi.cu", "gemm_tcgen05.cu", "rows.cu", "softpool.cu", "loss.cu", "model.cu", "dp.cu", "collate.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

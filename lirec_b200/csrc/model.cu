@@ -567,8 +567,26 @@ static void push_reduction(std::vector<lirec_gemm_problem>& pr, lirec_gemm_probl
   pr.push_back(g);
 }
 
+// Sum the split-K partials collected so far into the flat gradient buffer (fixed order) and start a new list.
+static int flush_partials(SplitCtx& sc, cudaStream_t stream) {
+  if (sc.jobs.n > 0) {
+    int64_t biggest = 0;
+    for (int i = 0; i < sc.jobs.n; ++i) biggest = std::max<int64_t>(biggest, (int64_t)sc.jobs.job[i].M * sc.jobs.job[i].N);
+    dim3 grid((unsigned)((biggest + 1023) / 1024), sc.jobs.n);
+    reduce_partials_kernel<<<grid, 256, 0, stream>>>(sc.jobs);
+    LIREC_CUDA_OK(cudaGetLastError());
+    note_launch();
+    sc.jobs.n = 0;
+  }
+  return LIREC_OK;
+}
+
+// heads_event (optional): recorded on `stream` as soon as the gradients of the gate and of the two heads are
+// FINAL in the flat gradient buffer (after stage G and its split-K sums; after stage H for the models without
+// a gate) — the data-parallel exchange and the Adam pass of those parameters (53 % of all weights) can then
+// run on another stream while the encoder stages of backward are still going (lirec_b200/dp.py).
 int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lirec_batch& B, void* ws,
-             const float* d_ints, const float* d_rels, cudaStream_t stream) {
+             const float* d_ints, const float* d_rels, cudaStream_t stream, cudaEvent_t heads_event) {
   const Dims d = make_dims(cfg, B);
   const Workspace w = carve(d, ws);
   const float p = (B.training && cfg.dropout_p > 0.f) ? cfg.dropout_p : 0.f;
@@ -651,6 +669,10 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
     pr.push_back(g);
   }
   if ((rc = gemm::run_grouped(pr.data(), (int)pr.size(), stream)) != LIREC_OK) return rc;
+  if (heads_event && !d.gates) {
+    if ((rc = flush_partials(sc, stream)) != LIREC_OK) return rc;
+    LIREC_CUDA_OK(cudaEventRecord(heads_event, stream));
+  }
 
   // ---- stage G: gate wgrad/bgrad + dgrad to the two concat features --------------
   if (d.gates) {
@@ -675,6 +697,10 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
       pr.push_back(g);
     }
     if ((rc = gemm::run_grouped(pr.data(), (int)pr.size(), stream)) != LIREC_OK) return rc;
+    if (heads_event) {
+      if ((rc = flush_partials(sc, stream)) != LIREC_OK) return rc;
+      LIREC_CUDA_OK(cudaEventRecord(heads_event, stream));
+    }
   }
 
   // ---- stage L2: second-layer wgrad/bgrad + dgrad to the expanded rows ------------
@@ -752,15 +778,7 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
   if ((rc = gemm::run_grouped(pr.data(), (int)pr.size(), stream)) != LIREC_OK) return rc;
 
   // ---- sum the split-K partials into the flat gradient buffer (fixed order) -----------------------
-  if (sc.jobs.n > 0) {
-    int64_t biggest = 0;
-    for (int i = 0; i < sc.jobs.n; ++i) biggest = std::max<int64_t>(biggest, (int64_t)sc.jobs.job[i].M * sc.jobs.job[i].N);
-    dim3 grid((unsigned)((biggest + 1023) / 1024), sc.jobs.n);
-    reduce_partials_kernel<<<grid, 256, 0, stream>>>(sc.jobs);
-    LIREC_CUDA_OK(cudaGetLastError());
-    note_launch();
-  }
-  return LIREC_OK;
+  return flush_partials(sc, stream);
 }
 
 }  // namespace model
@@ -811,5 +829,15 @@ extern "C" int lirec_model_backward(const lirec_model_cfg* cfg, const lirec_mode
   LIREC_ENTER();
   int rc = model::validate(cfg, params, batch, workspace, workspace_bytes);
   if (rc != LIREC_OK) return rc;
-  return model::backward(*cfg, *params, *batch, workspace, d_ints, d_rels, static_cast<cudaStream_t>(stream));
+  return model::backward(*cfg, *params, *batch, workspace, d_ints, d_rels, static_cast<cudaStream_t>(stream), nullptr);
+}
+
+extern "C" int lirec_model_backward_ex(const lirec_model_cfg* cfg, const lirec_model_params* params,
+                                       const lirec_batch* batch, void* workspace, size_t workspace_bytes,
+                                       const float* d_ints, const float* d_rels, void* stream, void* heads_event) {
+  LIREC_ENTER();
+  int rc = model::validate(cfg, params, batch, workspace, workspace_bytes);
+  if (rc != LIREC_OK) return rc;
+  return model::backward(*cfg, *params, *batch, workspace, d_ints, d_rels, static_cast<cudaStream_t>(stream),
+                         static_cast<cudaEvent_t>(heads_event));
 }

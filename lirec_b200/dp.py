@@ -8,10 +8,10 @@ NVSwitch per step; the 1/world_size average is folded into the fused Adam kernel
 (or applied in place for torch.optim.Adam).
 
 `SwitchReduceAdam` goes one step further on NVSwitch boxes: the gradient buffer lives in symmetric
-memory mapped into a multicast object, and ONE kernel per rank (csrc/dp.cu:lirec_dp_allreduce_adam)
-reduces the gradients inside the switch (multimem.ld_reduce / multimem.st) and runs Adam — no NCCL
-call on the step's critical path.  torch.distributed._symmetric_memory only allocates and
-rendezvous-es the buffers.
+memory mapped into a multicast object and is reduced inside the switch (csrc/dp.cu:lirec_dp_exchange,
+multimem.ld_reduce / multimem.st) bucket by bucket, the gate + head bucket while backward is still
+running — no NCCL call on the step's critical path.  torch.distributed._symmetric_memory only allocates
+and rendezvous-es the buffers.
 """
 import os
 
@@ -73,20 +73,42 @@ def broadcast_params(flat_param, src=0):
 
 
 class SwitchReduceAdam:
-    """In-switch gradient reduction fused with the flat Adam step (needs NVSwitch multicast).
+    """Gradient exchange + Adam of one step as two buckets, the first overlapped with backward.
 
         fused = SwitchReduceAdam.attach(model, optimizer)      # collective; None if unsupported
         ...
-        lv.backward()
-        fused.step()                                           # instead of all_reduce + optimizer.step
-    """
+        train_step(model, loss, optimizer, pb, world, fused)   # lirec_b200/mlp/train.py drives it
 
-    def __init__(self, model, optimizer, grad, hdl, flags, flag_hdl):
+    The flat parameter buffer is laid out [ints encoder | ctx encoder | gate | out_ints | out_ctx]
+    (construction order, lirec_b200/mlp/model.py:_build).  Bucket 0 = gate + heads (53 % of the weights):
+    lirec_model_backward_ex records an event as soon as those gradients are final, ~0.6 ms before backward
+    ends at 1024 clips per GPU, and this bucket's chain — in-switch exchange (lirec_dp_exchange: barrier,
+    multimem.ld_reduce / multimem.st of this rank's shard, barrier) followed by lirec_adam_flat over the
+    bucket — runs on a high-priority side stream while the second-layer / first-layer stages of backward go
+    on.  Nothing those stages read (encoder weights, activations, the feature banks) is written by it.
+    Bucket 1 = the encoders: same chain on the main stream after backward.  The step ends with the main
+    stream waiting for the side chain.
+
+    world == 1 (`attach(..., single_gpu=True)`): no exchange, only the bucket-0 Adam pass overlapped.
+    torch.distributed._symmetric_memory only allocates and rendezvous-es the buffers."""
+
+    overlap = True
+
+    def __init__(self, model, optimizer, grad=None, hdl=None, flags=None, flag_hdl=None):
         self.model, self.optimizer = model, optimizer
         self.grad, self.hdl, self.flags, self.flag_hdl = grad, hdl, flags, flag_hdl
-        self.ws = torch.zeros(4, dtype=torch.int32, device=grad.device)
-        self.epoch = 0
-        self.rank, self.world = hdl.rank, hdl.world_size
+        self.rank, self.world = (hdl.rank, hdl.world_size) if hdl is not None else (0, 1)
+        dev = model._flat.device
+        self.side = torch.cuda.Stream(device=dev, priority=-1)
+        self.ev_heads = torch.cuda.Event()
+        self.ev_done = torch.cuda.Event()
+        self.ev_heads.record()                       # creates the cudaEvent_t the library re-records
+        # bucket boundary: the first parameter of the gate (models with a gate) or of out_ints
+        names = [n for n, _ in model.named_parameters()]
+        first = "gates_ints.fc_out.weight" if "gates_ints.fc_out.weight" in names else "out_ints.weight"
+        self.split = int(model._offsets[names.index(first)])
+        self.n = int(model._flat.numel())
+        assert self.split % 64 == 0 and self.n % 64 == 0
 
     @staticmethod
     def supported(device):
@@ -98,13 +120,17 @@ class SwitchReduceAdam:
             return False
 
     @classmethod
-    def attach(cls, model, optimizer):
+    def attach(cls, model, optimizer, single_gpu=False):
         """Move the model's flat gradient buffer into symmetric memory (collective over the world group).
-        Returns None — and leaves everything as it was — when there is a single rank or no multicast."""
+        Returns None — and leaves everything as it was — without FlatAdam, without multicast, or on a single
+        rank (unless single_gpu=True: then only the overlapped bucket-0 Adam is set up)."""
+        from lirec_b200 import _ext
         from lirec_b200.mlp.model import FlatAdam
-        if world_size() < 2 or not isinstance(optimizer, FlatAdam):
+        if not isinstance(optimizer, FlatAdam):
             return None
         model._sync_flat()
+        if world_size() < 2:
+            return cls(model, optimizer) if single_gpu else None
         dev = model._flat.device
         ok = torch.tensor([1 if cls.supported(dev) else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
@@ -115,7 +141,8 @@ class SwitchReduceAdam:
         n = model._flat.numel()
         grad = symm_mem.empty(n, dtype=torch.float32, device=dev)
         hdl = symm_mem.rendezvous(grad, group)
-        flags = symm_mem.empty(max(64, 2 * dist.get_world_size()), dtype=torch.int32, device=dev)
+        words = int(_ext.lib().lirec_dp_flag_words(dist.get_world_size()))
+        flags = symm_mem.empty(max(64, words), dtype=torch.int32, device=dev)
         flag_hdl = symm_mem.rendezvous(flags, group)
         if not hdl.multicast_ptr:
             return None
@@ -126,20 +153,57 @@ class SwitchReduceAdam:
         dist.barrier()
         return cls(model, optimizer, grad, hdl, flags, flag_hdl)
 
-    @torch.no_grad()
-    def step(self, local_clips=None, global_clips=None):
+    def detach(self):
+        """Give the model an ordinary gradient buffer again (the symmetric allocation is released with this
+        object)."""
+        torch.cuda.synchronize()
+        if self.grad is not None and self.model is not None and self.model._flat_grad is self.grad:
+            self.model.use_grad_buffer(torch.zeros_like(self.model._flat))
+        self.model._heads_event = None
+        self.model = self.optimizer = None
+
+    # ---- per-step protocol --------------------------------------------------------------------------
+    def arm(self, equal_shards=True):
+        """Before backward: ask lirec_model_backward_ex for the heads-final event (only when this step's
+        exchange needs no host-side re-weighting)."""
+        self._armed = bool(self.overlap and equal_shards and 0 < self.split < self.n)
+        self.model._heads_event = self.ev_heads if self._armed else None
+        return self._armed
+
+    def _bucket(self, off, n, channel, stream, scale):
         from lirec_b200 import ops
         m, o = self.model, self.optimizer
-        scale = 1.0 / self.world
-        if local_clips is not None and global_clips is not None and local_clips * self.world != global_clips:
-            self.grad.mul_(float(local_clips) / float(global_clips))      # unequal last shards: weighted sum
-            scale = 1.0
         g = o.param_groups[0]
+        if self.world > 1:
+            ops.dp_exchange(self.hdl.multicast_ptr, off, n, self.rank, self.world, self.flag_hdl.buffer_ptrs_dev,
+                            channel, stream)
+        ops.adam_flat(m._flat, m._flat_grad, o._m, o._v, m._flat_bf16, g["lr"], g["betas"][0], g["betas"][1],
+                      g["eps"], g["weight_decay"], o._t, scale, offset=off, n=n, stream=stream)
+
+    @torch.no_grad()
+    def step(self, local_clips=None, global_clips=None):
+        """After backward: exchange + Adam of every bucket.  If `arm()` armed this step, bucket 0 runs on the
+        side stream behind the event backward recorded; otherwise everything runs on the current stream."""
+        m, o = self.model, self.optimizer
+        scale = 1.0 / self.world
+        armed = bool(getattr(self, "_armed", False))
+        self._armed = False
+        m._heads_event = None
+        if local_clips is not None and global_clips is not None and local_clips * self.world != global_clips:
+            assert not armed, "unequal shards are re-weighted on the host: arm(equal_shards=False)"
+            m._flat_grad.mul_(float(local_clips) / float(global_clips))      # unequal last shards: weighted sum
+            scale = 1.0
         o._t += 1
-        self.epoch += 1
-        ops.dp_allreduce_adam(m._flat, self.grad, self.hdl.multicast_ptr, o._m, o._v, m._flat_bf16, g["lr"],
-                              g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], o._t, scale, self.rank,
-                              self.world, self.flag_hdl.buffer_ptrs_dev, self.ws, self.epoch)
+        main = torch.cuda.current_stream()
+        if armed:
+            self.side.wait_event(self.ev_heads)              # recorded mid-backward on the main stream
+            self._bucket(self.split, self.n - self.split, 0, self.side, scale)
+            self.ev_done.record(self.side)
+            if self.split:
+                self._bucket(0, self.split, 1, main, scale)
+            main.wait_event(self.ev_done)
+        else:
+            self._bucket(0, self.n, 0, main, scale)
         m.mark_bf16_fresh()          # FlatAdam materialises the per-parameter step counters lazily
 
 

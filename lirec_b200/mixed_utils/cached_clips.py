@@ -1,0 +1,106 @@
+"""Independent synthetic clips behind the reference's dataset surface, with the features CACHED in two
+dataset-level banks — the shape of the reference's real pipeline: `MixedFeaturesDataset.cache()` pools every
+clip / track vector once (mixed_utils/classification_dataloader.py:139-186, mixed_features.py:37-112) and
+`__getitem__` (:291-616) then assembles rows out of cached vectors.
+
+    --synthetic 3   `cache()` draws `size` clips with mixed_utils/synthetic.py:make_clip (the bench workload,
+                    SURVEY.md §8d C1-C5) and stores their vectors once: clip bank = every clip's own row followed
+                    by its context clips (+ one all-zero last row), track bank = row 0 all zero, then every
+                    clip's character tracks and context tracks.  An item is the clip's index-only record in the
+                    format of mixed_utils/indexed_dataset.py (candidate / context triples into the dataset
+                    banks), so batches are built by the same native collate (`lirec_collate_tables`) and, with
+                    `--resident_banks 1`, staged by the same device row gather as the annotation-world dataset.
+
+This is the dataset `bench.py` drives its end-to-end leg through (`packed_loader` with worker processes)."""
+import numpy as np
+from torch.utils.data import Dataset
+
+from lirec_b200.mixed_utils import synthetic
+from lirec_b200.mixed_utils.indexed_dataset import collate_indexed
+from lirec_b200.packing import CLIP_DIM, TRACK_DIM
+from lirec_b200.utils.arg_pars import opt
+
+
+class CachedClipsDataset(Dataset):
+    SIZES = {"train": 4096, "val": 512, "test": 512}
+
+    def __init__(self, mode="train", size=None, preset=None, seed_base=None, max_n_tripl=None, rels_n_clips=None,
+                 clip_kwargs=None):
+        from lirec_b200.mixed_utils.classification_dataloader import preset_from_opt
+        self.mode = mode
+        self.n_classes = synthetic.N_CLASSES
+        self.rels_list = ["rel%02d" % i for i in range(synthetic.N_RELS)] + ["None"]
+        self.n_rels = len(self.rels_list)
+        self.interidx2mgdidx = list(range(self.n_classes))
+        self._max_n_tripl = int(max_n_tripl or getattr(opt, "max_n_tripl", 20))
+        self.rels_n_clips = int(rels_n_clips or (opt.rels_n_clips if opt.rels_multi_clip else 18))
+        self.epoch = 0
+        self._size = int(size or self.SIZES.get(mode, 512))
+        self._base = int(seed_base) if seed_base is not None else \
+            {"train": 0, "val": 1, "test": 2}.get(mode, 3) * 10_000_019 + int(opt.seed) * 7919
+        self.preset = preset or preset_from_opt()
+        self.clip_kwargs = dict(clip_kwargs or {})
+        self.records = None
+        self.clip_bank = self.track_bank = None
+        self.zero_clip = -1
+
+    # ---- the reference's cache(): every vector pooled once ---------------------------------------------
+    def cache(self):
+        if self.records is not None:
+            return self
+        clips = [synthetic.make_clip(self._base + i, preset=self.preset, max_n_tripl=self._max_n_tripl,
+                                     rels_n_clips=self.rels_n_clips, **self.clip_kwargs) for i in range(self._size)]
+        has_ctx = clips[0]["ctx_rows"] is not None
+        track_models = synthetic.PRESETS[self.preset]["enumerate_tracks"]
+        n_clip = sum(c["clip_vecs"].shape[0] if has_ctx else 1 for c in clips)
+        n_track = sum((c["track_vecs"].shape[0] if has_ctx else c["n_own_tracks"]) - 1 for c in clips)
+        self.clip_bank = np.zeros((n_clip + 1, CLIP_DIM), dtype=np.float32)       # last row: the all-zero clip
+        self.track_bank = np.zeros((n_track + 1, TRACK_DIM), dtype=np.float32)    # row 0: the all-zero track
+        self.zero_clip = n_clip
+        self.records = []
+        c0, t0 = 0, 1
+        for c in clips:
+            nc = c["clip_vecs"].shape[0] if has_ctx else 1
+            nt = (c["track_vecs"].shape[0] if has_ctx else c["n_own_tracks"]) - 1
+            self.clip_bank[c0:c0 + nc] = c["clip_vecs"][:nc]
+            self.track_bank[t0:t0 + nt] = c["track_vecs"][1:1 + nt]
+
+            def remap(rows, c0=c0, t0=t0):
+                out = np.empty(rows.shape, dtype=np.int32)
+                out[:, 0] = c0 + rows[:, 0]
+                out[:, 1:] = np.where(rows[:, 1:] == 0, 0, t0 + rows[:, 1:] - 1)     # local 0 = "no track"
+                return out
+            rec = {"labels": int(c["label"]), "cand_rows": remap(c["cand_rows"]),
+                   "multilab_weights": c["multilab"].astype(np.float64), "n_ctx_slots": c["n_ctx_slots"],
+                   "n_names": c["n_names"], "just_zeros": c["just_zeros"]}
+            if has_ctx:
+                rec["ctx_cat"] = remap(c["ctx_rows"])
+                rec["ctx_counts"] = c["ctx_counts"].astype(np.int32)
+                rec["ctx_rows"] = None                       # marks a context batch (the blocks are ctx_cat / ctx_counts)
+                rec["rels_label"] = c["rels_label"] if track_models else int(c["rels_label"][0])
+            if track_models:
+                rec["gt_tracks"] = c["gt_tracks"]
+            self.records.append(rec)
+            c0, t0 = c0 + nc, t0 + nt
+        return self
+
+    def init_relships(self):
+        assert self.rels_list[-1] == "None"
+        return self
+
+    def warm_records(self):
+        return self.cache()
+
+    def __len__(self):
+        return self._size
+
+    def __getitem__(self, idx):
+        if self.records is None:
+            self.cache()
+        return self.records[int(idx)]
+
+    def collate(self, records):
+        pb = collate_indexed(records, self, resident=bool(getattr(opt, "resident_banks", 0)))
+        pb.preset = self.preset
+        pb.kind = synthetic.PRESETS[self.preset]["kind"]
+        return pb

@@ -12,6 +12,9 @@ The MovieGraphs annotations / feature dump (~80 GB) are not available offline, a
 without `opt.synthetic` the dataset refuses to construct instead of pretending.
 
   --synthetic 1   independent synthetic clips (mixed_utils/synthetic.py; the bench workload)
+  --synthetic 3   the same independent clips with their vectors cached once in dataset-level banks and index-only
+                  items (mixed_utils/cached_clips.py) — the reference's cache() + __getitem__ split; what
+                  bench.py's end-to-end leg iterates
   --synthetic 2   a synthetic ANNOTATION world (mixed_utils/synthetic_world.py) run through the index-only
                   port of the reference dataset logic (mixed_utils/indexed_dataset.py: relationship
                   timelines, shared context clips, the reference's slot order and RNG use), the path real
@@ -35,6 +38,9 @@ def preset_from_opt():
 
 def MixedFeaturesDataset(mode="train", size=None):
     """Reference constructor signature (classification_dataloader.py:30); dispatches on opt.synthetic."""
+    if int(getattr(opt, "synthetic", 0)) == 3:
+        from lirec_b200.mixed_utils.cached_clips import CachedClipsDataset
+        return CachedClipsDataset(mode, size)
     if int(getattr(opt, "synthetic", 0)) == 2:
         from lirec_b200.mixed_utils import indexed_dataset, synthetic_world
         world = synthetic_world.build_world(int(opt.seed), n_movies=int(getattr(opt, "world_movies", 6)),
@@ -107,6 +113,8 @@ class EmptyShard:
     def pin(self):
         return self
 
+    pin_memory = pin
+
     def record_stream(self, stream):
         return self
 
@@ -127,21 +135,30 @@ def plan_batches(n, batch_size, order, rank, world, drop_last=False):
 
 
 def packed_loader(dataset, batch_size, shuffle, num_workers=0, device="cuda", rank=0, world=1, drop_last=False,
-                  seed=0):
+                  seed=0, repeat=1):
     """Iterate device-resident PackedBatches with one-batch-ahead async H2D prefetch.
 
     Data parallel: every rank iterates the same shuffled order and takes its contiguous share of each
     global batch (lirec_b200/dp.py:shard_range), so the global batch equals the single-GPU one.  A rank whose
-    share is empty receives an `EmptyShard` for that step (see there)."""
+    share is empty receives an `EmptyShard` for that step (see there).  `repeat` > 1 chains that many epochs
+    (each its own permutation) behind ONE set of worker processes instead of re-forking them per epoch."""
     g = torch.Generator()
     g.manual_seed(int(seed) * 1000003 + int(getattr(dataset, "epoch", 0)))
     n = len(dataset)
-    order = torch.randperm(n, generator=g).tolist() if shuffle else list(range(n))
-    batches = plan_batches(n, batch_size, order, rank, world, drop_last)
+    batches = []
+    for _ in range(max(1, int(repeat))):
+        order = torch.randperm(n, generator=g).tolist() if shuffle else list(range(n))
+        batches += plan_batches(n, batch_size, order, rank, world, drop_last)
     if int(num_workers) > 0 and hasattr(dataset, "warm_records"):
         dataset.warm_records()              # workers fork with the record cache already built
+    # worker processes build the batches (items + native collate); with workers the DataLoader's own pinning
+    # thread calls PackedBatch.pin_memory(), so the training thread only issues the async copies
     loader = torch.utils.data.DataLoader(_IndexView(dataset, batches), batch_size=None, shuffle=False,
-                                         num_workers=int(num_workers), collate_fn=None)
+                                         num_workers=int(num_workers), collate_fn=None,
+                                         pin_memory=int(num_workers) > 0,
+                                         prefetch_factor=(int(getattr(opt, "prefetch_factor", 2)) if int(num_workers) > 0
+                                                          else None),
+                                         persistent_workers=False)
     copy_stream = torch.cuda.Stream(device=device)
     pending = None
     banks = None

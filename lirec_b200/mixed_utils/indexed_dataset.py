@@ -802,9 +802,8 @@ class ResidentBanks:
     def stage(self, pb, non_blocking=True):
         """Host PackedBatch from `collate_indexed` -> device PackedBatch whose banks were gathered on the GPU."""
         from lirec_b200 import ops
-        c_rows, t_rows = pb.extras["bank_rows"]
         if not hasattr(pb, "_bank_rows_pinned"):
-            pb._bank_rows_pinned = (torch.from_numpy(c_rows).pin_memory(), torch.from_numpy(t_rows).pin_memory())
+            pb._pin_bank_rows()
         idx_c = pb._bank_rows_pinned[0].to(self.device, non_blocking=non_blocking)
         idx_t = pb._bank_rows_pinned[1].to(self.device, non_blocking=non_blocking)
         dev = pb.to_device(self.device, non_blocking=non_blocking, banks=False)

@@ -19,8 +19,11 @@ def _offsets(seqs):
     return off
 
 
-def pool_sequences(seqs, dim, device="cuda", out=None, pinned=True):
-    """seqs: list of float arrays [len_i, dim] (len_i may be 0) -> bf16 [len(seqs), dim] on device."""
+def pool_sequences(seqs, dim, device="cuda", out=None, pinned=True, mode="max", beta=1.0):
+    """seqs: list of float arrays [len_i, dim] (len_i may be 0) -> bf16 [len(seqs), dim] on device.
+    mode: 'max' — the reference's pooling (np.max, mixed_features.py:54, 61, 105) and the default; 'mean'; or
+    'softmax' — softmax_r(beta * x[r, c])-weighted sum per channel (lirec_seg_softmax_pool_fwd; the reference has
+    no such pooling: parity unpinned, its beta -> inf / beta = 0 limits are the other two modes)."""
     off = _offsets(seqs)
     total = int(off[-1])
     flat = np.concatenate([np.asarray(s, dtype=np.float32).reshape(-1, dim) for s in seqs]) if total else \
@@ -35,7 +38,11 @@ def pool_sequences(seqs, dim, device="cuda", out=None, pinned=True):
     if total == 0:
         out.zero_()
         return out
-    ops.seg_reduce(x, offd, "max", out_bf16=out)
+    if mode == "softmax":
+        pooled, _ = ops.seg_softmax_pool(x, offd, beta=beta, need_lse=False)
+        out.copy_(pooled)
+    else:
+        ops.seg_reduce(x, offd, mode, out_bf16=out)
     return out
 
 

@@ -40,6 +40,9 @@ def train_step(model, loss, optimizer, pb, world=1, fused=None):
         dp.reduce_and_step(model, optimizer, fused, 0, pb.global_clips)
         return model._flat_grad.new_zeros(())
     loss._dp_world = world                       # multi-task losses normalise their relationship term globally
+    if fused is not None:                        # bucket 0 of the exchange / Adam overlaps the rest of backward
+        gc = getattr(pb.host, "global_clips", None) if getattr(pb, "host", None) is not None else None
+        fused.arm(equal_shards=(world == 1 or gc is None or pb.B * world == gc))
     if int(getattr(opt, "native_step", 1)) and isinstance(model, _HotPath) and isinstance(loss, _FusedLoss):
         loss_values = native_train_step(model, loss, pb)
     else:
@@ -70,6 +73,8 @@ def training(train_dataset, **kwargs):
             loss.set_rank(rank)
         if int(getattr(opt, "dp_switch_reduce", 1)):
             fused = dp.SwitchReduceAdam.attach(model, optimizer)     # None without NVSwitch multicast / FlatAdam
+    if fused is None and world == 1 and int(getattr(opt, "overlap_adam", 1)):
+        fused = dp.SwitchReduceAdam.attach(model, optimizer, single_gpu=True)    # None unless FlatAdam
     batch_time, data_time, losses = Averaging(), Averaging(), Averaging()
     print("epochs: %s", opt.epochs)
     model_saver_val = ModelSaver(path=opt.store_root)

@@ -11,8 +11,8 @@ from . import _ext
 from ._ext import (ACT_NONE, ACT_RELU, ACT_TANH, OUT_F32, OUT_SPLIT, OUT_SPLIT_T, POST_DRELU, POST_DROPOUT, POST_DTANH,
                    POST_NONE)
 
-__all__ = ["gemm_problem", "gemm_grouped", "seg_reduce", "rows_expand_fwd", "rows_expand_bwd", "split_f32",
-           "cast_bf16", "gather_rows", "roi_max_pool", "loss_track", "loss_rowmargin", "loss_ce", "predict_tracks", "adam_flat", "dp_allreduce_adam", "dropout_desc"]
+__all__ = ["gemm_problem", "gemm_grouped", "seg_reduce", "seg_softmax_pool", "seg_softmax_pool_bwd", "SegSoftmaxPool", "rows_expand_fwd", "rows_expand_bwd", "split_f32",
+           "cast_bf16", "gather_rows", "roi_max_pool", "loss_track", "loss_rowmargin", "loss_ce", "predict_tracks", "adam_flat", "dp_exchange", "dropout_desc"]
 
 
 def dropout_desc(p=0.0, seed=0, stream_id=0, col_off=0):
@@ -76,6 +76,65 @@ def seg_reduce(x, seg_off, mode="max", out_f32=None, out_bf16=None, row_idx=None
         _ext.ptr(x), _ext.ptr(seg_off), nseg, x.shape[1], 0 if mode == "max" else 1,
         _ext.ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
         _ext.ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, _ext.stream_ptr()))
+
+
+def _score_mode(x, scores):
+    if scores is None:
+        return 0
+    assert scores.dtype == torch.float32 and scores.is_contiguous()
+    if scores.dim() == 1:
+        assert scores.numel() == x.shape[0]
+        return 2
+    assert scores.shape == x.shape
+    return 1
+
+
+def seg_softmax_pool(x, seg_off, beta=1.0, scores=None, need_lse=True):
+    """Softmax-weighted segmented reduction (lirec_seg_softmax_pool_fwd; parity unpinned — the reference has none).
+    x [total, dim] fp32; scores None (score = x), [total, dim] or [total].  Returns (out [nseg, dim], lse)."""
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous() and seg_off.dtype == torch.int32
+    mode = _score_mode(x, scores)
+    nseg, dim = seg_off.numel() - 1, x.shape[1]
+    out = torch.empty(nseg, dim, dtype=torch.float32, device=x.device)
+    lse = None
+    if need_lse:
+        lse = torch.empty((nseg,) if mode == 2 else (nseg, dim), dtype=torch.float32, device=x.device)
+    _ext.check(_ext.lib().lirec_seg_softmax_pool_fwd(
+        _ext.ptr(x), _ext.ptr(scores), mode, _ext.ptr(seg_off), nseg, dim, float(beta), _ext.ptr(out), out.stride(0),
+        _ext.ptr(lse), lse.stride(0) if (lse is not None and lse.dim() == 2) else 0, _ext.stream_ptr()))
+    return out, lse
+
+
+def seg_softmax_pool_bwd(x, seg_off, beta, scores, out, lse, d_out, need_d_scores=True):
+    """Gradients of seg_softmax_pool: (d_x, d_scores | None)."""
+    mode = _score_mode(x, scores)
+    nseg, dim = seg_off.numel() - 1, x.shape[1]
+    d_out = d_out.contiguous()
+    d_x = torch.zeros_like(x)
+    d_s = torch.zeros_like(scores) if (mode != 0 and need_d_scores) else None
+    _ext.check(_ext.lib().lirec_seg_softmax_pool_bwd(
+        _ext.ptr(x), _ext.ptr(scores), mode, _ext.ptr(seg_off), nseg, dim, float(beta), _ext.ptr(out), out.stride(0),
+        _ext.ptr(lse), lse.stride(0) if lse.dim() == 2 else 0, _ext.ptr(d_out), d_out.stride(0), _ext.ptr(d_x),
+        _ext.ptr(d_s), _ext.stream_ptr()))
+    return d_x, d_s
+
+
+class SegSoftmaxPool(torch.autograd.Function):
+    """Differentiable front of the two entry points (x and scores may require grad)."""
+
+    @staticmethod
+    def forward(ctx, x, seg_off, beta, scores):
+        out, lse = seg_softmax_pool(x, seg_off, beta, scores)
+        ctx.save_for_backward(x, seg_off, scores if scores is not None else x.new_empty(0), out, lse)
+        ctx.beta, ctx.has_scores = float(beta), scores is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, seg_off, scores, out, lse = ctx.saved_tensors
+        scores = scores if ctx.has_scores else None
+        d_x, d_s = seg_softmax_pool_bwd(x, seg_off, ctx.beta, scores, out, lse, d_out)
+        return d_x, None, None, d_s
 
 
 def rows_expand_fwd(r1, J, rows, seg_off, n_out, guard_zero, drop, out_split, row_flag_out=None):
@@ -193,20 +252,22 @@ def predict_tracks(ints, rels, cand_off, labels, rels_label, gt_tracks, n_rels):
 
 
 def adam_flat(param, grad, exp_avg, exp_avg_sq, param_bf16, lr, beta1, beta2, eps, weight_decay, step,
-              grad_scale=1.0):
+              grad_scale=1.0, offset=0, n=None, stream=None):
+    """Fused Adam over floats [offset, offset + n) of the flat buffers (default: everything) on `stream`."""
     L = _ext.lib()
-    _ext.check(L.lirec_adam_flat(_ext.ptr(param), _ext.ptr(grad), _ext.ptr(exp_avg), _ext.ptr(exp_avg_sq),
-                                 _ext.ptr(param_bf16), param.numel(), float(lr), float(beta1), float(beta2),
-                                 float(eps), float(weight_decay), int(step), float(grad_scale),
-                                 _ext.stream_ptr()))
+    n = param.numel() - offset if n is None else n
+    sp = _ext.stream_ptr() if stream is None else C.c_void_p(stream.cuda_stream)
+    _ext.check(L.lirec_adam_flat(_ext.ptr(param) + 4 * offset, _ext.ptr(grad) + 4 * offset,
+                                 _ext.ptr(exp_avg) + 4 * offset, _ext.ptr(exp_avg_sq) + 4 * offset,
+                                 (_ext.ptr(param_bf16) + 2 * offset) if param_bf16 is not None else None, int(n),
+                                 float(lr), float(beta1), float(beta2),
+                                 float(eps), float(weight_decay), int(step), float(grad_scale), sp))
 
 
-def dp_allreduce_adam(param, grad, grad_multicast_ptr, exp_avg, exp_avg_sq, param_bf16, lr, beta1, beta2, eps,
-                      weight_decay, step, grad_scale, rank, world, flag_ptrs_dev, sync_ws, epoch):
-    """In-switch gradient sum over ranks + Adam in one launch (lirec_dp_allreduce_adam)."""
+def dp_exchange(grad_multicast_ptr, offset, n, rank, world, flag_ptrs_dev, channel, stream=None):
+    """In-switch sum over ranks of floats [offset, offset + n) of the symmetric flat gradient buffer
+    (lirec_dp_exchange: barrier, multimem reduce + broadcast of this rank's shard, barrier) on `stream`."""
     L = _ext.lib()
-    _ext.check(L.lirec_dp_allreduce_adam(
-        _ext.ptr(param), _ext.ptr(grad), C.c_void_p(int(grad_multicast_ptr)), _ext.ptr(exp_avg), _ext.ptr(exp_avg_sq),
-        _ext.ptr(param_bf16), param.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
-        int(step), float(grad_scale), int(rank), int(world), C.c_void_p(int(flag_ptrs_dev)), _ext.ptr(sync_ws),
-        int(epoch), _ext.stream_ptr()))
+    sp = _ext.stream_ptr() if stream is None else C.c_void_p(stream.cuda_stream)
+    _ext.check(L.lirec_dp_exchange(C.c_void_p(int(grad_multicast_ptr)), int(offset), int(n), int(rank), int(world),
+                                   C.c_void_p(int(flag_ptrs_dev)), int(channel), sp))

@@ -103,3 +103,98 @@ def test_text_pooling_matches_the_reference():
                    row_idx=torch.from_numpy(idx).cuda())
     ref = np.stack([x[l].mean(0) if len(l) else np.zeros(768, dtype=np.float32) for l in lists])
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-6)
+
+
+# ---- softmax-weighted segmented reduction (row N1; parity unpinned by construction: the reference has none) -------
+def _np_softpool(x, off, beta, scores):
+    """float64 numpy statement: out, and the gradients of sum(out * dy) for a given dy."""
+    x = x.astype(np.float64)
+    nseg, dim = len(off) - 1, x.shape[1]
+    out = np.zeros((nseg, dim))
+    ws = []
+    for s in range(nseg):
+        a, b = off[s], off[s + 1]
+        if b <= a:
+            ws.append(None)
+            continue
+        sc = x[a:b] if scores is None else (scores[a:b].astype(np.float64) if scores.ndim == 2
+                                            else np.repeat(scores[a:b, None].astype(np.float64), dim, 1))
+        z = beta * sc
+        w = np.exp(z - z.max(0, keepdims=True))
+        w /= w.sum(0, keepdims=True)
+        out[s] = (w * x[a:b]).sum(0)
+        ws.append(w)
+    return out, ws
+
+
+def _np_softpool_bwd(x, off, beta, scores, out, ws, dy):
+    x = x.astype(np.float64)
+    dx = np.zeros_like(x)
+    ds = None if scores is None else np.zeros(scores.shape)
+    for s in range(len(off) - 1):
+        a, b = off[s], off[s + 1]
+        if b <= a:
+            continue
+        w = ws[s]
+        gx = w * dy[s]
+        gs = beta * gx * (x[a:b] - out[s])
+        if scores is None:
+            dx[a:b] = gx + gs
+        else:
+            dx[a:b] = gx
+            ds[a:b] = gs if scores.ndim == 2 else gs.sum(1)
+    return dx, ds
+
+
+@pytest.mark.parametrize("kind", ["self", "elem", "row"])
+def test_softmax_pool_forward_backward_vs_numpy(kind):
+    from lirec_b200 import ops
+    rng = np.random.default_rng(3)
+    lens = [5, 0, 1, 37, 12, 0, 64, 3]                       # ragged, with empty segments
+    off = np.concatenate(([0], np.cumsum(lens))).astype(np.int32)
+    dim, beta = 768, 1.7
+    x = rng.standard_normal((off[-1], dim)).astype(np.float32)
+    scores = None if kind == "self" else (rng.standard_normal((off[-1], dim)) if kind == "elem"
+                                          else rng.standard_normal(off[-1])).astype(np.float32)
+    dy = rng.standard_normal((len(lens), dim))
+    ref, ws = _np_softpool(x, off, beta, scores)
+    rdx, rds = _np_softpool_bwd(x, off, beta, scores, ref, ws, dy)
+    xd = torch.from_numpy(x).cuda().requires_grad_(True)
+    sd = None if scores is None else torch.from_numpy(scores).cuda().requires_grad_(True)
+    offd = torch.from_numpy(off).cuda()
+    out = ops.SegSoftmaxPool.apply(xd, offd, beta, sd)
+    (out * torch.from_numpy(dy).float().cuda()).sum().backward()
+    assert float(np.abs(out.detach().cpu().numpy() - ref).max()) < 2e-5 * max(1.0, np.abs(ref).max())
+    assert (out.detach().cpu().numpy()[[1, 5]] == 0).all()    # empty segments -> zeros, like max / mean
+    assert float(np.abs(xd.grad.cpu().numpy() - rdx).max()) < 3e-5 * np.abs(rdx).max()
+    if scores is not None:
+        assert float(np.abs(sd.grad.cpu().numpy() - rds).max()) < 3e-5 * np.abs(rds).max()
+
+
+def test_softmax_pool_limits_are_the_reference_poolings():
+    """beta = 0 (uniform weights) is the masked MEAN and beta -> inf with score = x is the MAX — the two poolings
+    the reference does have (mlp/model.py:301-304, mixed_features.py:54) and lirec_seg_reduce_f32 is pinned on."""
+    from lirec_b200 import ops
+    rng = np.random.default_rng(4)
+    lens = [9, 1, 0, 128, 17]
+    off = torch.from_numpy(np.concatenate(([0], np.cumsum(lens))).astype(np.int32)).cuda()
+    x = torch.from_numpy(np.abs(rng.standard_normal((sum(lens), 2048))).astype(np.float32)).cuda()
+    mean = torch.empty(len(lens), 2048, device="cuda")
+    mx = torch.empty(len(lens), 2048, device="cuda")
+    ops.seg_reduce(x, off, "mean", out_f32=mean)
+    ops.seg_reduce(x, off, "max", out_f32=mx)
+    soft0, _ = ops.seg_softmax_pool(x, off, beta=0.0)
+    hard, _ = ops.seg_softmax_pool(x, off, beta=1e6)
+    assert float((soft0 - mean).abs().max()) < 1e-6 * float(mean.abs().max())
+    assert torch.equal(hard, mx)                               # an exact selection, ties included
+    # all-zero scores of either kind are the mean too
+    z, _ = ops.seg_softmax_pool(x, off, beta=3.0, scores=torch.zeros(x.shape[0], device="cuda"))
+    assert float((z - mean).abs().max()) < 1e-6 * float(mean.abs().max())
+    # temperature -> 0 on per-row scores selects the best-scored row of every segment
+    sc = torch.from_numpy(rng.standard_normal(sum(lens)).astype(np.float32)).cuda()
+    sel, _ = ops.seg_softmax_pool(x, off, beta=1e6, scores=sc)
+    o = off.cpu().numpy()
+    for s in range(len(lens)):
+        if lens[s]:
+            r = o[s] + int(torch.argmax(sc[o[s]:o[s + 1]]))
+            assert torch.equal(sel[s], x[r])

@@ -4,7 +4,8 @@ NCCL on the same box).  Under torchrun on N >= 2 GPUs of one NVSwitch box:
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/dp_exchange_probe.py
 
 times, with CUDA events and the max over ranks, per step:
-  (a) lirec_dp_allreduce_adam: in-switch reduce (multimem.ld_reduce / multimem.st) + Adam, one kernel;
+  (a) dp.SwitchReduceAdam.step(): lirec_dp_exchange (barrier, in-switch multimem.ld_reduce / multimem.st, barrier)
+      + lirec_adam_flat over the whole buffer;
   (b) ncclAllReduce(sum, fp32) of the same flat gradient buffer, alone;
   (c) (b) + lirec_adam_flat, the two-launch form the fused kernel replaces;
   (d) lirec_adam_flat alone.

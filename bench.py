@@ -157,7 +157,7 @@ class ClockSampler:
                             self.reasons.add(name)
                 except Exception:
                     pass
-            time.sleep(0.01)
+            time.sleep(float(os.environ.get("LIREC_BENCH_SAMPLE_S", "0.02")))
 
     def _start_smi(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -335,6 +335,8 @@ class Bench:
         torch.cuda.synchronize()
 
     def max_over_ranks(self, ms):
+        if os.environ.get("LIREC_BENCH_DEBUG"):
+            print("[rank %d] leg %.3f ms" % (self.rank, ms), file=sys.stderr, flush=True)
         if self.world == 1:
             return float(ms)
         import torch.distributed as dist
@@ -515,7 +517,7 @@ def run_ours(args):
 
     b = Bench(args, args.preset, args.batch, args.n_batches, rank, world, dev)
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("LIREC_BENCH_NO_SAMPLER"):
         sampler.start()
 
     # ---------------- device-resident timed region ----------------

@@ -34,6 +34,7 @@ namespace gemm {
 
 constexpr int BM = 128;       // tile rows  (UMMA M, cta_group::1)
 constexpr int BK = 64;        // bf16 elements per k-block = one 128B swizzle span
+constexpr int BN128 = 128;    // tile columns of the single-CTA kernel
 constexpr int UMMA_K = 16;
 #ifndef LIREC_EPI_WARPS
 #define LIREC_EPI_WARPS 8
@@ -49,11 +50,30 @@ constexpr int MAX_PASSES = LIREC_GEMM_MAX_PASSES;
 constexpr int MAX_PROBLEMS = LIREC_GEMM_MAX_PROBLEMS;
 constexpr int MAX_MAPS = LIREC_GEMM_MAX_MAPS;
 
-struct DevPass {
-  int16_t a_map, b_map;
-  int32_t a_mn_off, a_k_off, b_mn_off, b_k_off;
-  int32_t k_blocks;
+// One operand tile fetched per stage: tensor map, MN offset and first K offset (elements).
+struct DevLoad {
+  int32_t mn_off, k_off;
+  int16_t map, pad;
 };
+// A GROUP of passes that walk the same k range and share operand tiles.  One pipeline stage holds up to two A
+// tiles and two B tiles of one k-block and feeds up to four MMAs over them:
+//     forward with a hi/lo split input   (x_hi, W) (x_lo, W)                  2 A, 1 B, 2 MMAs
+//     weight gradient                    (x_hi, dy_hi) (x_lo, dy_hi) (x_hi, dy_lo)   2 A, 2 B, 3 MMAs
+//     first-layer weight gradient        (x, dy_hi) (x, dy_lo)                1 A, 2 B, 2 MMAs
+//     data gradient                      (dy_hi, W^T) (dy_lo, W^T)            2 A, 1 B, 2 MMAs
+//     single pass                        two consecutive k-blocks per stage   2 A, 2 B, 2 MMAs
+// so a shared tile crosses L2 -> shared memory ONCE instead of once per pass: 24 / 21 KB of operand bytes per
+// 256x256x64 MMA block instead of 32 KB.  The pair kernel at 32 KB per block asks L2 for ~64 B/clk/SM at the
+// full tensor rate, which B200's L2 does not deliver (round-1 ncu: tensor pipe 63-78 % active on the long-K
+// launches, 19-28 % on the short-K ones).
+struct DevGroup {
+  DevLoad a[2], b[2];
+  int32_t k_iters;             // stages this group takes per tile (before split-K)
+  int32_t k_step;              // K elements advanced per stage (64, or 128 for the two-k-block form)
+  int8_t na, nb, nmma, pad;
+  int8_t mma_a[4], mma_b[4];   // operand slots of each MMA
+};
+constexpr int MAX_GROUPS = 3;
 
 struct DevEpi {
   float alpha;
@@ -81,17 +101,16 @@ struct DevProblem {
   int32_t M, N;
   int32_t bn;                  // tile width of this problem (pair kernel: 128 or 256 per CTA pair)
   int32_t tiles_n, tiles_mn;   // tiles per row of tiles / per split slice
-  int32_t split_chunk;         // k-blocks per split-K slice (INT_MAX: no split)
+  int32_t split_chunk;         // group iterations per split-K slice (0x3fffffff: no split)
   int64_t split_stride;        // elements between the partial outputs of consecutive slices
-  int32_t num_passes;
+  int32_t num_groups;
   int32_t a_mn_major, b_mn_major;
-  int32_t kb_major;            // 1: all passes cover the same k-blocks and are interleaved per k-block
-  DevPass pass[MAX_PASSES];
+  DevGroup group[MAX_GROUPS];
   DevEpi epi;
 };
 
 constexpr int EPI_STAGE_BYTES = 4096;   // per epilogue warp: a 32 x 32 chunk as bf16 hi + lo (pair kernel)
-constexpr int MAX_ORDERED_TILES = 6144;
+constexpr int MAX_ORDERED_TILES = 5120;
 constexpr uint16_t NO_TILE = 0xFFFF;
 
 struct alignas(64) GemmParams {
@@ -518,30 +537,44 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpi& e, int M, int N, in
 }
 
 // ---------------------------------------------------------------------------
-// The kernel.  BN = tile columns (UMMA N), STAGES = smem ring depth.
+// The kernel body, shared by the two launch forms:
+//   PAIR = false  one CTA per 128 x 128 tile (cta_group::1) — launches too small to fill the clusters;
+//   PAIR = true   the two SMs of a TPC run ONE 256 x bn tile (cta_group::2, bn = 128 or 256 per problem).
+//                 Each CTA stages its own 128 rows of A and bn/2 rows of B, so a k-block costs each SM half
+//                 the shared-memory fill and operand reads of two independent 128x128 tiles:
+//                   * both CTAs' producers issue their TMA loads; every load signals the LEADER's full barrier;
+//                   * the leader's MMA thread issues tcgen05.mma.cta_group::2 and commits (multicast) to the
+//                     stage-empty and accumulator-full barriers of both CTAs;
+//                   * each CTA's eight epilogue warps drain their own 128 accumulator lanes and arrive on the
+//                     leader's accumulator-empty barrier.
+// A pipeline stage = four 16 KB slots (A0, A1, B0, B1) holding the operand tiles of one DevGroup step.
 // ---------------------------------------------------------------------------
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-lirec_gemm_tcgen05_kernel(const __grid_constant__ GemmParams P) {
-  constexpr uint32_t A_BYTES = BM * BK * 2;  // 16 KB
-  constexpr uint32_t B_BYTES = BN * BK * 2;
-  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator buffers
-  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512 || TMEM_COLS == 128, "TMEM cols pow2");
+constexpr uint32_t SLOT_BYTES = BM * BK * 2;            // 16 KB: 128 rows x 64 bf16
+constexpr uint32_t GSTAGE_BYTES = 4 * SLOT_BYTES;       // 64 KB
+constexpr int GSTAGES = 3;
 
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
+template <bool PAIR>
+__device__ __forceinline__ void gemm_body(const GemmParams& P, uint8_t* smem_raw) {
+  constexpr int STAGES = GSTAGES;
+  constexpr uint32_t ACC_COLS = PAIR ? 256 : 128;  // accumulator buffer stride in TMEM columns
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+  constexpr int TILE_M = PAIR ? 2 * BM : BM;
+
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + STAGES;
-  uint64_t* tfull_bar = bars + 2 * STAGES;
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * GSTAGE_BYTES);
+  uint64_t* full_bar = bars;                       // PAIR: used in the leader only
+  uint64_t* empty_bar = bars + STAGES;             // per CTA
+  uint64_t* tfull_bar = bars + 2 * STAGES;         // per CTA
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;    // PAIR: used in the leader only
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int unit = PAIR ? (blockIdx.x >> 1) : blockIdx.x;          // persistent worker id
+  const int num_units = PAIR ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp == PRODUCER_WARP && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -550,28 +583,35 @@ lirec_gemm_tcgen05_kernel(const __grid_constant__ GemmParams P) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tfull_bar[s]), 1);
-      mbar_init(smem_u32(&tempty_bar[s]), NUM_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&tempty_bar[s]), (PAIR ? 2 : 1) * NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_slot)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == PRODUCER_WARP) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (PAIR: both CTAs) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int slot = blockIdx.x; slot < P.num_slots; slot += gridDim.x) {
+      for (int slot = unit; slot < P.num_slots; slot += num_units) {
         const int t = P.use_order ? static_cast<int>(P.tile_order[slot]) : slot;
         if (t == NO_TILE) continue;
         int p = 0;
@@ -579,94 +619,116 @@ lirec_gemm_tcgen05_kernel(const __grid_constant__ GemmParams P) {
         const DevProblem& pr = P.probs[p];
         const int local = t - P.tile_start[p];
         const int slice = local / pr.tiles_mn, rem = local - slice * pr.tiles_mn;
-        const int m0 = (rem / pr.tiles_n) * BM;
-        const int n0 = (rem % pr.tiles_n) * BN;
-        auto issue = [&](int ps, int kb) {
-          const DevPass& pa = pr.pass[ps];
-          const CUtensorMap* amap = &P.maps[pa.a_map];
-          const CUtensorMap* bmap = &P.maps[pa.b_map];
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_expect_tx(fb, STAGE_BYTES);
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
-          if (!pr.a_mn_major) {
-            tma_load_2d(sa, amap, fb, pa.a_k_off + kb * BK, pa.a_mn_off + m0);
-          } else {
+        const int brows = PAIR ? (pr.bn >> 1) : BN128;                  // B rows this CTA stages
+        const int m0 = (rem / pr.tiles_n) * TILE_M + static_cast<int>(rank) * BM;
+        const int n0 = (rem % pr.tiles_n) * (PAIR ? pr.bn : BN128) + static_cast<int>(rank) * brows;
+        const uint32_t b_bytes = static_cast<uint32_t>(brows) * (BK * 2);
+        for (int g = 0; g < pr.num_groups; ++g) {
+          const DevGroup& G = pr.group[g];
+          const int it_end = min(G.k_iters, (slice + 1) * pr.split_chunk);
+          const uint32_t cta_bytes = static_cast<uint32_t>(G.na) * SLOT_BYTES + static_cast<uint32_t>(G.nb) * b_bytes;
+          for (int it = slice * pr.split_chunk; it < it_end; ++it) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            const uint32_t fb_local = smem_u32(&full_bar[stage]);
+            uint32_t fb = fb_local;
+            if constexpr (PAIR) {
+              if (rank == 0) mbar_expect_tx(fb_local, 2 * cta_bytes);   // both CTAs' bytes land here
+              fb = mapa_rank(fb_local, 0);
+            } else {
+              mbar_expect_tx(fb_local, cta_bytes);
+            }
+            const uint32_t s0 = smem_u32(smem + stage * GSTAGE_BYTES);
+            const int kadv = it * G.k_step;
+            for (int j = 0; j < G.na; ++j) {
+              const DevLoad& L = G.a[j];
+              const CUtensorMap* map = &P.maps[L.map];
+              const uint32_t dst = s0 + j * SLOT_BYTES;
+              if (!pr.a_mn_major) {
+                if constexpr (PAIR) tma_load_2d_pair(dst, map, fb, L.k_off + kadv, L.mn_off + m0);
+                else tma_load_2d(dst, map, fb, L.k_off + kadv, L.mn_off + m0);
+              } else {
 #pragma unroll
-            for (int h = 0; h < BM / 64; ++h)
-              tma_load_2d(sa + h * (BK * 128), amap, fb, pa.a_mn_off + m0 + h * 64,
-                          pa.a_k_off + kb * BK);
-          }
-          if (!pr.b_mn_major) {
-            tma_load_2d(sb, bmap, fb, pa.b_k_off + kb * BK, pa.b_mn_off + n0);
-          } else {
-#pragma unroll
-            for (int h = 0; h < BN / 64; ++h)
-              tma_load_2d(sb + h * (BK * 128), bmap, fb, pa.b_mn_off + n0 + h * 64,
-                          pa.b_k_off + kb * BK);
-          }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        };
-        if (pr.kb_major) {   // passes share their k range: visit them k-block by k-block (operand reuse in L2)
-          const int kb_end = min(pr.pass[0].k_blocks, (slice + 1) * pr.split_chunk);
-          for (int kb = slice * pr.split_chunk; kb < kb_end; ++kb)
-            for (int ps = 0; ps < pr.num_passes; ++ps) issue(ps, kb);
-        } else {
-          for (int ps = 0; ps < pr.num_passes; ++ps) {
-            const int kb_end = min(pr.pass[ps].k_blocks, (slice + 1) * pr.split_chunk);
-            for (int kb = slice * pr.split_chunk; kb < kb_end; ++kb) issue(ps, kb);
+                for (int h = 0; h < BM / 64; ++h) {
+                  if constexpr (PAIR) tma_load_2d_pair(dst + h * (BK * 128), map, fb, L.mn_off + m0 + h * 64, L.k_off + kadv);
+                  else tma_load_2d(dst + h * (BK * 128), map, fb, L.mn_off + m0 + h * 64, L.k_off + kadv);
+                }
+              }
+            }
+            for (int j = 0; j < G.nb; ++j) {
+              const DevLoad& L = G.b[j];
+              const CUtensorMap* map = &P.maps[L.map];
+              const uint32_t dst = s0 + (2 + j) * SLOT_BYTES;
+              if (!pr.b_mn_major) {
+                if constexpr (PAIR) tma_load_2d_pair(dst, map, fb, L.k_off + kadv, L.mn_off + n0);
+                else tma_load_2d(dst, map, fb, L.k_off + kadv, L.mn_off + n0);
+              } else {
+                for (int h = 0; h < brows / 64; ++h) {
+                  if constexpr (PAIR) tma_load_2d_pair(dst + h * (BK * 128), map, fb, L.mn_off + n0 + h * 64, L.k_off + kadv);
+                  else tma_load_2d(dst + h * (BK * 128), map, fb, L.mn_off + n0 + h * 64, L.k_off + kadv);
+                }
+              }
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == MMA_WARP) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (PAIR: leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int slot = blockIdx.x; slot < P.num_slots; slot += gridDim.x) {
+      for (int slot = unit; slot < P.num_slots; slot += num_units) {
         const int t = P.use_order ? static_cast<int>(P.tile_order[slot]) : slot;
         if (t == NO_TILE) continue;
         int p = 0;
         while (t >= P.tile_start[p + 1]) ++p;
         const DevProblem& pr = P.probs[p];
-        // instruction descriptor: D=f32, A=B=bf16, majorness, N>>3, M>>4
+        // instruction descriptor: D=f32, A=B=bf16, majorness, N>>3, M>>4 (PAIR: M = 256 over the pair)
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
                                (static_cast<uint32_t>(pr.a_mn_major) << 15) |
                                (static_cast<uint32_t>(pr.b_mn_major) << 16) |
-                               (static_cast<uint32_t>(BN >> 3) << 17) |
-                               (static_cast<uint32_t>(BM >> 4) << 24);
+                               (static_cast<uint32_t>((PAIR ? pr.bn : BN128) >> 3) << 17) |
+                               (static_cast<uint32_t>(TILE_M >> 4) << 24);
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc) * ACC_COLS;
         uint32_t accumulate = 0;
         const int slice = (t - P.tile_start[p]) / pr.tiles_mn;
-        for (int ps = 0; ps < pr.num_passes; ++ps) {
-          const int kb_end = min(pr.pass[ps].k_blocks, (slice + 1) * pr.split_chunk);
-          for (int kb = slice * pr.split_chunk; kb < kb_end; ++kb) {
+        for (int g = 0; g < pr.num_groups; ++g) {
+          const DevGroup& G = pr.group[g];
+          const int it_end = min(G.k_iters, (slice + 1) * pr.split_chunk);
+          for (int it = slice * pr.split_chunk; it < it_end; ++it) {
             mbar_wait(smem_u32(&full_bar[stage]), phase);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-            const uint32_t sb = sa + A_BYTES;
+            const uint32_t s0 = smem_u32(smem + stage * GSTAGE_BYTES);
+            for (int j = 0; j < G.nmma; ++j) {
+              const uint32_t sa = s0 + static_cast<uint32_t>(G.mma_a[j]) * SLOT_BYTES;
+              const uint32_t sb = s0 + static_cast<uint32_t>(2 + G.mma_b[j]) * SLOT_BYTES;
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t adesc = pr.a_mn_major
-                                         ? make_smem_desc(sa + k * (UMMA_K * 128), BK * 128, 1024)
-                                         : make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
-              const uint64_t bdesc = pr.b_mn_major
-                                         ? make_smem_desc(sb + k * (UMMA_K * 128), BK * 128, 1024)
-                                         : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-              tc_mma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
-              accumulate = 1;
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint64_t adesc = pr.a_mn_major
+                                           ? make_smem_desc(sa + k * (UMMA_K * 128), BK * 128, 1024)
+                                           : make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+                const uint64_t bdesc = pr.b_mn_major
+                                           ? make_smem_desc(sb + k * (UMMA_K * 128), BK * 128, 1024)
+                                           : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+                if constexpr (PAIR) tc_mma_bf16_pair(tmem_d, adesc, bdesc, idesc, accumulate);
+                else tc_mma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+                accumulate = 1;
+              }
             }
-            tc_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot when the MMAs retire
+            // frees the stage (PAIR: in both CTAs) when its MMAs retire
+            if constexpr (PAIR) tc_commit_pair(smem_u32(&empty_bar[stage]));
+            else tc_commit(smem_u32(&empty_bar[stage]));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
-        tc_commit(smem_u32(&tfull_bar[acc]));  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue(s)
+        if constexpr (PAIR) tc_commit_pair(smem_u32(&tfull_bar[acc]));
+        else tc_commit(smem_u32(&tfull_bar[acc]));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -675,9 +737,10 @@ lirec_gemm_tcgen05_kernel(const __grid_constant__ GemmParams P) {
     // two warps per TMEM lane quarter; they split the 32-column chunks of the tile between them
     const int quarter = warp & 3;            // TMEM lane quarter this warp may read
     const int half = warp >> 2;              // 0 or 1
+    uint8_t* epi_stage = smem + STAGES * GSTAGE_BYTES + 256 + warp * EPI_STAGE_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int slot = blockIdx.x; slot < P.num_slots; slot += gridDim.x) {
+    for (int slot = unit; slot < P.num_slots; slot += num_units) {
       const int t = P.use_order ? static_cast<int>(P.tile_order[slot]) : slot;
       if (t == NO_TILE) continue;
       int p = 0;
@@ -685,222 +748,10 @@ lirec_gemm_tcgen05_kernel(const __grid_constant__ GemmParams P) {
       const DevProblem& pr = P.probs[p];
       const int local = t - P.tile_start[p];
       const int slice = local / pr.tiles_mn, rem = local - slice * pr.tiles_mn;
-      const int m0 = (rem / pr.tiles_n) * BM;
-      const int n0 = (rem % pr.tiles_n) * BN;
-      mbar_wait_sleepy(smem_u32(&tfull_bar[acc]), acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = half; c < BN / 32; c += NUM_EPI_WARPS / 4) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                               static_cast<uint32_t>(acc * BN + c * 32);
-        tmem_ld_32x32(taddr, r);
-        epilogue_chunk(pr.epi, pr.M, pr.N, m0 + quarter * 32 + lane, n0 + c * 32, r,
-                       static_cast<int64_t>(slice) * pr.split_stride, slice == 0, nullptr, lane);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == MMA_WARP) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(TMEM_COLS)
-                 : "memory");
-  }
-}
-
-
-// ---------------------------------------------------------------------------
-// CTA-pair kernel (cta_group::2): the two SMs of a TPC run ONE 256 x bn tile (bn = 128 or 256 per
-// problem).  Each CTA stages its own 128 rows of A and bn/2 rows of B, so a k-block costs each SM
-// 32 KB of shared-memory fill and 8 KB of operand reads per 256x256x16 MMA — half of what two
-// independent 128x128 tiles need, which is what lets the tensor pipe run near its rate (a 1-CTA
-// 128x128 SS-mode mainloop is bound by the 128 B/clk shared-memory port).
-//   * both CTAs' producers issue their TMA loads; every load signals the LEADER's full barrier;
-//   * the leader's MMA thread issues tcgen05.mma.cta_group::2 and commits (multicast) to the
-//     stage-empty and accumulator-full barriers of both CTAs;
-//   * each CTA's eight epilogue warps drain their own 128 accumulator lanes (rows m0 + 128*rank ..)
-//     and arrive on the leader's accumulator-empty barrier.
-// ---------------------------------------------------------------------------
-template <int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-lirec_gemm_tcgen05_pair_kernel(const __grid_constant__ GemmParams P) {
-  constexpr uint32_t A_BYTES = BM * BK * 2;        // 16 KB: this CTA's 128 rows of A
-  constexpr uint32_t B_BYTES_MAX = 128 * BK * 2;   // 16 KB: this CTA's half of a 256-wide B tile
-  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES_MAX;
-  constexpr uint32_t ACC_COLS = 256;               // accumulator buffer stride in TMEM columns
-  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
-
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full_bar = bars;                       // used in the leader only
-  uint64_t* empty_bar = bars + STAGES;             // per CTA
-  uint64_t* tfull_bar = bars + 2 * STAGES;         // per CTA
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;    // used in the leader only
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int cluster_id = blockIdx.x >> 1;
-  const int num_clusters = gridDim.x >> 1;
-
-  if (warp == PRODUCER_WARP && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&tfull_bar[s]), 1);
-      mbar_init(smem_u32(&tempty_bar[s]), 2 * NUM_EPI_WARPS);  // the epilogue warps of both CTAs
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == MMA_WARP) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_slot)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();   // the peer's barriers are initialised before anything signals them
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == PRODUCER_WARP) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int slot = cluster_id; slot < P.num_slots; slot += num_clusters) {
-        const int t = P.use_order ? static_cast<int>(P.tile_order[slot]) : slot;
-        if (t == NO_TILE) continue;
-        int p = 0;
-        while (t >= P.tile_start[p + 1]) ++p;
-        const DevProblem& pr = P.probs[p];
-        const int local = t - P.tile_start[p];
-        const int slice = local / pr.tiles_mn, rem = local - slice * pr.tiles_mn;
-        const int bhalf = pr.bn >> 1;
-        const int m0 = (rem / pr.tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
-        const int n0 = (rem % pr.tiles_n) * pr.bn + static_cast<int>(rank) * bhalf;
-        const uint32_t cta_bytes = A_BYTES + static_cast<uint32_t>(bhalf) * (BK * 2);
-        auto issue = [&](int ps, int kb) {
-          const DevPass& pa = pr.pass[ps];
-          const CUtensorMap* amap = &P.maps[pa.a_map];
-          const CUtensorMap* bmap = &P.maps[pa.b_map];
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          const uint32_t fb_local = smem_u32(&full_bar[stage]);
-          if (rank == 0) mbar_expect_tx(fb_local, 2 * cta_bytes);   // both CTAs' bytes land here
-          const uint32_t fb = mapa_rank(fb_local, 0);
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
-          if (!pr.a_mn_major) {
-            tma_load_2d_pair(sa, amap, fb, pa.a_k_off + kb * BK, pa.a_mn_off + m0);
-          } else {
-#pragma unroll
-            for (int h = 0; h < BM / 64; ++h)
-              tma_load_2d_pair(sa + h * (BK * 128), amap, fb, pa.a_mn_off + m0 + h * 64,
-                               pa.a_k_off + kb * BK);
-          }
-          if (!pr.b_mn_major) {
-            tma_load_2d_pair(sb, bmap, fb, pa.b_k_off + kb * BK, pa.b_mn_off + n0);
-          } else {
-            for (int h = 0; h < bhalf / 64; ++h)
-              tma_load_2d_pair(sb + h * (BK * 128), bmap, fb, pa.b_mn_off + n0 + h * 64,
-                               pa.b_k_off + kb * BK);
-          }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        };
-        if (pr.kb_major) {   // passes share their k range: visit them k-block by k-block (operand reuse in L2)
-          const int kb_end = min(pr.pass[0].k_blocks, (slice + 1) * pr.split_chunk);
-          for (int kb = slice * pr.split_chunk; kb < kb_end; ++kb)
-            for (int ps = 0; ps < pr.num_passes; ++ps) issue(ps, kb);
-        } else {
-          for (int ps = 0; ps < pr.num_passes; ++ps) {
-            const int kb_end = min(pr.pass[ps].k_blocks, (slice + 1) * pr.split_chunk);
-            for (int kb = slice * pr.split_chunk; kb < kb_end; ++kb) issue(ps, kb);
-          }
-        }
-      }
-    }
-  } else if (warp == MMA_WARP) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && rank == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int slot = cluster_id; slot < P.num_slots; slot += num_clusters) {
-        const int t = P.use_order ? static_cast<int>(P.tile_order[slot]) : slot;
-        if (t == NO_TILE) continue;
-        int p = 0;
-        while (t >= P.tile_start[p + 1]) ++p;
-        const DevProblem& pr = P.probs[p];
-        // instruction descriptor: D=f32, A=B=bf16, majorness, N>>3, M>>4 with M = 256 over the pair
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
-                               (static_cast<uint32_t>(pr.a_mn_major) << 15) |
-                               (static_cast<uint32_t>(pr.b_mn_major) << 16) |
-                               (static_cast<uint32_t>(pr.bn >> 3) << 17) |
-                               (static_cast<uint32_t>((2 * BM) >> 4) << 24);
-        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc) * ACC_COLS;
-        uint32_t accumulate = 0;
-        const int slice = (t - P.tile_start[p]) / pr.tiles_mn;
-        for (int ps = 0; ps < pr.num_passes; ++ps) {
-          const int kb_end = min(pr.pass[ps].k_blocks, (slice + 1) * pr.split_chunk);
-          for (int kb = slice * pr.split_chunk; kb < kb_end; ++kb) {
-            mbar_wait(smem_u32(&full_bar[stage]), phase);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-            const uint32_t sb = sa + A_BYTES;
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t adesc = pr.a_mn_major
-                                         ? make_smem_desc(sa + k * (UMMA_K * 128), BK * 128, 1024)
-                                         : make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
-              const uint64_t bdesc = pr.b_mn_major
-                                         ? make_smem_desc(sb + k * (UMMA_K * 128), BK * 128, 1024)
-                                         : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-              tc_mma_bf16_pair(tmem_d, adesc, bdesc, idesc, accumulate);
-              accumulate = 1;
-            }
-            tc_commit_pair(smem_u32(&empty_bar[stage]));  // frees the slot in both CTAs
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-        }
-        tc_commit_pair(smem_u32(&tfull_bar[acc]));  // accumulator complete -> both epilogues
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  } else {
-    // ===================== epilogue warps (0..7), both CTAs =====================
-    const int quarter = warp & 3;
-    const int half = warp >> 2;
-    uint8_t* epi_stage = smem + STAGES * STAGE_BYTES + 256 + warp * EPI_STAGE_BYTES;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int slot = cluster_id; slot < P.num_slots; slot += num_clusters) {
-      const int t = P.use_order ? static_cast<int>(P.tile_order[slot]) : slot;
-      if (t == NO_TILE) continue;
-      int p = 0;
-      while (t >= P.tile_start[p + 1]) ++p;
-      const DevProblem& pr = P.probs[p];
-      const int local = t - P.tile_start[p];
-      const int slice = local / pr.tiles_mn, rem = local - slice * pr.tiles_mn;
-      const int m0 = (rem / pr.tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
-      const int n0 = (rem % pr.tiles_n) * pr.bn;
-      const int chunks = pr.bn >> 5;
+      const int tile_n = PAIR ? pr.bn : BN128;
+      const int m0 = (rem / pr.tiles_n) * TILE_M + static_cast<int>(rank) * BM;
+      const int n0 = (rem % pr.tiles_n) * tile_n;
+      const int chunks = tile_n >> 5;
       mbar_wait_sleepy(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -914,21 +765,37 @@ lirec_gemm_tcgen05_pair_kernel(const __grid_constant__ GemmParams P) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[acc]), 0));
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[acc]), 0));
+        else mbar_arrive(smem_u32(&tempty_bar[acc]));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
-  // neither CTA may leave (or free TMEM) while the pair still reads its smem / signals its barriers
+  // PAIR: neither CTA may leave (or free TMEM) while the pair still reads its smem / signals its barriers
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();
+  if constexpr (PAIR) cluster_sync_all();
   if (warp == MMA_WARP) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(TMEM_COLS)
-                 : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+lirec_gemm_tcgen05_kernel(const __grid_constant__ GemmParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  gemm_body<false>(P, smem_raw);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+lirec_gemm_tcgen05_pair_kernel(const __grid_constant__ GemmParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  gemm_body<true>(P, smem_raw);
 }
 
 // ---------------------------------------------------------------------------
@@ -1006,9 +873,9 @@ static void schedule_tiles(GemmParams& P, int grid) {
   bool uniform = true;
   int first_cost = -1;
   for (int p = 0; p < P.num_problems; ++p) {
-    int kb = 0;
-    for (int ps = 0; ps < P.probs[p].num_passes; ++ps)
-      kb += std::min(P.probs[p].pass[ps].k_blocks, P.probs[p].split_chunk);
+    int kb = 0;                                     // MMA k-blocks per tile (of one split slice)
+    for (int g = 0; g < P.probs[p].num_groups; ++g)
+      kb += std::min(P.probs[p].group[g].k_iters, P.probs[p].split_chunk) * P.probs[p].group[g].nmma;
     const DevEpi& e = P.probs[p].epi;
     const int epi = (e.act == LIREC_ACT_TANH || e.post != LIREC_POST_NONE) ? 10 : (e.out_kind == LIREC_OUT_F32 ? 4 : 6);
     const int cost = kb + epi * P.probs[p].bn / 128;
@@ -1060,15 +927,16 @@ static int record_end(ProfRec& rec, cudaStream_t stream) {
   return LIREC_OK;
 }
 
-template <int BN, int STAGES>
-static int launch(const GemmParams& P, cudaStream_t stream) {
-  constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/;
-  static_assert(smem <= 232448, "shared memory budget");
+constexpr size_t GEMM_SMEM = GSTAGES * GSTAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+                             NUM_EPI_WARPS * EPI_STAGE_BYTES /*epilogue staging*/;
+static_assert(GEMM_SMEM <= 232448, "shared memory budget");
+
+static int launch_single(const GemmParams& P, cudaStream_t stream) {
   static bool configured = false;
   static int num_sms = 0;
   if (!configured) {
-    LIREC_CUDA_OK(cudaFuncSetAttribute(lirec_gemm_tcgen05_kernel<BN, STAGES>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LIREC_CUDA_OK(cudaFuncSetAttribute(lirec_gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)GEMM_SMEM));
     int dev = 0;
     LIREC_CUDA_OK(cudaGetDevice(&dev));
     LIREC_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1079,7 +947,7 @@ static int launch(const GemmParams& P, cudaStream_t stream) {
   ProfRec rec{};
   int rc = record_begin(rec, P, stream);
   if (rc != LIREC_OK) return rc;
-  lirec_gemm_tcgen05_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, stream>>>(P);
+  lirec_gemm_tcgen05_kernel<<<grid, NUM_THREADS, GEMM_SMEM, stream>>>(P);
   LIREC_CUDA_OK(cudaGetLastError());
   if ((rc = record_end(rec, stream)) != LIREC_OK) return rc;
   note_launch();
@@ -1087,16 +955,12 @@ static int launch(const GemmParams& P, cudaStream_t stream) {
 }
 
 // CTA-pair launch: one cluster of two CTAs per TPC, persistent over the pair tiles.
-template <int STAGES>
 static int launch_pair(const GemmParams& P, cudaStream_t stream) {
-  constexpr size_t smem = STAGES * (BM * BK * 2 + 128 * BK * 2) + 1024 /*align*/ + 256 /*barriers*/ +
-                          NUM_EPI_WARPS * EPI_STAGE_BYTES /*epilogue staging*/;
-  static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   static int max_clusters = 0;
   if (!configured) {
-    LIREC_CUDA_OK(cudaFuncSetAttribute(lirec_gemm_tcgen05_pair_kernel<STAGES>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LIREC_CUDA_OK(cudaFuncSetAttribute(lirec_gemm_tcgen05_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)GEMM_SMEM));
     int dev = 0, num_sms = 0;
     LIREC_CUDA_OK(cudaGetDevice(&dev));
     LIREC_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1105,10 +969,9 @@ static int launch_pair(const GemmParams& P, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(num_sms / 2 * 2);
     cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = smem;
+    cfg.dynamicSmemBytes = GEMM_SMEM;
     int active = 0;
-    if (cudaOccupancyMaxActiveClusters(&active, lirec_gemm_tcgen05_pair_kernel<STAGES>, &cfg) == cudaSuccess &&
-        active > 0)
+    if (cudaOccupancyMaxActiveClusters(&active, lirec_gemm_tcgen05_pair_kernel, &cfg) == cudaSuccess && active > 0)
       max_clusters = std::min(max_clusters, active);
     else
       (void)cudaGetLastError();
@@ -1119,7 +982,7 @@ static int launch_pair(const GemmParams& P, cudaStream_t stream) {
   ProfRec rec{};
   int rc = record_begin(rec, P, stream);
   if (rc != LIREC_OK) return rc;
-  lirec_gemm_tcgen05_pair_kernel<STAGES><<<2 * clusters, NUM_THREADS, smem, stream>>>(P);
+  lirec_gemm_tcgen05_pair_kernel<<<2 * clusters, NUM_THREADS, GEMM_SMEM, stream>>>(P);
   LIREC_CUDA_OK(cudaGetLastError());
   if ((rc = record_end(rec, stream)) != LIREC_OK) return rc;
   note_launch();
@@ -1138,14 +1001,6 @@ static int pair_mode() {
     v = (e == nullptr || e[0] == '\0') ? -1 : (e[0] == '0' ? 0 : 1);
   }
   return v;
-}
-static bool kb_major_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("LIREC_GEMM_KB_MAJOR");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v != 0;
 }
 static bool choose_pair_kernel(const lirec_gemm_problem* probs, int nprobs) {
   const int mode = pair_mode();
@@ -1219,28 +1074,71 @@ int run_grouped(const lirec_gemm_problem* probs, int nprobs, cudaStream_t stream
     d.split_chunk = (split > 1) ? (max_kb + split - 1) / split : 0x3fffffff;
     if (split > 1) split = (max_kb + d.split_chunk - 1) / d.split_chunk;   // every slice non-empty
     d.split_stride = g.split_stride;
-    d.num_passes = g.num_passes;
     d.a_mn_major = g.a_mn_major ? 1 : 0;
     d.b_mn_major = g.b_mn_major ? 1 : 0;
+    // ---- passes -> groups: consecutive passes over the same k range that share operand tiles run out of ONE
+    // pipeline stage (see DevGroup).  Order of accumulation inside a tile changes, the sum does not.
+    struct Spec { int map, mn_off, k_off; };
+    auto same = [](const Spec& x, const Spec& y) { return x.map == y.map && x.mn_off == y.mn_off && x.k_off == y.k_off; };
+    d.num_groups = 0;
+    int cur_kb = -1;
+    std::vector<Spec> ga, gb;
+    auto flush = [&]() { ga.clear(); gb.clear(); cur_kb = -1; };
     for (int ps = 0; ps < g.num_passes; ++ps) {
       const lirec_gemm_pass& s = g.pass[ps];
       LIREC_REQUIRE(s.k_len > 0, "problem %d pass %d: k_len=%d", idx, ps, s.k_len);
       const int ia = map_index(s.a, d.a_mn_major, BM);
       const int ib = map_index(s.b, d.b_mn_major, b_box);
       if (ia < 0 || ib < 0) return fail(LIREC_ERR_LIMIT, "more than %d tensor maps in one launch", MAX_MAPS);
-      d.pass[ps] = DevPass{(int16_t)ia, (int16_t)ib, s.a_mn_off, s.a_k_off, s.b_mn_off, s.b_k_off,
-                           (s.k_len + BK - 1) / BK};
+      const Spec sa{ia, s.a_mn_off, s.a_k_off}, sb{ib, s.b_mn_off, s.b_k_off};
+      const int kb = (s.k_len + BK - 1) / BK;
+      int ja = -1, jb = -1;
+      bool fits = d.num_groups > 0 && kb == cur_kb && d.group[d.num_groups - 1].nmma < 4;
+      if (fits) {
+        for (size_t q = 0; q < ga.size(); ++q) if (same(ga[q], sa)) ja = (int)q;
+        for (size_t q = 0; q < gb.size(); ++q) if (same(gb[q], sb)) jb = (int)q;
+        if ((ja < 0 && ga.size() >= 2) || (jb < 0 && gb.size() >= 2)) fits = false;
+      }
+      if (!fits) {
+        LIREC_REQUIRE(d.num_groups < MAX_GROUPS, "problem %d: its passes need more than %d operand groups", idx, MAX_GROUPS);
+        flush();
+        DevGroup& G = d.group[d.num_groups++];
+        memset(&G, 0, sizeof(G));
+        G.k_iters = kb;
+        G.k_step = BK;
+        cur_kb = kb;
+        ja = jb = -1;
+      }
+      DevGroup& G = d.group[d.num_groups - 1];
+      if (ja < 0) { ja = (int)ga.size(); ga.push_back(sa); G.a[ja] = DevLoad{sa.mn_off, sa.k_off, (int16_t)sa.map, 0}; G.na = (int8_t)ga.size(); }
+      if (jb < 0) { jb = (int)gb.size(); gb.push_back(sb); G.b[jb] = DevLoad{sb.mn_off, sb.k_off, (int16_t)sb.map, 0}; G.nb = (int8_t)gb.size(); }
+      G.mma_a[G.nmma] = (int8_t)ja;
+      G.mma_b[G.nmma] = (int8_t)jb;
+      ++G.nmma;
     }
-    // Optional (LIREC_GEMM_KB_MAJOR=1): passes over the same k range (hi/lo splits of one operand pair)
-    // interleaved k-block by k-block, so the operand tile two passes share (x_hi in x_hi*dy_hi and
-    // x_hi*dy_lo) is re-read while it is still in L2.  Measured on B200 it LOSES to the pass-major
-    // default: gate backward 0.67 -> 0.70 ms, first-layer wgrad 0.311 -> 0.329 ms, heads backward
-    // unchanged (the long sequential K sweep per operand is what the TMA/HBM path likes), so it is off.
-    d.kb_major = 0;
-    if (g.num_passes > 1 && kb_major_enabled()) {
-      d.kb_major = 1;
-      for (int ps = 1; ps < g.num_passes; ++ps)
-        if (d.pass[ps].k_blocks != d.pass[0].k_blocks) d.kb_major = 0;
+    // a lone pass (nothing to share): two consecutive k-blocks per stage, so three stages still keep six
+    // k-blocks in flight; an odd k-block count leaves a one-block tail group
+    if (split == 1) {
+      const int ng = d.num_groups;
+      for (int q = 0; q < ng; ++q) {
+        DevGroup& G = d.group[q];
+        if (G.nmma != 1 || G.k_iters < 2 || d.num_groups >= MAX_GROUPS + (G.k_iters % 2 == 0 ? 1 : 0)) continue;
+        const int kb = G.k_iters;
+        if (kb % 2) {                                    // tail group: the last k-block alone
+          DevGroup& T = d.group[d.num_groups++];
+          T = G;
+          T.a[0].k_off += (kb - 1) * BK;
+          T.b[0].k_off += (kb - 1) * BK;
+          T.k_iters = 1;
+        }
+        G.a[1] = G.a[0]; G.a[1].k_off += BK;
+        G.b[1] = G.b[0]; G.b[1].k_off += BK;
+        G.na = G.nb = 2;
+        G.nmma = 2;
+        G.mma_a[1] = 1; G.mma_b[1] = 1;
+        G.k_iters = kb / 2;
+        G.k_step = 2 * BK;
+      }
     }
     const lirec_epilogue& e = g.epi;
     LIREC_REQUIRE(e.out != nullptr, "problem %d: null output", idx);
@@ -1304,7 +1202,7 @@ int run_grouped(const lirec_gemm_problem* probs, int nprobs, cudaStream_t stream
     int rc = encode_map(&P.maps[i], keys[i]);
     if (rc != LIREC_OK) return rc;
   }
-  return pair ? launch_pair<6>(P, stream) : launch<128, 6>(P, stream);
+  return pair ? launch_pair(P, stream) : launch_single(P, stream);
 }
 
 }  // namespace gemm

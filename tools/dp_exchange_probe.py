@@ -83,6 +83,19 @@ def switch_adam():
     grad.mul_(1.0 / world)
 
 
+def switch_only():
+    from lirec_b200 import ops
+    ops.dp_exchange(fused.hdl.multicast_ptr, 0, n, rank, world, fused.flag_hdl.buffer_ptrs_dev, 0)
+    grad.mul_(1.0 / world)
+
+
+def switch_two_buckets():
+    from lirec_b200 import ops
+    ops.dp_exchange(fused.hdl.multicast_ptr, fused.split, n - fused.split, rank, world, fused.flag_hdl.buffer_ptrs_dev, 0)
+    ops.dp_exchange(fused.hdl.multicast_ptr, 0, fused.split, rank, world, fused.flag_hdl.buffer_ptrs_dev, 1)
+    grad.mul_(1.0 / world)
+
+
 res = {"world": world, "params": n, "bytes": 4 * n}
 scale_ms = timed(scale_only)
 res["adam_ms"] = timed(lambda: optimizer.step(grad_scale=1.0))
@@ -90,6 +103,9 @@ res["nccl_allreduce_ms"] = timed(nccl_only) - scale_ms
 res["nccl_allreduce_plus_adam_ms"] = timed(nccl_adam) - scale_ms
 if fused is not None:
     res["switch_reduce_adam_ms"] = timed(switch_adam) - scale_ms
+    res["switch_exchange_only_ms"] = timed(switch_only) - scale_ms
+    res["switch_exchange_two_buckets_ms"] = timed(switch_two_buckets) - scale_ms
+    res["switch_exchange_only_busbw_GBs"] = 2.0 * (world - 1) / world * 4 * n / (res["switch_exchange_only_ms"] * 1e-3) / 1e9
 bus = 2.0 * (world - 1) / world * 4 * n
 res["nccl_busbw_GBs"] = bus / (res["nccl_allreduce_ms"] * 1e-3) / 1e9
 if fused is not None:

@@ -102,8 +102,13 @@ def parse_args():
     ap.add_argument("--dump_profile", default="", help="write the per-launch GEMM event timings to this file")
     ap.add_argument("--nccl_allreduce", action="store_true",
                     help="N > 1: use ncclAllReduce + Adam instead of the in-switch reduce + Adam kernels")
+    ap.add_argument("--dp_mode", default="", choices=["", "shard", "bucket"],
+                    help="N > 1: 'shard' (default) = in-switch sum + sharded Adam + parameter multicast in one pass; "
+                         "'bucket' = in-switch sum and full-replica Adam per bucket")
     ap.add_argument("--no_overlap", action="store_true",
-                    help="N > 1: run the whole gradient exchange after backward (no bucket overlapped with it)")
+                    help="N > 1, --dp_mode bucket: run the whole exchange after backward (no bucket overlapped with it)")
+    ap.add_argument("--overlap_adam", action="store_true",
+                    help="N = 1: run the gate + head bucket's Adam pass on a side stream during backward")
     ap.add_argument("--autograd_step", action="store_true",
                     help="drive the step through model()/loss()/backward()/optimizer.step() and the autograd engine "
                          "(the drop-in surface) instead of lirec_b200.mlp.train.train_step's native sequence")
@@ -304,10 +309,12 @@ class Bench:
         # gradient exchange (N > 1: in-switch, bucketed) + Adam, the gate + head bucket overlapped with backward;
         # N = 1: only the overlapped bucket-0 Adam pass
         self.fused = None
-        if not args.nccl_allreduce and fused_ok and not (world == 1 and args.no_overlap):
-            self.fused = dp.SwitchReduceAdam.attach(self.model, self.optimizer, single_gpu=True)
+        if world > 1 and not args.nccl_allreduce and fused_ok:
+            self.fused = dp.SwitchReduceAdam.attach(self.model, self.optimizer, mode=args.dp_mode or None)
             if self.fused is not None and args.no_overlap:
                 self.fused.overlap = False
+        elif world == 1 and args.overlap_adam:
+            self.fused = dp.SwitchReduceAdam.attach(self.model, self.optimizer, single_gpu=True)
         # the rank's dataset: n_batches * batch distinct clips, cached once (the reference's dataset.cache())
         self.dataset = CachedClipsDataset("train", size=n_batches * batch, preset=PRESETS[preset]["model"],
                                           seed_base=(1000 * rank + 17) * 1000003,
@@ -450,12 +457,14 @@ def dp_parity_check(b):
     out = {"replicas_bit_identical": identical}
     if b.fused is not None:
         pb = b.resident[0]
+        b.fused.gather_moments()                                 # 'shard' mode: every rank sees all moments
         M.train_step(m, b.loss_fn, pb, seed=123)                 # forward + loss + backward only
         torch.cuda.synchronize()
         g_local = m._flat_grad.clone()
         state = (flat.clone(), o._m.clone(), o._v.clone(), o._t)
-        b.fused.step()                                           # in-switch reduce + Adam, all buckets
+        b.fused.step()                                           # the in-switch step (exchange + Adam)
         torch.cuda.synchronize()
+        dist.barrier()
         p_switch, g_switch = flat.clone(), m._flat_grad.clone()
         flat.copy_(state[0]), o._m.copy_(state[1]), o._v.copy_(state[2])
         o._t = state[3]
@@ -466,9 +475,11 @@ def dp_parity_check(b):
         o.step(grad_scale=scale)
         torch.cuda.synchronize()
         gmax = float(m._flat_grad.abs().max())
-        out["grad_sum_max_abs_diff_rel"] = float((g_switch - m._flat_grad).abs().max()) / max(gmax, 1e-30)
+        out["mode"] = b.fused.mode
+        if b.fused.mode != "shard":                              # 'shard' never writes the gradient sum back
+            out["grad_sum_max_abs_diff_rel"] = float((g_switch - m._flat_grad).abs().max()) / max(gmax, 1e-30)
         out["param_max_abs_diff"] = float((p_switch - flat).abs().max())
-        out["switch_step_equals_nccl_step"] = bool(out["grad_sum_max_abs_diff_rel"] < 1e-5 and
+        out["switch_step_equals_nccl_step"] = bool(out.get("grad_sum_max_abs_diff_rel", 0.0) < 1e-5 and
                                                    out["param_max_abs_diff"] < 1e-7)
         m.mark_bf16_fresh()
     ok = identical and out.get("switch_step_equals_nccl_step", True)
@@ -689,9 +700,11 @@ def run_ours(args):
     roofline = b.roofline(prof, steps, ms_total, clocks, pk) if rank == 0 else None
     exchange = "none (1 GPU)"
     if world > 1:
-        exchange = ("in-switch multimem reduce + Adam per bucket, first bucket overlapped with backward "
-                    "(lirec_dp_*)" if (b.fused is not None and getattr(b.fused, "overlap", False)) else
-                    "in-switch multimem reduce + Adam after backward (lirec_dp_*)" if b.fused is not None
+        exchange = ("in-switch gradient sum + sharded Adam + multicast of the new parameters in one pass "
+                    "(lirec_dp_reduce_adam_bcast)" if (b.fused is not None and b.fused.mode == "shard") else
+                    "in-switch multimem reduce + Adam per bucket, first bucket overlapped with backward "
+                    "(lirec_dp_exchange)" if (b.fused is not None and getattr(b.fused, "overlap", False)) else
+                    "in-switch multimem reduce + Adam after backward (lirec_dp_exchange)" if b.fused is not None
                     else "ncclAllReduce fp32 + Adam")
     n_cand, n_ctx, in_bytes = b.n_cand, b.n_ctx, res_bytes
     b.close()
@@ -739,8 +752,7 @@ def run_ours(args):
                        "preset": args.preset, "clips_per_gpu": args.batch, "global_batch": args.batch * world,
                        "candidate_rows_per_step": n_cand, "context_rows_per_step": n_ctx,
                        "parallelism": "dp%d" % world,
-                       "optimizer": "fused flat Adam" + ("" if args.no_overlap else
-                                                         ", the gate + head bucket's pass overlapped with backward"),
+                       "optimizer": "fused flat Adam",
                        "step_api": ("model()/loss()/backward()/optimizer.step() (autograd)" if args.autograd_step
                                     else "lirec_b200.mlp.train.train_step (native forward+loss+backward, no autograd)"),
                        "gradient_exchange": exchange,

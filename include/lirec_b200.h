@@ -439,8 +439,32 @@ int lirec_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_
  * lirec_dp_flag_words(world) uint32; `channel` (0..3) selects the flag slots, so chains for different buckets may
  * be in flight on different streams at the same time (all ranks must use the same channel for the same bucket). */
 int lirec_dp_flag_words(int32_t world);
+/* Exchange + optimizer + parameter broadcast in ONE pass (ZeRO-1 style), the default data-parallel step: every
+ * rank owns the Adam moments of its 1/world shard.  For its shard it sums the gradients inside the switch
+ * (multimem.ld_reduce.add on grad_multicast), applies torch.optim.Adam's update (mlp/model.py:599-601, same
+ * arithmetic as lirec_adam_flat) to the local parameters `param` with grad * grad_scale, stores the moments
+ * locally and multicast-stores the new fp32 parameters and their bf16 shadow into EVERY rank's buffers
+ * (param_multicast / param_bf16_multicast: the multicast addresses of the symmetric parameter buffers).
+ * exp_avg / exp_avg_sq are full-size arrays of which only this rank's shard [n/4*rank/world, n/4*(rank+1)/world)
+ * (in 16-byte units) is read and written.  Barriers before and after as in lirec_dp_exchange.               */
+int lirec_dp_reduce_adam_bcast(const void* grad_multicast, const float* param, void* param_multicast,
+                               void* param_bf16_multicast, float* exp_avg, float* exp_avg_sq, int64_t n,
+                               float lr, float beta1, float beta2, float eps, float weight_decay,
+                               int32_t step, float grad_scale, int32_t rank, int32_t world,
+                               const void* flag_ptrs_dev, int32_t channel, void* stream);
 int lirec_dp_exchange(void* grad_multicast, int64_t offset, int64_t n, int32_t rank, int32_t world,
                       const void* flag_ptrs_dev, int32_t channel, void* stream);
+
+/* The same pass over plain peer pointers instead of the multicast object (P2P loads of every rank's gradient
+ * shard, P2P stores of the new parameters into every rank): the better transport at 2 ranks, where an in-switch
+ * reduction drags the requester's own copy through the switch as well.  peer_bases_dev: device array [world] of
+ * every rank's peer-mapped symmetric allocation; *_off: byte offsets of the gradient, fp32 parameter and bf16
+ * shadow buffers inside it.  world must be 2, 4 or 8.                                                        */
+int lirec_dp_reduce_adam_bcast_peer(const void* peer_bases_dev, int64_t grad_off, int64_t param_off,
+                                    int64_t bf16_off, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                    float lr, float beta1, float beta2, float eps, float weight_decay,
+                                    int32_t step, float grad_scale, int32_t rank, int32_t world,
+                                    const void* flag_ptrs_dev, int32_t channel, void* stream);
 
 #ifdef __cplusplus
 }

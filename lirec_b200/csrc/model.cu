@@ -532,6 +532,11 @@ static void add_dgrad_passes_inplace(lirec_gemm_problem& g, const TGrad& dy, int
   add_pass(g, mk_pass(a, 0, dy.hi, b, in_off, 0, out_f));
   add_pass(g, mk_pass(a, 0, dy.lo, b, in_off, 0, out_f));
 }
+// LIREC_DEFER_REDUCTIONS=0 keeps every parameter-gradient reduction in the launch of its own stage (A/B knob).
+static bool defer_reductions() {
+  const char* e = getenv("LIREC_DEFER_REDUCTIONS");
+  return !(e && e[0] == '0');
+}
 // Below this many candidate rows backward multiplies by the weights in place instead of transposing them.
 static bool dgrad_in_place(int Ni) {
   const char* e = getenv("LIREC_DGRAD_INPLACE_ROWS");   // read per call: the tests switch it
@@ -632,14 +637,19 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
   const TGrad dpg{w.dpregT, 2 * Gd, NiP, 0, Gd};
 
   // ---- stage H: head wgrad/bgrad + dgrad through the head --------------------
-  std::vector<lirec_gemm_problem> pr;
-  push_reduction(pr, wgrad_t(d.C, hw, dli, hx, 2 * hw, 2 * hw, 0, hw, Ni, 1.f, P.out_ints.grad_w, hw), d.C, hw, Ni,
+  // The head parameter gradients have no consumer inside backward: with a gate they ride in stage G's launch,
+  // where their long memory-bound reductions (the [101, 3072] gradient streams the whole gate output) fill the
+  // schedule next to the gate's compute-bound tiles instead of stretching this short launch.
+  std::vector<lirec_gemm_problem> pr, head_red;
+  const bool defer_heads = d.gates && defer_reductions();
+  std::vector<lirec_gemm_problem>& hr = defer_heads ? head_red : pr;
+  push_reduction(hr, wgrad_t(d.C, hw, dli, hx, 2 * hw, 2 * hw, 0, hw, Ni, 1.f, P.out_ints.grad_w, hw), d.C, hw, Ni,
                  true, sc);
-  push_reduction(pr, bgrad_t(d.C, dli, w.onesT, Ni, P.out_ints.grad_b), d.C, 1, Ni, false, sc);
+  push_reduction(hr, bgrad_t(d.C, dli, w.onesT, Ni, P.out_ints.grad_b), d.C, 1, Ni, false, sc);
   if (d.ctx) {
-    push_reduction(pr, wgrad_t(d.R, F, dlr, w.f2[1], 2 * F, 2 * F, 0, F, Ni, 1.f, P.out_ctx.grad_w, F), d.R, F, Ni,
+    push_reduction(hr, wgrad_t(d.R, F, dlr, w.f2[1], 2 * F, 2 * F, 0, F, Ni, 1.f, P.out_ctx.grad_w, F), d.R, F, Ni,
                    true, sc);
-    push_reduction(pr, bgrad_t(d.R, dlr, w.onesT, Ni, P.out_ctx.grad_b), d.R, 1, Ni, false, sc);
+    push_reduction(hr, bgrad_t(d.R, dlr, w.onesT, Ni, P.out_ctx.grad_b), d.R, 1, Ni, false, sc);
   }
   {
     lirec_gemm_problem g = mk_problem(Ni, hw, true, false);
@@ -676,7 +686,7 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
 
   // ---- stage G: gate wgrad/bgrad + dgrad to the two concat features --------------
   if (d.gates) {
-    pr.clear();
+    pr = head_red;
     for (int h = 0; h < 2; ++h)  // columns [0,F) multiply the context feature, [F,2F) the ints feature
       push_reduction(pr, wgrad_t(Gd, F, dpg, w.f2[h ? 0 : 1], 2 * F, 2 * F, 0, F, Ni, 1.f, P.gate.grad_w + h * F,
                                  2 * F), Gd, F, Ni, true, sc);
@@ -704,15 +714,20 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
   }
 
   // ---- stage L2: second-layer wgrad/bgrad + dgrad to the expanded rows ------------
+  // Same deferral: the second-layer parameter gradients run in the first-layer launch (which only waits for the
+  // scatter-reduce of this stage's DATA gradients), leaving this launch the eight short data-gradient GEMMs.
   pr.clear();
+  std::vector<lirec_gemm_problem> l2_red;
+  const bool defer_l2 = defer_reductions();
+  std::vector<lirec_gemm_problem>& lr = defer_l2 ? l2_red : pr;
   for (int br = 0; br < nbr; ++br) {
     const lirec_encoder& enc = br ? P.enc_ctx : P.enc_ints;
     for (int s = 0; s < 4; ++s) {
       if (!d.act[s]) continue;
       const TGrad dz{w.dz2T[br], 2 * F, NiP, d.cs[s], F + d.cs[s]};
-      push_reduction(pr, wgrad_t(d.outw[s], J, dz, w.a2[br], 8 * J, 8 * J, s * 2 * J, s * 2 * J + J, Ni, keep_scale,
+      push_reduction(lr, wgrad_t(d.outw[s], J, dz, w.a2[br], 8 * J, 8 * J, s * 2 * J, s * 2 * J + J, Ni, keep_scale,
                                  enc.l2[s].grad_w, J), d.outw[s], J, Ni, true, sc);
-      push_reduction(pr, bgrad_t(d.outw[s], dz, br ? w.flagT : w.onesT, Ni, enc.l2[s].grad_b), d.outw[s], 1, Ni,
+      push_reduction(lr, bgrad_t(d.outw[s], dz, br ? w.flagT : w.onesT, Ni, enc.l2[s].grad_b), d.outw[s], 1, Ni,
                      false, sc);
       lirec_gemm_problem g = mk_problem(Ni, J, true, false);
       if (inplace) add_dgrad_passes_inplace(g, dz, Ni, enc.l2[s].w_bf16, d.outw[s], J, 0);
@@ -756,7 +771,7 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
   }
 
   // ---- stage L1: first-layer wgrad/bgrad on the unique rows (inputs carry no grad) ----
-  pr.clear();
+  pr = l2_red;
   for (int br = 0; br < nbr; ++br) {
     const lirec_encoder& enc = br ? P.enc_ctx : P.enc_ints;
     const int ncl = br ? d.nc : d.nci, ntr = br ? d.nt : d.nti;

@@ -73,33 +73,37 @@ def broadcast_params(flat_param, src=0):
 
 
 class SwitchReduceAdam:
-    """Gradient exchange + Adam of one step as two buckets, the first overlapped with backward.
+    """Gradient exchange + Adam of one data-parallel step on NVSwitch multicast (no NCCL call on the step).
 
         fused = SwitchReduceAdam.attach(model, optimizer)      # collective; None if unsupported
         ...
         train_step(model, loss, optimizer, pb, world, fused)   # lirec_b200/mlp/train.py drives it
 
-    The flat parameter buffer is laid out [ints encoder | ctx encoder | gate | out_ints | out_ctx]
-    (construction order, lirec_b200/mlp/model.py:_build).  Bucket 0 = gate + heads (53 % of the weights):
-    lirec_model_backward_ex records an event as soon as those gradients are final, ~0.6 ms before backward
-    ends at 1024 clips per GPU, and this bucket's chain — in-switch exchange (lirec_dp_exchange: barrier,
-    multimem.ld_reduce / multimem.st of this rank's shard, barrier) followed by lirec_adam_flat over the
-    bucket — runs on a high-priority side stream while the second-layer / first-layer stages of backward go
-    on.  Nothing those stages read (encoder weights, activations, the feature banks) is written by it.
-    Bucket 1 = the encoders: same chain on the main stream after backward.  The step ends with the main
-    stream waiting for the side chain.
+    mode 'shard' (default): ONE pass after backward, lirec_dp_reduce_adam_bcast — every rank sums its 1/world
+    shard of the gradients inside the switch, applies Adam to that shard (it owns the shard's moments) and
+    multicast-stores the new fp32 parameters and their bf16 shadow into every replica.  Parameters, bf16 shadow
+    and gradients therefore live in ONE symmetric allocation; `optimizer.state_dict()` gathers the moments.
+    Against exchange-then-Adam this removes the 553 MB full-replica optimizer pass from every rank's critical
+    path and sends 6 bytes per parameter back instead of 4.
 
-    world == 1 (`attach(..., single_gpu=True)`): no exchange, only the bucket-0 Adam pass overlapped.
+    mode 'bucket': the gradient sum (lirec_dp_exchange) and a full-replica lirec_adam_flat per bucket, the
+    gate + head bucket on a side stream behind the event lirec_model_backward_ex records when those gradients
+    are final (measured: the overlap buys < 1 % — the overlapped Adam pass competes with the L2-bound encoder
+    stages for the same memory system — and the exchange alone is slower than NCCL's at 2 ranks).
+
+    world == 1 (`attach(..., single_gpu=True)`): no exchange; only 'bucket' mode's overlapped Adam (off by
+    default: it measured 0.8 % slower than the plain Adam launch).
     torch.distributed._symmetric_memory only allocates and rendezvous-es the buffers."""
 
     overlap = True
 
-    def __init__(self, model, optimizer, grad=None, hdl=None, flags=None, flag_hdl=None):
+    def __init__(self, model, optimizer, hdl=None, flags=None, flag_hdl=None, mode="bucket", offsets=None):
         self.model, self.optimizer = model, optimizer
-        self.grad, self.hdl, self.flags, self.flag_hdl = grad, hdl, flags, flag_hdl
+        self.hdl, self.flags, self.flag_hdl, self.mode = hdl, flags, flag_hdl, mode
+        self.offsets = offsets or {}
         self.rank, self.world = (hdl.rank, hdl.world_size) if hdl is not None else (0, 1)
         dev = model._flat.device
-        self.side = torch.cuda.Stream(device=dev, priority=-1)
+        self.side = torch.cuda.Stream(device=dev)
         self.ev_heads = torch.cuda.Event()
         self.ev_done = torch.cuda.Event()
         self.ev_heads.record()                       # creates the cudaEvent_t the library re-records
@@ -109,6 +113,8 @@ class SwitchReduceAdam:
         self.split = int(model._offsets[names.index(first)])
         self.n = int(model._flat.numel())
         assert self.split % 64 == 0 and self.n % 64 == 0
+        if self.world > 1 and mode == "shard":
+            optimizer._shard_sync = self.gather_moments
 
     @staticmethod
     def supported(device):
@@ -120,10 +126,11 @@ class SwitchReduceAdam:
             return False
 
     @classmethod
-    def attach(cls, model, optimizer, single_gpu=False):
-        """Move the model's flat gradient buffer into symmetric memory (collective over the world group).
+    def attach(cls, model, optimizer, single_gpu=False, mode=None):
+        """Move the model's flat buffers into symmetric memory (collective over the world group).
         Returns None — and leaves everything as it was — without FlatAdam, without multicast, or on a single
         rank (unless single_gpu=True: then only the overlapped bucket-0 Adam is set up)."""
+        import os
         from lirec_b200 import _ext
         from lirec_b200.mlp.model import FlatAdam
         if not isinstance(optimizer, FlatAdam):
@@ -131,6 +138,7 @@ class SwitchReduceAdam:
         model._sync_flat()
         if world_size() < 2:
             return cls(model, optimizer) if single_gpu else None
+        mode = mode or os.environ.get("LIREC_DP_MODE", "shard")
         dev = model._flat.device
         ok = torch.tensor([1 if cls.supported(dev) else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
@@ -139,51 +147,94 @@ class SwitchReduceAdam:
         import torch.distributed._symmetric_memory as symm_mem
         group = dist.group.WORLD
         n = model._flat.numel()
-        grad = symm_mem.empty(n, dtype=torch.float32, device=dev)
-        hdl = symm_mem.rendezvous(grad, group)
-        words = int(_ext.lib().lirec_dp_flag_words(dist.get_world_size()))
-        flags = symm_mem.empty(max(64, words), dtype=torch.int32, device=dev)
-        flag_hdl = symm_mem.rendezvous(flags, group)
+        words = max(64, int(_ext.lib().lirec_dp_flag_words(dist.get_world_size())))
+        # one symmetric allocation: [gradients fp32 | parameters fp32 | bf16 shadow | flags], 256-byte aligned parts
+        sizes = [4 * n, 4 * n if mode == "shard" else 0, 2 * n if mode == "shard" else 0, 4 * words]
+        offs, total = [], 0
+        for sz in sizes:
+            offs.append(total)
+            total += (sz + 255) // 256 * 256
+        buf = symm_mem.empty(total, dtype=torch.uint8, device=dev)
+        hdl = symm_mem.rendezvous(buf, group)
         if not hdl.multicast_ptr:
             return None
-        grad.zero_()
-        flags.zero_()
-        model.use_grad_buffer(grad)
+        buf.zero_()
+        grad = buf[offs[0]:offs[0] + 4 * n].view(torch.float32)
+        flags = buf[offs[3]:offs[3] + 4 * words].view(torch.int32)
+        flat = bf16 = None
+        if mode == "shard":
+            flat = buf[offs[1]:offs[1] + 4 * n].view(torch.float32)
+            bf16 = buf[offs[2]:offs[2] + 2 * n].view(torch.bfloat16)
+        model.use_buffers(flat=flat, grad=grad, bf16=bf16)
+        # device array of every rank's flag buffer (peer pointers of the one allocation + the flags' offset)
+        ptrs = torch.tensor([int(hdl.buffer_ptrs[r]) + offs[3] for r in range(hdl.world_size)], dtype=torch.int64,
+                            device=dev)
+        bases = torch.tensor([int(hdl.buffer_ptrs[r]) for r in range(hdl.world_size)], dtype=torch.int64, device=dev)
         torch.cuda.synchronize(dev)
         dist.barrier()
-        return cls(model, optimizer, grad, hdl, flags, flag_hdl)
+        self = cls(model, optimizer, hdl, flags, None, mode, dict(grad=offs[0], flat=offs[1], bf16=offs[2]))
+        self._buf, self._flag_ptrs, self._bases = buf, ptrs, bases
+        # transport of the 'shard' pass: plain peer loads / stores at 2 ranks, the switch (multimem) from 4 on
+        self.transport = os.environ.get("LIREC_DP_TRANSPORT") or ("peer" if hdl.world_size == 2 else "multimem")
+        return self
 
     def detach(self):
-        """Give the model an ordinary gradient buffer again (the symmetric allocation is released with this
-        object)."""
+        """Give the model ordinary buffers again (the symmetric allocation is released with this object)."""
         torch.cuda.synchronize()
-        if self.grad is not None and self.model is not None and self.model._flat_grad is self.grad:
-            self.model.use_grad_buffer(torch.zeros_like(self.model._flat))
-        self.model._heads_event = None
+        m = self.model
+        if m is not None and self.hdl is not None:
+            if self.mode == "shard":
+                self.gather_moments()
+            m.use_buffers(flat=torch.empty_like(m._flat) if self.mode == "shard" else None,
+                          grad=torch.empty_like(m._flat_grad),
+                          bf16=torch.empty_like(m._flat_bf16) if self.mode == "shard" else None)
+        if m is not None:
+            m._heads_event = None
+        if self.optimizer is not None and getattr(self.optimizer, "_shard_sync", None) is not None:
+            self.optimizer._shard_sync = None
         self.model = self.optimizer = None
+
+    def shard_range(self, rank=None):
+        """[begin, end) in floats of the shard a rank owns in 'shard' mode."""
+        r = self.rank if rank is None else rank
+        n4 = self.n // 4
+        return 4 * (n4 * r // self.world), 4 * (n4 * (r + 1) // self.world)
+
+    @torch.no_grad()
+    def gather_moments(self):
+        """'shard' mode: every rank receives the Adam moments of all shards (checkpoints, mode switches)."""
+        if self.world < 2 or self.mode != "shard":
+            return
+        o = self.optimizer
+        for r in range(self.world):
+            a, b = self.shard_range(r)
+            dist.broadcast(o._m[a:b], src=r)
+            dist.broadcast(o._v[a:b], src=r)
 
     # ---- per-step protocol --------------------------------------------------------------------------
     def arm(self, equal_shards=True):
-        """Before backward: ask lirec_model_backward_ex for the heads-final event (only when this step's
-        exchange needs no host-side re-weighting)."""
-        self._armed = bool(self.overlap and equal_shards and 0 < self.split < self.n)
+        """Before backward ('bucket' mode): ask lirec_model_backward_ex for the heads-final event (only when this
+        step's exchange needs no host-side re-weighting)."""
+        self._armed = bool(self.mode == "bucket" and self.overlap and equal_shards and 0 < self.split < self.n)
         self.model._heads_event = self.ev_heads if self._armed else None
         return self._armed
+
+    def _mc(self, what):
+        return int(self.hdl.multicast_ptr) + self.offsets[what]
 
     def _bucket(self, off, n, channel, stream, scale):
         from lirec_b200 import ops
         m, o = self.model, self.optimizer
         g = o.param_groups[0]
         if self.world > 1:
-            ops.dp_exchange(self.hdl.multicast_ptr, off, n, self.rank, self.world, self.flag_hdl.buffer_ptrs_dev,
-                            channel, stream)
+            ops.dp_exchange(self._mc("grad"), off, n, self.rank, self.world, self._flag_ptrs.data_ptr(), channel, stream)
         ops.adam_flat(m._flat, m._flat_grad, o._m, o._v, m._flat_bf16, g["lr"], g["betas"][0], g["betas"][1],
                       g["eps"], g["weight_decay"], o._t, scale, offset=off, n=n, stream=stream)
 
     @torch.no_grad()
     def step(self, local_clips=None, global_clips=None):
-        """After backward: exchange + Adam of every bucket.  If `arm()` armed this step, bucket 0 runs on the
-        side stream behind the event backward recorded; otherwise everything runs on the current stream."""
+        """After backward: the exchange + Adam of the step."""
+        from lirec_b200 import ops
         m, o = self.model, self.optimizer
         scale = 1.0 / self.world
         armed = bool(getattr(self, "_armed", False))
@@ -195,7 +246,18 @@ class SwitchReduceAdam:
             scale = 1.0
         o._t += 1
         main = torch.cuda.current_stream()
-        if armed:
+        if self.world > 1 and self.mode == "shard":
+            g = o.param_groups[0]
+            if self.transport == "peer" and self.world in (2, 4, 8):
+                ops.dp_reduce_adam_bcast_peer(self._bases.data_ptr(), self.offsets["grad"], self.offsets["flat"],
+                                              self.offsets["bf16"], o._m, o._v, self.n, g["lr"], g["betas"][0],
+                                              g["betas"][1], g["eps"], g["weight_decay"], o._t, scale, self.rank,
+                                              self.world, self._flag_ptrs.data_ptr(), 0)
+            else:
+                ops.dp_reduce_adam_bcast(self._mc("grad"), m._flat, self._mc("flat"), self._mc("bf16"), o._m, o._v,
+                                         g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], o._t,
+                                         scale, self.rank, self.world, self._flag_ptrs.data_ptr(), 0)
+        elif armed:
             self.side.wait_event(self.ev_heads)              # recorded mid-backward on the main stream
             self._bucket(self.split, self.n - self.split, 0, self.side, scale)
             self.ev_done.record(self.side)

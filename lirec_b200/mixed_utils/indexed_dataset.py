@@ -668,23 +668,6 @@ def collate_indexed(records, dataset, resident=False):
         if len(ctx_counts) != Ni or int(ctx_counts.sum()) != Nx:
             raise ValueError("collate_indexed: context blocks do not match the candidate rows")
     T = dataset._max_n_tripl if track_models else 1
-    arena = np.empty(int(L.lirec_collate_arena_bound(B, Ni, Nx, int(has_ctx))), dtype=np.int32)
-    layout = np.empty((24, 2), dtype=np.int64)
-    sizes = np.empty(4, dtype=np.int32)
-    _ext.check(L.lirec_collate_tables(
-        cand.ctypes.data, counts.ctypes.data, B, ctx.ctypes.data if has_ctx else None,
-        ctx_counts.ctypes.data if has_ctx else None, int(dataset.zero_clip), len(dataset.clip_bank),
-        len(dataset.track_bank), int(T), arena.ctypes.data, arena.size, layout.ctypes.data, sizes.ctypes.data))
-    n_clip, n_clip_ints, n_track, n_track_ints = (int(v) for v in sizes)
-    clip_src = arena[layout[22, 0]:layout[22, 0] + n_clip].copy()
-    track_src = arena[layout[23, 0]:layout[23, 0] + n_track].copy()
-    if resident:                                                # banks are gathered on the device
-        clip_bank = torch.empty((n_clip, 0), dtype=torch.bfloat16)
-        track_bank = torch.empty((n_track, 0), dtype=torch.bfloat16)
-    else:                                                       # gather the rows from the bf16 copy of the banks
-        clip16, track16 = _banks_bf16(dataset)
-        clip_bank = clip16.index_select(0, torch.from_numpy(clip_src).long())
-        track_bank = track16.index_select(0, torch.from_numpy(track_src).long())
     rels_label = None
     if has_ctx and track_models:
         rels_label = np.concatenate([np.asarray(r["rels_label"]).reshape(-1) for r in records])
@@ -695,11 +678,43 @@ def collate_indexed(records, dataset, resident=False):
     mw = np.concatenate([r["multilab_weights"] for r in records]).reshape(B, -1) if "multilab_weights" in records[0] \
         else np.ones((B, dataset.n_classes))
     extras = {k: np.array([r[k] for r in records]) for k in ("just_zeros", "n_names", "hash_rel") if k in records[0]}
+    return collate_arrays(dataset, cand, counts, ctx if has_ctx else None, ctx_counts if has_ctx else None,
+                          [r["labels"] for r in records], rels_label, gt, mw, extras, T, records[0]["n_ctx_slots"],
+                          resident)
+
+
+def collate_arrays(dataset, cand, counts, ctx, ctx_counts, labels, rels_label, gt, multilab, extras, n_slots,
+                   n_ctx_slots, resident):
+    """The batch-level half of `collate_indexed`: the concatenated index triples of B clips (int32, C-contiguous)
+    -> every integer table by `lirec_collate_tables`, in one arena, -> host PackedBatch.  `ctx is None`: no
+    context branch."""
+    from lirec_b200 import _ext
+    L = _ext.lib()
+    B, Ni = int(len(counts)), int(cand.shape[0])
+    has_ctx = ctx is not None
+    Nx = int(ctx.shape[0]) if has_ctx else 0
+    arena = np.empty(int(L.lirec_collate_arena_bound(B, Ni, Nx, int(has_ctx))), dtype=np.int32)
+    layout = np.empty((24, 2), dtype=np.int64)
+    sizes = np.empty(4, dtype=np.int32)
+    _ext.check(L.lirec_collate_tables(
+        cand.ctypes.data, counts.ctypes.data, B, ctx.ctypes.data if has_ctx else None,
+        ctx_counts.ctypes.data if has_ctx else None, int(dataset.zero_clip), len(dataset.clip_bank),
+        len(dataset.track_bank), int(n_slots), arena.ctypes.data, arena.size, layout.ctypes.data, sizes.ctypes.data))
+    n_clip, n_clip_ints, n_track, n_track_ints = (int(v) for v in sizes)
+    src = (int(layout[22, 0]), n_clip, int(layout[23, 0]), n_track)
+    clip_src = arena[src[0]:src[0] + n_clip]
+    track_src = arena[src[2]:src[2] + n_track]
+    if resident:                                                # banks are gathered on the device
+        clip_bank = torch.empty((n_clip, 0), dtype=torch.bfloat16)
+        track_bank = torch.empty((n_track, 0), dtype=torch.bfloat16)
+    else:                                                       # gather the rows from the bf16 copy of the banks
+        clip16, track16 = _banks_bf16(dataset)
+        clip_bank = clip16.index_select(0, torch.from_numpy(clip_src).long())
+        track_bank = track16.index_select(0, torch.from_numpy(track_src).long())
     pb = PackedBatch.from_arena(
         arena, layout[:22], clip_bank, track_bank, n_clip_ints, n_track_ints, B, Ni, Nx if has_ctx else None,
-        [r["labels"] for r in records], rels_label, gt, mw, n_slots=T,
-        n_ctx_slots=records[0]["n_ctx_slots"], extras=extras)
-    pb.extras["bank_rows"] = (clip_src, track_src)
+        labels, rels_label, gt, multilab, n_slots=n_slots, n_ctx_slots=n_ctx_slots, extras=extras, src_layout=src)
+    pb.extras["bank_rows"] = (clip_src, track_src)              # views into the arena: they travel (and pin) with it
     return pb
 
 
@@ -802,11 +817,16 @@ class ResidentBanks:
     def stage(self, pb, non_blocking=True):
         """Host PackedBatch from `collate_indexed` -> device PackedBatch whose banks were gathered on the GPU."""
         from lirec_b200 import ops
-        if not hasattr(pb, "_bank_rows_pinned"):
-            pb._pin_bank_rows()
-        idx_c = pb._bank_rows_pinned[0].to(self.device, non_blocking=non_blocking)
-        idx_t = pb._bank_rows_pinned[1].to(self.device, non_blocking=non_blocking)
         dev = pb.to_device(self.device, non_blocking=non_blocking, banks=False)
+        src = getattr(pb, "_src_layout", None)
+        if src is not None:                                     # the row lists crossed PCIe inside the arena
+            idx_c = dev._arena_dev[src[0]:src[0] + src[1]]
+            idx_t = dev._arena_dev[src[2]:src[2] + src[3]]
+        else:
+            if not hasattr(pb, "_bank_rows_pinned"):
+                pb._pin_bank_rows()
+            idx_c = pb._bank_rows_pinned[0].to(self.device, non_blocking=non_blocking)
+            idx_t = pb._bank_rows_pinned[1].to(self.device, non_blocking=non_blocking)
         dev.clip_bank = ops.gather_rows(self.clip, idx_c)
         dev.track_bank = ops.gather_rows(self.track, idx_t)
         dev._bank_idx = (idx_c, idx_t)

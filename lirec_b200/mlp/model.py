@@ -188,12 +188,30 @@ class _HotPath(nn.Module):
     def use_grad_buffer(self, buf):
         """Adopt `buf` (flat fp32, same size) as the gradient buffer — e.g. symmetric memory for the
         in-switch data-parallel reduction (lirec_b200/dp.py:SwitchReduceAdam)."""
+        self.use_buffers(grad=buf)
+
+    def use_buffers(self, flat=None, grad=None, bf16=None):
+        """Adopt caller-owned storage (same sizes, same device) for the flat fp32 parameters, the flat gradient
+        buffer and / or the bf16 shadow — symmetric memory for the in-switch data-parallel step
+        (lirec_b200/dp.py:SwitchReduceAdam).  Contents are carried over; every nn.Parameter is re-pointed."""
         self._sync_flat()
-        assert buf.dtype == torch.float32 and buf.numel() == self._flat.numel() and buf.device == self._flat.device
-        buf.copy_(self._flat_grad)
-        self._flat_grad = buf
-        for p in self._param_list:
-            p.grad = None
+        n, dev = self._flat.numel(), self._flat.device
+        for buf, dt in ((flat, torch.float32), (grad, torch.float32), (bf16, torch.bfloat16)):
+            assert buf is None or (buf.dtype == dt and buf.numel() == n and buf.device == dev and buf.is_contiguous())
+        with torch.no_grad():
+            if flat is not None:
+                flat.copy_(self._flat)
+                for p, off in zip(self._param_list, self._offsets):
+                    p.data = flat[off:off + p.numel()].view(p.shape)
+                self._flat = flat
+            if bf16 is not None:
+                bf16.copy_(self._flat_bf16)
+                self._flat_bf16 = bf16
+            if grad is not None:
+                grad.copy_(self._flat_grad)
+                self._flat_grad = grad
+                for p in self._param_list:
+                    p.grad = None
         self._build_structs()
 
     def _grad_view(self, i):
@@ -690,6 +708,9 @@ class FlatAdam(torch.optim.Optimizer):
             st["step"].fill_(float(self._t))
 
     def state_dict(self):
+        sync = getattr(self, "_shard_sync", None)        # data parallel, sharded moments: gather them first
+        if sync is not None:
+            sync()
         self._sync_steps()
         return super().state_dict()
 

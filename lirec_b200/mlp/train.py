@@ -73,7 +73,7 @@ def training(train_dataset, **kwargs):
             loss.set_rank(rank)
         if int(getattr(opt, "dp_switch_reduce", 1)):
             fused = dp.SwitchReduceAdam.attach(model, optimizer)     # None without NVSwitch multicast / FlatAdam
-    if fused is None and world == 1 and int(getattr(opt, "overlap_adam", 1)):
+    if fused is None and world == 1 and int(getattr(opt, "overlap_adam", 0)):
         fused = dp.SwitchReduceAdam.attach(model, optimizer, single_gpu=True)    # None unless FlatAdam
     batch_time, data_time, losses = Averaging(), Averaging(), Averaging()
     print("epochs: %s", opt.epochs)

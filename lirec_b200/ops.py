@@ -12,7 +12,7 @@ from ._ext import (ACT_NONE, ACT_RELU, ACT_TANH, OUT_F32, OUT_SPLIT, OUT_SPLIT_T
                    POST_NONE)
 
 __all__ = ["gemm_problem", "gemm_grouped", "seg_reduce", "seg_softmax_pool", "seg_softmax_pool_bwd", "SegSoftmaxPool", "rows_expand_fwd", "rows_expand_bwd", "split_f32",
-           "cast_bf16", "gather_rows", "roi_max_pool", "loss_track", "loss_rowmargin", "loss_ce", "predict_tracks", "adam_flat", "dp_exchange", "dropout_desc"]
+           "cast_bf16", "gather_rows", "roi_max_pool", "loss_track", "loss_rowmargin", "loss_ce", "predict_tracks", "adam_flat", "dp_exchange", "dp_reduce_adam_bcast", "dp_reduce_adam_bcast_peer", "dropout_desc"]
 
 
 def dropout_desc(p=0.0, seed=0, stream_id=0, col_off=0):
@@ -262,6 +262,30 @@ def adam_flat(param, grad, exp_avg, exp_avg_sq, param_bf16, lr, beta1, beta2, ep
                                  (_ext.ptr(param_bf16) + 2 * offset) if param_bf16 is not None else None, int(n),
                                  float(lr), float(beta1), float(beta2),
                                  float(eps), float(weight_decay), int(step), float(grad_scale), sp))
+
+
+def dp_reduce_adam_bcast(grad_mc, param, param_mc, bf16_mc, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay,
+                         step, grad_scale, rank, world, flag_ptrs_dev, channel, stream=None):
+    """In-switch gradient sum of this rank's shard + Adam on the shard + multicast of the new parameters and their
+    bf16 shadow to every rank (lirec_dp_reduce_adam_bcast)."""
+    L = _ext.lib()
+    sp = _ext.stream_ptr() if stream is None else C.c_void_p(stream.cuda_stream)
+    _ext.check(L.lirec_dp_reduce_adam_bcast(
+        C.c_void_p(int(grad_mc)), _ext.ptr(param), C.c_void_p(int(param_mc)), C.c_void_p(int(bf16_mc)),
+        _ext.ptr(exp_avg), _ext.ptr(exp_avg_sq), param.numel(), float(lr), float(beta1), float(beta2), float(eps),
+        float(weight_decay), int(step), float(grad_scale), int(rank), int(world), C.c_void_p(int(flag_ptrs_dev)),
+        int(channel), sp))
+
+
+def dp_reduce_adam_bcast_peer(peer_bases_dev, grad_off, param_off, bf16_off, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                              weight_decay, step, grad_scale, rank, world, flag_ptrs_dev, channel, stream=None):
+    """lirec_dp_reduce_adam_bcast over plain peer pointers (P2P loads / stores instead of multicast)."""
+    L = _ext.lib()
+    sp = _ext.stream_ptr() if stream is None else C.c_void_p(stream.cuda_stream)
+    _ext.check(L.lirec_dp_reduce_adam_bcast_peer(
+        C.c_void_p(int(peer_bases_dev)), int(grad_off), int(param_off), int(bf16_off), _ext.ptr(exp_avg),
+        _ext.ptr(exp_avg_sq), int(n), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+        float(grad_scale), int(rank), int(world), C.c_void_p(int(flag_ptrs_dev)), int(channel), sp))
 
 
 def dp_exchange(grad_multicast_ptr, offset, n, rank, world, flag_ptrs_dev, channel, stream=None):

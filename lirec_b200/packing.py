@@ -183,7 +183,7 @@ class PackedBatch:
 
     @staticmethod
     def from_arena(arena, layout, clip_bank, track_bank, n_clip_ints, n_track_ints, B, Ni, Nx, labels, rels_label,
-                   gt_tracks, multilab, n_slots=20, n_ctx_slots=18, extras=None):
+                   gt_tracks, multilab, n_slots=20, n_ctx_slots=18, extras=None, src_layout=None):
         """A host batch whose integer tables already lie in one int32 arena in `_INT_TABLES` order
         (`lirec_collate_tables`, csrc/collate.cu): `layout[i] = (offset, length)` of table i, length -1 =
         absent.  The tables are views into the arena, so `pin()` is a single copy.  Nx is None without a
@@ -211,6 +211,10 @@ class PackedBatch:
         t["gt_tracks"][:] = np.asarray(gt_tracks).reshape(B, 2)
         if pb.has_ctx:
             t["rels_label"][:] = np.asarray(rels_label).reshape(Ni)
+        if src_layout is not None:                 # (clip offset, n, track offset, n): the dataset-bank row lists
+            assert src_layout[0] >= end and src_layout[2] >= src_layout[0] + src_layout[1]
+            end = src_layout[2] + src_layout[3]
+            pb._src_layout = tuple(int(v) for v in src_layout)
         pb._host_arena, pb._host_layout = arena[:end], host_layout
         pb.extras = dict(extras or {})
         return pb
@@ -230,7 +234,10 @@ class PackedBatch:
             rows = st.get("extras", {}).get("bank_rows")
             if rows is not None:
                 st["extras"] = dict(st["extras"])
-                st["extras"]["bank_rows"] = tuple(torch.from_numpy(np.ascontiguousarray(r)) for r in rows)
+                if st.get("_src_layout") is not None:      # views of the arena: rebuilt on arrival
+                    st["extras"]["bank_rows"] = None
+                else:
+                    st["extras"]["bank_rows"] = tuple(torch.from_numpy(np.ascontiguousarray(r)) for r in rows)
         return st
 
     def __setstate__(self, st):
@@ -240,6 +247,10 @@ class PackedBatch:
         rows = self.extras.get("bank_rows") if isinstance(self.extras, dict) else None
         if rows is not None and isinstance(rows[0], torch.Tensor):
             self.extras["bank_rows"] = tuple(r.numpy() for r in rows)
+        src = self.__dict__.get("_src_layout")
+        if src is not None and isinstance(self.extras, dict) and self.extras.get("bank_rows", 0) is None:
+            a = self._host_arena
+            self.extras["bank_rows"] = (a[src[0]:src[0] + src[1]], a[src[2]:src[2] + src[3]])
         if self.tables is None:
             self.tables = {k: self._host_arena[off:off + n].reshape(shape)
                            for k, (off, n, shape) in self._host_layout.items()}
@@ -257,6 +268,8 @@ class PackedBatch:
 
     def _pin_bank_rows(self):
         rows = self.extras.get("bank_rows")
+        if getattr(self, "_src_layout", None) is not None:
+            return                                  # the row lists are part of the (pinned) arena
         if rows is not None and not hasattr(self, "_bank_rows_pinned"):
             self._bank_rows_pinned = tuple(torch.from_numpy(np.ascontiguousarray(r)).pin_memory() for r in rows)
 

@@ -4,8 +4,8 @@ NCCL on the same box).  Under torchrun on N >= 2 GPUs of one NVSwitch box:
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/dp_exchange_probe.py
 
 times, with CUDA events and the max over ranks, per step:
-  (a) dp.SwitchReduceAdam.step(): lirec_dp_exchange (barrier, in-switch multimem.ld_reduce / multimem.st, barrier)
-      + lirec_adam_flat over the whole buffer;
+  (a) dp.SwitchReduceAdam.step(): mode 'shard' = lirec_dp_reduce_adam_bcast (in-switch sum of the rank's shard + Adam on
+      it + multicast of the new parameters); mode 'bucket' (LIREC_DP_MODE=bucket) = lirec_dp_exchange + lirec_adam_flat;
   (b) ncclAllReduce(sum, fp32) of the same flat gradient buffer, alone;
   (c) (b) + lirec_adam_flat, the two-launch form the fused kernel replaces;
   (d) lirec_adam_flat alone.
@@ -38,7 +38,7 @@ torch.manual_seed(0)
 with contextlib.redirect_stdout(io.StringIO()):
     model, loss_fn, optimizer = M.create_model(101, n_rels=15)
 dp.broadcast_params(model._flat)
-fused = dp.SwitchReduceAdam.attach(model, optimizer)
+fused = dp.SwitchReduceAdam.attach(model, optimizer, mode=os.environ.get('LIREC_DP_MODE', 'shard'))
 n = model._flat.numel()
 grad = model._flat_grad
 grad.normal_(generator=torch.Generator(device=grad.device).manual_seed(rank))
@@ -85,14 +85,14 @@ def switch_adam():
 
 def switch_only():
     from lirec_b200 import ops
-    ops.dp_exchange(fused.hdl.multicast_ptr, 0, n, rank, world, fused.flag_hdl.buffer_ptrs_dev, 0)
+    ops.dp_exchange(fused._mc("grad"), 0, n, rank, world, fused._flag_ptrs.data_ptr(), 0)
     grad.mul_(1.0 / world)
 
 
 def switch_two_buckets():
     from lirec_b200 import ops
-    ops.dp_exchange(fused.hdl.multicast_ptr, fused.split, n - fused.split, rank, world, fused.flag_hdl.buffer_ptrs_dev, 0)
-    ops.dp_exchange(fused.hdl.multicast_ptr, 0, fused.split, rank, world, fused.flag_hdl.buffer_ptrs_dev, 1)
+    ops.dp_exchange(fused._mc("grad"), fused.split, n - fused.split, rank, world, fused._flag_ptrs.data_ptr(), 0)
+    ops.dp_exchange(fused._mc("grad"), 0, fused.split, rank, world, fused._flag_ptrs.data_ptr(), 1)
     grad.mul_(1.0 / world)
 
 
@@ -102,6 +102,7 @@ res["adam_ms"] = timed(lambda: optimizer.step(grad_scale=1.0))
 res["nccl_allreduce_ms"] = timed(nccl_only) - scale_ms
 res["nccl_allreduce_plus_adam_ms"] = timed(nccl_adam) - scale_ms
 if fused is not None:
+    res["mode"] = fused.mode
     res["switch_reduce_adam_ms"] = timed(switch_adam) - scale_ms
     res["switch_exchange_only_ms"] = timed(switch_only) - scale_ms
     res["switch_exchange_two_buckets_ms"] = timed(switch_two_buckets) - scale_ms

@@ -539,73 +539,22 @@ def run_ours(args):
     if args.only_value:
         if rank == 0:
             sampler.stop()
-            print(json.dumps({"value": value, "ms_per_step": ms_total / steps, "only_value": True}))
+            per = max(1, int(round(len(prof) / float(steps))))
+            launches_ms = [float(np.mean([r[0] for r in prof[j::per]])) for j in range(per)] if prof else []
+            print(json.dumps({"value": value, "ms_per_step": ms_total / steps, "only_value": True,
+                              "gemm_ms_per_step": sum(p[0] for p in prof) / steps,
+                              "gemm_launch_ms": [round(x, 4) for x in launches_ms]}))
         return
 
     copy_stream = torch.cuda.Stream(device=dev)
-    loss_host = torch.empty(max(steps, 1), dtype=torch.float32).pin_memory()
     main = torch.cuda.current_stream()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    # ---------------- end to end through the loader (the headline e2e) ----------------
-    # `packed_loader` over the cached dataset: index-only items, collate_indexed -> lirec_collate_tables in
-    # worker processes, shared-memory hand-over, pinning on the DataLoader's pin thread, async H2D of the int
-    # tables on a copy stream one batch ahead, device gather of the batch banks from the resident dataset
-    # banks, train step, loss read-back.  The iterator is warmed (workers forked, queues primed) by `warmup`
-    # untimed steps; the timed region is the next `steps` batches of the same iterator.
-    from lirec_b200.mixed_utils.classification_dataloader import packed_loader
-    cores = os.cpu_count() or 1
-    workers = args.workers if args.workers >= 0 else max(1, min(6, cores // max(world, 1) - 1))
-    b.opt.prefetch_factor = 2
-
-    def loader(n_steps):
-        # one DataLoader (one set of worker processes) for the whole leg: enough epochs of the rank's dataset,
-        # each its own permutation, chained behind it
-        rep = (n_steps + 2 * workers + 4 + args.n_batches - 1) // args.n_batches + 1
-        return iter(packed_loader(b.dataset, args.batch, shuffle=True, num_workers=workers, device=dev,
-                                  drop_last=True, seed=rank, repeat=rep))
-
-    e2e_err = None
-    e2e_value = e2e_host_rate = None
-    h2d_loader = 0
-    try:
-        it = loader(warmup + steps)
-        for _ in range(warmup):
-            b.step(next(it))
-        b.barrier()
-        if rank == 0:
-            sampler.region(True)
-        e0.record()
-        for i in range(steps):
-            pb = next(it)
-            lv = b.step(pb)
-            loss_host[i:i + 1].copy_(lv.detach().reshape(1), non_blocking=True)
-            if i == 0:
-                from lirec_b200.mixed_utils.indexed_dataset import ResidentBanks
-                h2d_loader = ResidentBanks.h2d_bytes(pb.host)
-        e1.record()
-        b.barrier()
-        if rank == 0:
-            sampler.region(False)
-        assert bool(torch.isfinite(loss_host[:steps]).all()), "e2e: non-finite loss read back"
-        e2e_value = clips_total / (b.max_over_ranks(e0.elapsed_time(e1)) / 1e3)
-        it.close()
-        # the loader alone (items, collate, pin, H2D, device gather — no train step): what the host side sustains
-        b.dataset.epoch = 1000
-        it = loader(min(steps, 24) + 4)
-        for _ in range(4):
-            next(it)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        n_host = 0
-        for _ in range(min(steps, 24)):
-            n_host += next(it).B
-        torch.cuda.synchronize()
-        e2e_host_rate = n_host / (time.perf_counter() - t0)
-        it.close()
-    except Exception as exc:                                     # never lose the headline line over this leg
-        e2e_err = repr(exc)[:300]
-        b.barrier()
+    # The end-to-end regions run max(steps, 100) steps: at the driver's --steps 20 a region is 40 ms, and one 10 ms
+    # hiccup of a worker process or of the pinning thread is a quarter of it.
+    e2e_steps = max(steps, 100)
+    e2e_clips = args.batch * world * e2e_steps
+    loss_host = torch.empty(e2e_steps, dtype=torch.float32).pin_memory()
 
     # ---------------- pre-collated legs (batches built before the clock starts) ----------------
     def run_prefetched(stage_fn, n_steps):
@@ -635,19 +584,90 @@ def run_ours(args):
         e1.record()
         b.barrier()
         assert bool(torch.isfinite(loss_host[:n_steps]).all()), "pre-collated leg: non-finite loss read back"
-        return clips_total / (b.max_over_ranks(e0.elapsed_time(e1)) / 1e3)
+        return args.batch * world * n_steps / (b.max_over_ranks(e0.elapsed_time(e1)) / 1e3)
 
     from lirec_b200.mixed_utils.indexed_dataset import ResidentBanks
     res_bytes = int(np.mean([ResidentBanks.h2d_bytes(h) for h in b.host]))
-    e2e_pre = run_prefetched(lambda i: b.banks.stage(b.host[i % len(b.host)]), steps)
+    e2e_pre = run_prefetched(lambda i: b.banks.stage(b.host[i % len(b.host)]), e2e_steps)
     # streamed: every feature row of every batch crosses PCIe every step (no resident banks)
     b.opt.resident_banks = 0
     full_host = [b.dataset.collate([b.dataset[j] for j in range(i * args.batch, (i + 1) * args.batch)]).pin()
                  for i in range(min(2, args.n_batches))]
     b.opt.resident_banks = 1
     full_bytes = int(np.mean([h.h2d_bytes() for h in full_host]))
-    e2e_streamed = run_prefetched(lambda i: full_host[i % len(full_host)].to_device(dev, non_blocking=True), steps)
+    e2e_streamed = run_prefetched(lambda i: full_host[i % len(full_host)].to_device(dev, non_blocking=True),
+                                  min(e2e_steps, 40))
     del full_host
+
+    # ---------------- end to end through the loader (the headline e2e) ----------------
+    # `packed_loader` over the cached dataset: index-only items, collate -> lirec_collate_tables in worker
+    # processes, shared-memory hand-over, pinning on the DataLoader's pin thread, async H2D of the int tables on
+    # a copy stream one batch ahead, device gather of the batch banks from the resident dataset banks, train step,
+    # loss read-back.  The iterator is warmed (workers forked, queues primed) by `warmup` untimed steps; the
+    # timed region is the next e2e_steps batches of the same iterator.
+    from lirec_b200.mixed_utils.classification_dataloader import packed_loader
+    cores = os.cpu_count() or 1
+    workers = args.workers if args.workers >= 0 else max(1, min(12, (cores - 2 * world) // max(world, 1)))
+    b.opt.prefetch_factor = 2
+
+    def loader(n_steps):
+        # one DataLoader (one set of worker processes) for the whole leg: enough epochs of the rank's dataset,
+        # each its own permutation, chained behind it
+        rep = (n_steps + 2 * workers + 4 + args.n_batches - 1) // args.n_batches + 1
+        return iter(packed_loader(b.dataset, args.batch, shuffle=True, num_workers=workers, device=dev,
+                                  drop_last=True, seed=rank, repeat=rep))
+
+    e2e_err = None
+    e2e_value = e2e_host_rate = None
+    h2d_loader = 0
+    try:
+        it = loader(warmup + e2e_steps)
+        for _ in range(warmup):
+            b.step(next(it))
+        b.barrier()
+        if rank == 0:
+            sampler.region(True)
+        e0.record()
+        t_wait = t_step = 0.0
+        for i in range(e2e_steps):
+            t0 = time.perf_counter()
+            pb = next(it)
+            t1 = time.perf_counter()
+            lv = b.step(pb)
+            loss_host[i:i + 1].copy_(lv.detach().reshape(1), non_blocking=True)
+            t_wait, t_step = t_wait + (t1 - t0), t_step + (time.perf_counter() - t1)
+            if i == 0:
+                h2d_loader = ResidentBanks.h2d_bytes(pb.host)
+        e1.record()
+        b.barrier()
+        if rank == 0:
+            sampler.region(False)
+        assert bool(torch.isfinite(loss_host[:e2e_steps]).all()), "e2e: non-finite loss read back"
+        if os.environ.get("LIREC_BENCH_DEBUG"):
+            print("[rank %d] e2e loader leg: host waited %.2f ms for batches, spent %.2f ms issuing steps (%d steps)"
+                  % (rank, 1e3 * t_wait, 1e3 * t_step, e2e_steps), file=sys.stderr, flush=True)
+        e2e_value = e2e_clips / (b.max_over_ranks(e0.elapsed_time(e1)) / 1e3)
+        it.close()
+        # the loader alone (items, collate, pin, H2D, device gather — no train step): what the host side sustains
+        b.dataset.epoch = 1000
+        it = loader(44)
+        for _ in range(4):
+            next(it)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_host = 0
+        for _ in range(40):
+            n_host += next(it).B
+        torch.cuda.synchronize()
+        e2e_host_rate = n_host / (time.perf_counter() - t0)
+        it.close()
+        del it
+    except Exception as exc:                                     # never lose the headline line over this leg
+        e2e_err = repr(exc)[:300]
+        b.barrier()
+    import gc
+    gc.collect()
+    b.barrier()
 
     # ---------------- inference: forward + device-side prediction arg-maxes (no_grad) ----------------
     from lirec_b200 import ops
@@ -766,7 +786,7 @@ def run_ours(args):
                              "processes, pinning, async H2D of the index tables, device gather from the HBM-resident "
                              "dataset banks, train step and loss read-back inside the timed region" % workers)
                     if e2e_value is not None else "loader leg failed (%s); pre-collated index-only batches" % e2e_err,
-                    "loader_workers": workers, "host_cores": cores,
+                    "loader_workers": workers, "host_cores": cores, "steps": e2e_steps,
                     "loader_only_clips_per_s": e2e_host_rate},
             "e2e_precollated": {"value": e2e_pre, "unit": "clips/s", "h2d_bytes_per_step": int(in_bytes),
                                 "d2h_bytes_per_step": 4,

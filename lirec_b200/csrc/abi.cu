@@ -1,4 +1,5 @@
 // abi.cu — error plumbing and device checks behind the C ABI (include/lirec_b200.h).
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -19,6 +20,15 @@ int fail(int code, const char* fmt, ...) {
 }
 
 void note_launch(int n) { g_launches += n; }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LIREC_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 void reset_launch_count() { g_launches = 0; }
 
 // No CPU fallback and no other architecture: anything but sm_100 is an error.

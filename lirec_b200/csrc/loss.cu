@@ -39,6 +39,8 @@ track_loss_kernel(const float* __restrict__ ints, const float* __restrict__ rels
                   const uint8_t* __restrict__ multilab, lirec_track_loss_cfg cfg,
                   float* __restrict__ loss_per_clip, int32_t* __restrict__ assign,
                   float* __restrict__ d_ints, float* __restrict__ d_rels) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_score[MAX_SLOTS];
   __shared__ float s_red[8];
   __shared__ int s_tstar;
@@ -235,6 +237,8 @@ __global__ void __launch_bounds__(128)
 rowmargin_kernel(const float* __restrict__ logits, int64_t ld, int rows, int C,
                  const int32_t* __restrict__ labels, const uint8_t* __restrict__ weights, float margin,
                  float scale, float* __restrict__ loss_per_row, float* __restrict__ d_logits, int64_t d_ld) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_red[8];
   const int b = blockIdx.x;
   const int y = labels[b];
@@ -399,6 +403,8 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, __nv_bfloat16* __restrict__ pb, int64_t n, float lr, float beta1,
             float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const float step = lr / bc1;
@@ -463,10 +469,9 @@ extern "C" int lirec_loss_track_fwd_bwd(const float* ints, const float* rels, co
   LIREC_REQUIRE(cfg.max_slots > 0 && cfg.max_slots <= loss::MAX_SLOTS, "track loss: max_slots=%d (limit %d)",
                 cfg.max_slots, loss::MAX_SLOTS);
   if (B <= 0) return LIREC_OK;
-  loss::track_loss_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      ints, rels, cand_off, B, labels, rels_label, gt_tracks, multilab, cfg, loss_per_clip, assign, d_ints,
-      d_rels);
-  LIREC_CUDA_OK(cudaGetLastError());
+  LIREC_CUDA_OK(launch_pdl(loss::track_loss_kernel, dim3(B), dim3(128), 0, static_cast<cudaStream_t>(stream), ints, rels,
+                           cand_off, B, labels, rels_label, gt_tracks, multilab, cfg, loss_per_clip, assign, d_ints,
+                           d_rels));
   note_launch();
   return LIREC_OK;
 }
@@ -478,9 +483,8 @@ extern "C" int lirec_loss_rowmargin_fwd_bwd(const float* logits, int64_t ld, int
   LIREC_ENTER();
   LIREC_REQUIRE(logits && labels && loss_per_row && d_logits && C > 0, "rowmargin loss: bad arguments");
   if (rows <= 0) return LIREC_OK;
-  loss::rowmargin_kernel<<<rows, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      logits, ld, rows, C, labels, weights, margin, scale, loss_per_row, d_logits, d_ld);
-  LIREC_CUDA_OK(cudaGetLastError());
+  LIREC_CUDA_OK(launch_pdl(loss::rowmargin_kernel, dim3(rows), dim3(128), 0, static_cast<cudaStream_t>(stream), logits,
+                           ld, rows, C, labels, weights, margin, scale, loss_per_row, d_logits, d_ld));
   note_launch();
   return LIREC_OK;
 }
@@ -522,10 +526,9 @@ extern "C" int lirec_adam_flat(float* param, const float* grad, float* exp_avg, 
   const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), static_cast<double>(step)));
   const float bc2 = static_cast<float>(1.0 - pow(static_cast<double>(beta2), static_cast<double>(step)));
   const int grid = static_cast<int>(std::min<int64_t>((n / 4 + 255) / 256 + 1, 148 * 16));
-  loss::adam_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      param, grad, exp_avg, exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(param_bf16), n, lr, beta1, beta2,
-      eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
-  LIREC_CUDA_OK(cudaGetLastError());
+  LIREC_CUDA_OK(launch_pdl(loss::adam_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), param, grad,
+                           exp_avg, exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(param_bf16), n, lr, beta1, beta2, eps,
+                           weight_decay, bc1, sqrtf(bc2), grad_scale));
   note_launch();
   return LIREC_OK;
 }

@@ -199,6 +199,8 @@ static Workspace carve(const Dims& d, void* base) {
 }
 
 __global__ void fill_bf16_kernel(bf16* p, int64_t n, float v) {
+  pdl_wait();
+  pdl_trigger();
   const bf16 b = __float2bfloat16_rn(v);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     p[i] = b;
@@ -219,6 +221,8 @@ struct ReduceJobs {
 // 128-bit loads in flight), so the big first-layer jobs stream at HBM rate; blockIdx.y selects the job
 // and CTAs beyond a job's size exit at once.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceJobs jobs) {
+  pdl_wait();
+  pdl_trigger();
   const ReduceJob& j = jobs.job[blockIdx.y];
   const int64_t total = (int64_t)j.M * j.N;
   const bool vec = (j.N % 4 == 0) && (j.dst_ld % 4 == 0) && (total % 4 == 0) &&
@@ -334,8 +338,7 @@ int forward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lirec
 
   {  // ones column for the bias-gradient GEMMs
     const int64_t n = d.onesP;
-    fill_bf16_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, stream>>>(w.onesT, n, 1.0f);
-    LIREC_CUDA_OK(cudaGetLastError());
+    LIREC_CUDA_OK(launch_pdl(fill_bf16_kernel, dim3((unsigned)std::min<int64_t>((n + 255) / 256, 1184)), dim3(256), 0, stream, w.onesT, n, 1.0f));
     note_launch();
   }
 
@@ -468,8 +471,7 @@ int forward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lirec
     if (jobs.n > 0) {
       const int64_t total = (int64_t)d.Ni * d.C;
       dim3 grid((unsigned)((total + 1023) / 1024), jobs.n);
-      reduce_partials_kernel<<<grid, 256, 0, stream>>>(jobs);
-      LIREC_CUDA_OK(cudaGetLastError());
+      LIREC_CUDA_OK(launch_pdl(reduce_partials_kernel, grid, dim3(256), 0, stream, jobs));
       note_launch();
     }
   }
@@ -578,8 +580,7 @@ static int flush_partials(SplitCtx& sc, cudaStream_t stream) {
     int64_t biggest = 0;
     for (int i = 0; i < sc.jobs.n; ++i) biggest = std::max<int64_t>(biggest, (int64_t)sc.jobs.job[i].M * sc.jobs.job[i].N);
     dim3 grid((unsigned)((biggest + 1023) / 1024), sc.jobs.n);
-    reduce_partials_kernel<<<grid, 256, 0, stream>>>(sc.jobs);
-    LIREC_CUDA_OK(cudaGetLastError());
+    LIREC_CUDA_OK(launch_pdl(reduce_partials_kernel, grid, dim3(256), 0, stream, sc.jobs));
     note_launch();
     sc.jobs.n = 0;
   }

@@ -112,6 +112,8 @@ __device__ __forceinline__ void store_split4(__nv_bfloat16* hi_ptr, __nv_bfloat1
 constexpr int EF_IDX = 96;     // row triples of a segment staged in shared memory (longer segments read the rest in place)
 __global__ void __launch_bounds__(128)
 expand_fwd_kernel(const ExpandFwdJobs jobs) {
+  pdl_wait();
+  pdl_trigger();
   const ExpandFwdJob& jb = jobs.job[blockIdx.y];
   const int o = blockIdx.x;
   if (o >= jb.n_out) return;
@@ -187,6 +189,8 @@ expand_fwd_kernel(const ExpandFwdJobs jobs) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 expand_bwd_kernel(const ExpandBwdJobs jobs) {
+  pdl_wait();
+  pdl_trigger();
   const ExpandBwdJob& jb = jobs.job[blockIdx.y];
   const int u = blockIdx.x;
   if (u >= jb.n_unique) return;
@@ -253,6 +257,8 @@ constexpr int EBT_ZSPLIT = LIREC_EBT_ZSPLIT;   // references cached in shared me
 #endif
 __global__ void __launch_bounds__(256, LIREC_EBT_MIN_BLOCKS)
 expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
+  pdl_wait();
+  pdl_trigger();
   const ExpandBwdJob& jb = jobs.job[blockIdx.y];
   const int u0 = blockIdx.x * EBT_ROWS;
   if (u0 >= jb.n_unique) return;
@@ -374,6 +380,8 @@ expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
 __global__ void __launch_bounds__(256)
 split_t_kernel(const float* __restrict__ x, int64_t ld, int rows, int cols, __nv_bfloat16* __restrict__ out,
                int64_t pitch, int pad) {
+  pdl_wait();
+  pdl_trigger();
   const int c = blockIdx.y;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
     const float v = (c < cols) ? x[static_cast<int64_t>(r) * ld + c] : 0.f;
@@ -390,6 +398,8 @@ split_t_kernel(const float* __restrict__ x, int64_t ld, int rows, int cols, __nv
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 transpose_bf16_kernel(const TransposeJobs jobs) {
+  pdl_wait();
+  pdl_trigger();
   const TransposeJob& jb = jobs.job[blockIdx.y];
   const int tiles_c = (jb.C + 63) / 64, tiles_r = (jb.Rp + 63) / 64;
   __shared__ __nv_bfloat16 tile[64][64 + 2];
@@ -663,8 +673,7 @@ int expand_fwd(const ExpandFwdJobs& jobs, cudaStream_t stream) {
   }
   if (max_out == 0 || jobs.n == 0) return LIREC_OK;
   dim3 grid(max_out, jobs.n);
-  expand_fwd_kernel<<<grid, 128, 0, stream>>>(jobs);
-  LIREC_CUDA_OK(cudaGetLastError());
+  LIREC_CUDA_OK(launch_pdl(expand_fwd_kernel, grid, dim3(128), 0, stream, jobs));
   note_launch();
   return LIREC_OK;
 }
@@ -695,10 +704,10 @@ int expand_bwd(const ExpandBwdJobs& jobs, cudaStream_t stream) {
     const int row_ctas = (max_u + EBT_ROWS - 1) / EBT_ROWS;
     const int zsplit = (static_cast<long>(row_ctas) * jobs.n * EBT_ZSPLIT <= 2048) ? 2 * EBT_ZSPLIT : EBT_ZSPLIT;
     dim3 grid(row_ctas, jobs.n, std::max(1, std::min(zsplit, max_j / EBT_COLS)));
-    expand_bwd_t_kernel<<<grid, 256, 0, stream>>>(jobs);
+    LIREC_CUDA_OK(launch_pdl(expand_bwd_t_kernel, grid, dim3(256), 0, stream, jobs));
   } else {
     dim3 grid(max_u, jobs.n);
-    expand_bwd_kernel<<<grid, 128, 0, stream>>>(jobs);
+    LIREC_CUDA_OK(launch_pdl(expand_bwd_kernel, grid, dim3(128), 0, stream, jobs));
   }
   LIREC_CUDA_OK(cudaGetLastError());
   note_launch();
@@ -711,8 +720,7 @@ int split_f32_t(const float* x, int64_t ld, int rows, int cols, void* out, int64
                 (long long)pitch, rows);
   if (rows <= 0) return LIREC_OK;
   dim3 grid(std::min((rows + 255) / 256, 64), pad);
-  split_t_kernel<<<grid, 256, 0, stream>>>(x, ld, rows, cols, reinterpret_cast<__nv_bfloat16*>(out), pitch, pad);
-  LIREC_CUDA_OK(cudaGetLastError());
+  LIREC_CUDA_OK(launch_pdl(split_t_kernel, grid, dim3(256), 0, stream, x, ld, rows, cols, reinterpret_cast<__nv_bfloat16*>(out), pitch, pad));
   note_launch();
   return LIREC_OK;
 }
@@ -727,8 +735,7 @@ int transpose_bf16(const TransposeJobs& jobs, cudaStream_t stream) {
     max_tiles = std::max(max_tiles, ((j.C + 63) / 64) * ((j.Rp + 63) / 64));
   }
   dim3 grid(std::min(max_tiles, 148 * 4), jobs.n);
-  transpose_bf16_kernel<<<grid, 256, 0, stream>>>(jobs);
-  LIREC_CUDA_OK(cudaGetLastError());
+  LIREC_CUDA_OK(launch_pdl(transpose_bf16_kernel, grid, dim3(256), 0, stream, jobs));
   note_launch();
   return LIREC_OK;
 }

@@ -21,6 +21,8 @@ without `opt.synthetic` the dataset refuses to construct instead of pretending.
                   MovieGraphs annotations would take; `--resident_banks 1` keeps the split's pooled feature
                   banks in HBM so a batch ships only index tables.
 """
+import os
+
 import torch
 from torch.utils.data import Dataset
 
@@ -156,7 +158,8 @@ def packed_loader(dataset, batch_size, shuffle, num_workers=0, device="cuda", ra
     group = max(1, min(16, 512 // max(int(batch_size) // max(world, 1), 1))) if int(num_workers) > 0 else 1
     loader = torch.utils.data.DataLoader(_IndexView(dataset, batches, group), batch_size=None, shuffle=False,
                                          num_workers=int(num_workers), collate_fn=None,
-                                         pin_memory=int(num_workers) > 0,
+                                         pin_memory=(int(num_workers) > 0 and
+                                                     os.environ.get("LIREC_LOADER_PIN_THREAD", "1") != "0"),
                                          prefetch_factor=(int(getattr(opt, "prefetch_factor", 2)) if int(num_workers) > 0
                                                           else None),
                                          persistent_workers=False)

@@ -1,8 +1,11 @@
 #!/bin/bash
-# A/B: run the isolated GEMM bench and the step bench for each variant library in variants/
-for lib in variants/*.so; do
-  echo "=== $lib"
-  LIREC_B200_LIB=$PWD/$lib python tools/gemm_probe.py 2>&1 | grep -E "^bench|FAIL"
-  LIREC_B200_LIB=$PWD/$lib timeout 300 python bench.py --steps 40 --warmup 3 --no_cpu_baseline --dump_profile gpurun_out/ab_$(basename $lib .so).txt 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('clips/s %.0f ms/step %.3f gemm_ms %.3f clocks %s' % (d['value'], d['ms_per_step'], d['roofline']['gemm_ms_per_step'], d['clocks']))"
-  cut -d' ' -f1,2,4 gpurun_out/ab_$(basename $lib .so).txt | tr '\n' ';'; echo
+# A/B on one box: the device-resident step bench for each variant library in variants/, ROUNDS times interleaved
+# (box-to-box and minute-to-minute drift is ~1-2 %, more than most kernel changes are worth).
+ROUNDS=${ROUNDS:-3}
+ARGS=${ARGS:---steps 60 --warmup 5}
+for r in $(seq $ROUNDS); do
+  for lib in variants/*.so; do
+    LIREC_B200_LIB=$PWD/$lib timeout 300 python bench.py --only_value $ARGS 2>/dev/null | tail -1 | \
+      python -c "import sys,json; d=json.loads(sys.stdin.read()); print('%-22s round $r  clips/s %.0f  ms/step %.4f  gemm_ms %.4f  %s' % ('$(basename $lib .so)', d['value'], d['ms_per_step'], d['gemm_ms_per_step'], d['gemm_launch_ms']))"
+  done
 done

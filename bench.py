@@ -207,6 +207,22 @@ class ClockSampler:
                 "samples": len(self.sm), "how": "NVML / nvidia-smi polled every 10-20 ms inside the timed regions only"}
 
 
+def usable_cores():
+    """Host cores this process may actually use: the affinity mask, capped by a cgroup-v2 CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def load_peaks():
     pk = {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
     path = os.path.join(HERE, "MEASURED_PEAKS.json")
@@ -606,8 +622,8 @@ def run_ours(args):
     # loss read-back.  The iterator is warmed (workers forked, queues primed) by `warmup` untimed steps; the
     # timed region is the next e2e_steps batches of the same iterator.
     from lirec_b200.mixed_utils.classification_dataloader import packed_loader
-    cores = os.cpu_count() or 1
-    workers = args.workers if args.workers >= 0 else max(1, min(12, (cores - 2 * world) // max(world, 1)))
+    cores = usable_cores()
+    workers = args.workers if args.workers >= 0 else max(1, min(10, (cores - world) // max(world, 1)))
     b.opt.prefetch_factor = 2
 
     def loader(n_steps):
@@ -786,7 +802,8 @@ def run_ours(args):
                              "processes, pinning, async H2D of the index tables, device gather from the HBM-resident "
                              "dataset banks, train step and loss read-back inside the timed region" % workers)
                     if e2e_value is not None else "loader leg failed (%s); pre-collated index-only batches" % e2e_err,
-                    "loader_workers": workers, "host_cores": cores, "steps": e2e_steps,
+                    "loader_workers": workers, "host_cores": cores, "host_cores_reported": os.cpu_count(),
+                    "steps": e2e_steps,
                     "loader_only_clips_per_s": e2e_host_rate},
             "e2e_precollated": {"value": e2e_pre, "unit": "clips/s", "h2d_bytes_per_step": int(in_bytes),
                                 "d2h_bytes_per_step": 4,

@@ -420,6 +420,20 @@ int lirec_collate_tables(const int32_t* cand_host, const int32_t* cand_counts_ho
                          int32_t n_clip_rows, int32_t n_track_rows, int32_t max_slots,
                          int32_t* arena_host, int64_t arena_cap, int64_t* layout_host, int32_t* sizes_host);
 
+/* Ragged gather in front of lirec_collate_tables for datasets that keep every record's triples back to back in
+ * dataset-level tables (lirec_b200/mixed_utils/cached_clips.py): ds_cand_off [n_items + 1] / ds_cand [*, 3] = CSR of
+ * the candidate triples by item; ds_ctx_off [n_cand_total + 1] / ds_ctx_cnt [n_cand_total] / ds_ctx [*, 3] = CSR of
+ * the context triples by candidate (all three NULL: no context branch); idx [B] = the items of the batch.  Writes the
+ * batch's candidate triples, per-clip candidate counts, the dataset position of every candidate (cand_pos_out, may be
+ * NULL), context triples and per-candidate context counts — the inputs of lirec_collate_tables — and their row counts.
+ * Replaces the per-item `__getitem__` + list concatenation of the reference's loader (classification_dataloader.py
+ * :291-616 + default collate) for index-only records.  HOST pointers only.                                         */
+int lirec_collate_gather(const int64_t* ds_cand_off, const int32_t* ds_cand, const int64_t* ds_ctx_off,
+                         const int32_t* ds_ctx_cnt, const int32_t* ds_ctx, const int64_t* idx, int32_t B,
+                         int32_t* cand_out, int32_t* counts_out, int64_t* cand_pos_out, int64_t max_cand,
+                         int32_t* ctx_out, int32_t* ctx_counts_out, int64_t max_ctx, int64_t* n_cand_out,
+                         int64_t* n_ctx_out);
+
 /* ---- optimizer -----------------------------------------------------------
  * torch.optim.Adam with coupled L2 (reference mlp/model.py:599-601) over one
  * flat buffer; also refreshes the bf16 shadow of the weights.                */

@@ -175,6 +175,8 @@ def lib():
     L.lirec_collate_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
                                        C.c_void_p]
+    L.lirec_collate_gather.argtypes = [C.c_void_p] * 6 + [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                                          C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     if L.lirec_abi_version() != 1:
         raise RuntimeError("liblirec_b200.so ABI version mismatch; rebuild it")
     _lib = L
@@ -186,7 +188,7 @@ EXPORTED_SYMBOLS = [
     "lirec_gemm_grouped", "lirec_profile_begin", "lirec_profile_end", "lirec_seg_reduce_f32", "lirec_seg_reduce_gather_f32", "lirec_seg_softmax_pool_fwd", "lirec_seg_softmax_pool_bwd", "lirec_rows_expand_fwd", "lirec_rows_expand_bwd",
     "lirec_split_f32", "lirec_cast_bf16", "lirec_gather_rows", "lirec_roi_max_pool_f32", "lirec_loss_track_fwd_bwd", "lirec_loss_rowmargin_fwd_bwd", "lirec_loss_ce_fwd_bwd", "lirec_predict_tracks",
     "lirec_model_workspace_bytes", "lirec_model_workspace_layout", "lirec_model_forward", "lirec_model_backward", "lirec_model_backward_ex", "lirec_adam_flat", "lirec_dp_flag_words", "lirec_dp_exchange", "lirec_dp_reduce_adam_bcast", "lirec_dp_reduce_adam_bcast_peer",
-    "lirec_collate_arena_bound", "lirec_collate_tables",
+    "lirec_collate_arena_bound", "lirec_collate_tables", "lirec_collate_gather",
 ]
 
 # kernels launched through this binding since import (bench.py reports it as gpu_launches)

@@ -208,3 +208,42 @@ extern "C" int lirec_collate_tables(const int32_t* cand_host, const int32_t* can
   for (int32_t u = 0; u < n_track; ++u) track_src[u] = track.order[u] < B ? 0 : track.order[u] - B;
   return LIREC_OK;
 }
+
+// Ragged gather of the records of `B` clips out of dataset-level tables (CSR by clip for the candidate triples,
+// CSR by candidate for the context triples) into the contiguous arrays lirec_collate_tables takes.  Replaces ~10
+// numpy calls per clip (or the vectorised fancy-indexing equivalent) in the DataLoader worker.  Host code.
+// Returns the number of candidate rows through n_cand_out and of context rows through n_ctx_out; the output
+// buffers must hold max_cand / max_ctx rows (the call fails, writing nothing beyond them, if they do not).
+extern "C" int lirec_collate_gather(const int64_t* ds_cand_off, const int32_t* ds_cand, const int64_t* ds_ctx_off,
+                                    const int32_t* ds_ctx_cnt, const int32_t* ds_ctx, const int64_t* idx, int32_t B,
+                                    int32_t* cand_out, int32_t* counts_out, int64_t* cand_pos_out, int64_t max_cand,
+                                    int32_t* ctx_out, int32_t* ctx_counts_out, int64_t max_ctx, int64_t* n_cand_out,
+                                    int64_t* n_ctx_out) {
+  using lirec::fail;
+  lirec::reset_launch_count();
+  if (!ds_cand_off || !ds_cand || !idx || !cand_out || !counts_out || !n_cand_out || !n_ctx_out || B <= 0)
+    return fail(LIREC_ERR_ARG, "collate_gather: null argument or empty batch");
+  const bool has_ctx = ds_ctx_off != nullptr;
+  if (has_ctx && (!ds_ctx_cnt || !ds_ctx || !ctx_out || !ctx_counts_out))
+    return fail(LIREC_ERR_ARG, "collate_gather: context tables missing");
+  int64_t ni = 0, nx = 0;
+  for (int32_t b = 0; b < B; ++b) {
+    const int64_t c0 = ds_cand_off[idx[b]], c1 = ds_cand_off[idx[b] + 1];
+    if (ni + (c1 - c0) > max_cand) return fail(LIREC_ERR_ARG, "collate_gather: candidate buffer too small");
+    counts_out[b] = static_cast<int32_t>(c1 - c0);
+    std::memcpy(cand_out + 3 * ni, ds_cand + 3 * c0, sizeof(int32_t) * 3 * static_cast<size_t>(c1 - c0));
+    for (int64_t c = c0; c < c1; ++c, ++ni) {
+      if (cand_pos_out) cand_pos_out[ni] = c;
+      if (has_ctx) {
+        const int32_t k = ds_ctx_cnt[c];
+        if (nx + k > max_ctx) return fail(LIREC_ERR_ARG, "collate_gather: context buffer too small");
+        ctx_counts_out[ni] = k;
+        std::memcpy(ctx_out + 3 * nx, ds_ctx + 3 * ds_ctx_off[c], sizeof(int32_t) * 3 * static_cast<size_t>(k));
+        nx += k;
+      }
+    }
+  }
+  *n_cand_out = ni;
+  *n_ctx_out = nx;
+  return LIREC_OK;
+}

@@ -41,6 +41,19 @@ constexpr int UMMA_K = 16;
 #endif
 // A/B knobs of the epilogue (tools/build_variants.sh): per-tile copy of the epilogue descriptor out of parameter
 // space, and the auxiliary-tensor loads of the backward epilogues issued ahead of the accumulator wait
+// LIREC_GEMM_TRACE=1 (variant build, tools/gemm_trace.py): every role stamps clock64() per tile into a device
+// buffer — producer first / last issue, MMA accumulator-free / first-operands / commit, epilogue wake / done.
+#ifndef LIREC_GEMM_TRACE
+#define LIREC_GEMM_TRACE 0
+#endif
+#if LIREC_GEMM_TRACE
+#define LIREC_TRACE(field)                                                                        \
+  do {                                                                                            \
+    if (P.trace && trace_k < 64) P.trace[(static_cast<size_t>(unit) * 64 + trace_k) * 8 + (field)] = clock64(); \
+  } while (0)
+#else
+#define LIREC_TRACE(field) do { } while (0)
+#endif
 #ifndef LIREC_EPI_HOIST
 #define LIREC_EPI_HOIST 1
 #endif
@@ -132,6 +145,9 @@ struct alignas(64) GemmParams {
   // launch mixing 400-k-block wgrad tiles with 4-k-block dgrad tiles still finishes together.
   int32_t num_slots;
   int32_t use_order;
+#if LIREC_GEMM_TRACE
+  unsigned long long* trace;    // [units][TRACE_TILES][8] SM-clock stamps per tile (variant build only)
+#endif
   uint16_t tile_order[MAX_ORDERED_TILES];
 };
 static_assert(sizeof(GemmParams) < 32000, "kernel parameter space");
@@ -673,9 +689,12 @@ __device__ __forceinline__ void gemm_body(const GemmParams& P, uint8_t* smem_raw
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int trace_k = -1;
       for (int slot = unit; slot < P.num_slots; slot += num_units) {
         const int t = P.use_order ? static_cast<int>(P.tile_order[slot]) : slot;
         if (t == NO_TILE) continue;
+        ++trace_k;
+        if (rank == 0) LIREC_TRACE(0);
         int p = 0;
         while (t >= P.tile_start[p + 1]) ++p;
         const DevProblem& pr = P.probs[p];
@@ -733,6 +752,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& P, uint8_t* smem_raw
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
+        if (rank == 0) LIREC_TRACE(1);
       }
     }
   } else if (warp == MMA_WARP) {
@@ -742,9 +762,11 @@ __device__ __forceinline__ void gemm_body(const GemmParams& P, uint8_t* smem_raw
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int trace_k = -1;
       for (int slot = unit; slot < P.num_slots; slot += num_units) {
         const int t = P.use_order ? static_cast<int>(P.tile_order[slot]) : slot;
         if (t == NO_TILE) continue;
+        ++trace_k;
         int p = 0;
         while (t >= P.tile_start[p + 1]) ++p;
         const DevProblem& pr = P.probs[p];
@@ -754,8 +776,10 @@ __device__ __forceinline__ void gemm_body(const GemmParams& P, uint8_t* smem_raw
                                (static_cast<uint32_t>(pr.b_mn_major) << 16) |
                                (static_cast<uint32_t>((PAIR ? pr.bn : BN128) >> 3) << 17) |
                                (static_cast<uint32_t>(TILE_M >> 4) << 24);
+        LIREC_TRACE(2);
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
         tc_fence_after();
+        LIREC_TRACE(3);
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc) * ACC_COLS;
         uint32_t accumulate = 0;
         const int slice = (t - P.tile_start[p]) / pr.tiles_mn;
@@ -765,6 +789,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& P, uint8_t* smem_raw
           for (int it = slice * pr.split_chunk; it < it_end; ++it) {
             mbar_wait(smem_u32(&full_bar[stage]), phase);
             tc_fence_after();
+            if (g == 0 && it == slice * pr.split_chunk) LIREC_TRACE(4);
             const uint32_t s0 = smem_u32(smem + stage * GSTAGE_BYTES);
             for (int j = 0; j < G.nmma; ++j) {
               const uint32_t sa = s0 + static_cast<uint32_t>(G.mma_a[j]) * SLOT_BYTES;
@@ -791,6 +816,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& P, uint8_t* smem_raw
         // accumulator complete -> epilogue(s)
         if constexpr (PAIR) tc_commit_pair(smem_u32(&tfull_bar[acc]));
         else tc_commit(smem_u32(&tfull_bar[acc]));
+        LIREC_TRACE(5);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -802,9 +828,11 @@ __device__ __forceinline__ void gemm_body(const GemmParams& P, uint8_t* smem_raw
     uint8_t* epi_stage = smem + STAGES * GSTAGE_BYTES + 256 + warp * EPI_STAGE_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int trace_k = -1;
     for (int slot = unit; slot < P.num_slots; slot += num_units) {
       const int t = P.use_order ? static_cast<int>(P.tile_order[slot]) : slot;
       if (t == NO_TILE) continue;
+      ++trace_k;
       int p = 0;
       while (t >= P.tile_start[p + 1]) ++p;
       const DevProblem& pr = P.probs[p];
@@ -828,6 +856,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& P, uint8_t* smem_raw
       aux_prefetch(e, M, N, m_row, n0 + half * 32, aux);
       mbar_wait_sleepy(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
+      if (warp == 0 && lane == 0 && rank == 0) LIREC_TRACE(6);
 #pragma unroll 1
       for (int c = half; c < chunks; c += NUM_EPI_WARPS / 4) {
         uint32_t r[32];
@@ -842,6 +871,7 @@ __device__ __forceinline__ void gemm_body(const GemmParams& P, uint8_t* smem_raw
       }
       tc_fence_before();
       __syncwarp();
+      if (warp == 0 && lane == 0 && rank == 0) LIREC_TRACE(7);
       if (lane == 0) {
         if constexpr (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[acc]), 0));
         else mbar_arrive(smem_u32(&tempty_bar[acc]));
@@ -1008,6 +1038,35 @@ constexpr size_t GEMM_SMEM = GSTAGES * GSTAGE_BYTES + 1024 /*align*/ + 256 /*bar
                              NUM_EPI_WARPS * EPI_STAGE_BYTES /*epilogue staging*/;
 static_assert(GEMM_SMEM <= 232448, "shared memory budget");
 
+#if LIREC_GEMM_TRACE
+// Variant build only: one device buffer of clock stamps per launch, copied back synchronously and appended to the
+// file named by LIREC_GEMM_TRACE_FILE as "launch <n> units <u> tiles <t>" followed by u * 64 * 8 numbers.
+static unsigned long long* g_trace_dev = nullptr;
+static int g_trace_launch = 0;
+static void trace_prepare(GemmParams& P, int units) {
+  P.trace = nullptr;
+  if (!getenv("LIREC_GEMM_TRACE_FILE")) return;
+  if (!g_trace_dev) cudaMalloc(&g_trace_dev, sizeof(unsigned long long) * 148 * 64 * 8);
+  cudaMemset(g_trace_dev, 0, sizeof(unsigned long long) * 148 * 64 * 8);
+  P.trace = g_trace_dev;
+  (void)units;
+}
+static void trace_dump(const GemmParams& P, int units, cudaStream_t stream) {
+  if (!P.trace) return;
+  cudaStreamSynchronize(stream);
+  std::vector<unsigned long long> h(static_cast<size_t>(units) * 64 * 8);
+  cudaMemcpy(h.data(), g_trace_dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  FILE* f = fopen(getenv("LIREC_GEMM_TRACE_FILE"), "a");
+  if (!f) return;
+  fprintf(f, "launch %d units %d tiles %d problems %d\n", g_trace_launch++, units, P.total_tiles, P.num_problems);
+  for (size_t i = 0; i < h.size(); ++i) fprintf(f, "%llu%c", h[i], (i % 8 == 7) ? '\n' : ' ');
+  fclose(f);
+}
+#else
+static void trace_prepare(GemmParams&, int) {}
+static void trace_dump(const GemmParams&, int, cudaStream_t) {}
+#endif
+
 static int launch_single(const GemmParams& P, cudaStream_t stream) {
   static bool configured = false;
   static int num_sms = 0;
@@ -1021,10 +1080,12 @@ static int launch_single(const GemmParams& P, cudaStream_t stream) {
   }
   const int grid = std::min(P.total_tiles, num_sms);
   schedule_tiles(const_cast<GemmParams&>(P), grid);
+  trace_prepare(const_cast<GemmParams&>(P), grid);
   ProfRec rec{};
   int rc = record_begin(rec, P, stream);
   if (rc != LIREC_OK) return rc;
   LIREC_CUDA_OK(launch_pdl(lirec_gemm_tcgen05_kernel, dim3(grid), dim3(NUM_THREADS), GEMM_SMEM, stream, P));
+  trace_dump(P, grid, stream);
   if ((rc = record_end(rec, stream)) != LIREC_OK) return rc;
   note_launch();
   return LIREC_OK;
@@ -1055,10 +1116,12 @@ static int launch_pair(const GemmParams& P, cudaStream_t stream) {
   }
   const int clusters = std::min(P.total_tiles, max_clusters);
   schedule_tiles(const_cast<GemmParams&>(P), clusters);
+  trace_prepare(const_cast<GemmParams&>(P), clusters);
   ProfRec rec{};
   int rc = record_begin(rec, P, stream);
   if (rc != LIREC_OK) return rc;
   LIREC_CUDA_OK(launch_pdl(lirec_gemm_tcgen05_pair_kernel, dim3(2 * clusters), dim3(NUM_THREADS), GEMM_SMEM, stream, P));
+  trace_dump(P, clusters, stream);
   if ((rc = record_end(rec, stream)) != LIREC_OK) return rc;
   note_launch();
   return LIREC_OK;

@@ -79,9 +79,11 @@ class SwitchReduceAdam:
         ...
         train_step(model, loss, optimizer, pb, world, fused)   # lirec_b200/mlp/train.py drives it
 
-    mode 'shard' (default): ONE pass after backward, lirec_dp_reduce_adam_bcast — every rank sums its 1/world
-    shard of the gradients inside the switch, applies Adam to that shard (it owns the shard's moments) and
-    multicast-stores the new fp32 parameters and their bf16 shadow into every replica.  Parameters, bf16 shadow
+    mode 'shard' (default): lirec_dp_reduce_adam_bcast — every rank sums its 1/world shard of the gradients inside
+    the switch, applies Adam to that shard (it owns the shard's moments) and multicast-stores the new fp32
+    parameters and their bf16 shadow into every replica.  With `overlap` the pass is split in two: the gate +
+    head parameters (53 %) run on a side stream behind the event lirec_model_backward_ex records when their
+    gradients are final, while the encoder stages of backward still go; the encoders follow after backward.  Parameters, bf16 shadow
     and gradients therefore live in ONE symmetric allocation; `optimizer.state_dict()` gathers the moments.
     Against exchange-then-Adam this removes the 553 MB full-replica optimizer pass from every rank's critical
     path and sends 6 bytes per parameter back instead of 4.
@@ -194,11 +196,21 @@ class SwitchReduceAdam:
             self.optimizer._shard_sync = None
         self.model = self.optimizer = None
 
-    def shard_range(self, rank=None):
-        """[begin, end) in floats of the shard a rank owns in 'shard' mode."""
+    def buckets(self):
+        """(offset, length) in floats of the pieces one step exchanges: with `overlap`, the gate + head parameters
+        first (their pass runs on the side stream behind backward's heads-final event), then the encoders."""
+        if self.overlap and 0 < self.split < self.n:
+            return [(self.split, self.n - self.split), (0, self.split)]
+        return [(0, self.n)]
+
+    def shard_ranges(self, rank=None):
+        """[begin, end) in floats of the shards a rank owns in 'shard' mode: 1/world of every bucket."""
         r = self.rank if rank is None else rank
-        n4 = self.n // 4
-        return 4 * (n4 * r // self.world), 4 * (n4 * (r + 1) // self.world)
+        out = []
+        for off, n in self.buckets():
+            n4 = n // 4
+            out.append((off + 4 * (n4 * r // self.world), off + 4 * (n4 * (r + 1) // self.world)))
+        return out
 
     @torch.no_grad()
     def gather_moments(self):
@@ -207,15 +219,15 @@ class SwitchReduceAdam:
             return
         o = self.optimizer
         for r in range(self.world):
-            a, b = self.shard_range(r)
-            dist.broadcast(o._m[a:b], src=r)
-            dist.broadcast(o._v[a:b], src=r)
+            for a, b in self.shard_ranges(r):
+                dist.broadcast(o._m[a:b], src=r)
+                dist.broadcast(o._v[a:b], src=r)
 
     # ---- per-step protocol --------------------------------------------------------------------------
     def arm(self, equal_shards=True):
-        """Before backward ('bucket' mode): ask lirec_model_backward_ex for the heads-final event (only when this
-        step's exchange needs no host-side re-weighting)."""
-        self._armed = bool(self.mode == "bucket" and self.overlap and equal_shards and 0 < self.split < self.n)
+        """Before backward: ask lirec_model_backward_ex for the heads-final event (only when this step's exchange
+        needs no host-side re-weighting)."""
+        self._armed = bool(self.overlap and equal_shards and 0 < self.split < self.n)
         self.model._heads_event = self.ev_heads if self._armed else None
         return self._armed
 
@@ -230,6 +242,24 @@ class SwitchReduceAdam:
             ops.dp_exchange(self._mc("grad"), off, n, self.rank, self.world, self._flag_ptrs.data_ptr(), channel, stream)
         ops.adam_flat(m._flat, m._flat_grad, o._m, o._v, m._flat_bf16, g["lr"], g["betas"][0], g["betas"][1],
                       g["eps"], g["weight_decay"], o._t, scale, offset=off, n=n, stream=stream)
+
+    def _shard_pass(self, bucket, channel, stream, scale):
+        """lirec_dp_reduce_adam_bcast over floats [off, off + n) on `stream`."""
+        from lirec_b200 import ops
+        m, o = self.model, self.optimizer
+        g = o.param_groups[0]
+        off, n = bucket
+        if self.transport == "peer" and self.world in (2, 4, 8):
+            ops.dp_reduce_adam_bcast_peer(self._bases.data_ptr(), self.offsets["grad"] + 4 * off,
+                                          self.offsets["flat"] + 4 * off, self.offsets["bf16"] + 2 * off, o._m[off:],
+                                          o._v[off:], n, g["lr"], g["betas"][0], g["betas"][1], g["eps"],
+                                          g["weight_decay"], o._t, scale, self.rank, self.world,
+                                          self._flag_ptrs.data_ptr(), channel, stream)
+        else:
+            ops.dp_reduce_adam_bcast(self._mc("grad") + 4 * off, m._flat[off:], self._mc("flat") + 4 * off,
+                                     self._mc("bf16") + 2 * off, o._m[off:], o._v[off:], n, g["lr"], g["betas"][0],
+                                     g["betas"][1], g["eps"], g["weight_decay"], o._t, scale, self.rank, self.world,
+                                     self._flag_ptrs.data_ptr(), channel, stream)
 
     @torch.no_grad()
     def step(self, local_clips=None, global_clips=None):
@@ -247,16 +277,17 @@ class SwitchReduceAdam:
         o._t += 1
         main = torch.cuda.current_stream()
         if self.world > 1 and self.mode == "shard":
-            g = o.param_groups[0]
-            if self.transport == "peer" and self.world in (2, 4, 8):
-                ops.dp_reduce_adam_bcast_peer(self._bases.data_ptr(), self.offsets["grad"], self.offsets["flat"],
-                                              self.offsets["bf16"], o._m, o._v, self.n, g["lr"], g["betas"][0],
-                                              g["betas"][1], g["eps"], g["weight_decay"], o._t, scale, self.rank,
-                                              self.world, self._flag_ptrs.data_ptr(), 0)
+            # one fused pass per bucket; the ownership of the moments follows buckets(), armed or not
+            bk = self.buckets()
+            if armed and len(bk) == 2:
+                self.side.wait_event(self.ev_heads)          # recorded mid-backward on the main stream
+                self._shard_pass(bk[0], 0, self.side, scale)
+                self.ev_done.record(self.side)
+                self._shard_pass(bk[1], 1, main, scale)
+                main.wait_event(self.ev_done)
             else:
-                ops.dp_reduce_adam_bcast(self._mc("grad"), m._flat, self._mc("flat"), self._mc("bf16"), o._m, o._v,
-                                         g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], o._t,
-                                         scale, self.rank, self.world, self._flag_ptrs.data_ptr(), 0)
+                for ch, b in enumerate(bk):
+                    self._shard_pass(b, ch, main, scale)
         elif armed:
             self.side.wait_event(self.ev_heads)              # recorded mid-backward on the main stream
             self._bucket(self.split, self.n - self.split, 0, self.side, scale)

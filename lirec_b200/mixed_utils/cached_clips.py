@@ -106,6 +106,9 @@ class CachedClipsDataset(Dataset):
             self._rels = np.concatenate([np.asarray(r["rels_label"]).reshape(-1) for r in R]).astype(np.int64) \
                 if track_models else np.array([r["rels_label"] for r in R], dtype=np.int64)
         self._track_models = track_models
+        self._cand_off = np.ascontiguousarray(self._cand_off, dtype=np.int64)
+        self._max_cand = int(n_cand.max())
+        self._max_ctx = int(self._ctx_cnt.max()) if has_ctx else 0
 
     @staticmethod
     def _ranges(starts, counts):
@@ -119,14 +122,29 @@ class CachedClipsDataset(Dataset):
         tables (equal batches: tests/test_dataloader_cpu.py)."""
         if self.records is None:
             self.cache()
-        idx = np.asarray(indices, dtype=np.int64)
-        counts = (self._cand_off[idx + 1] - self._cand_off[idx])
-        cpos = self._ranges(self._cand_off[idx], counts)                 # dataset positions of the batch's candidates
-        cand = self._cand[cpos]
-        ctx = ctx_counts = rels = None
-        if self._ctx is not None:
-            ctx_counts = self._ctx_cnt[cpos]
-            ctx = self._ctx[self._ranges(self._ctx_off[cpos], ctx_counts.astype(np.int64))]
+        from lirec_b200 import _ext
+        idx = np.ascontiguousarray(indices, dtype=np.int64)
+        B = len(idx)
+        # native ragged gather (lirec_collate_gather): candidate / context triples of the batch, back to back
+        max_cand = B * self._max_cand
+        max_ctx = max_cand * self._max_ctx if self._ctx is not None else 0
+        cand = np.empty((max_cand, 3), dtype=np.int32)
+        counts = np.empty(B, dtype=np.int32)
+        cpos = np.empty(max_cand, dtype=np.int64)
+        ctx = np.empty((max(max_ctx, 1), 3), dtype=np.int32) if self._ctx is not None else None
+        ctx_counts = np.empty(max_cand, dtype=np.int32) if self._ctx is not None else None
+        n = np.zeros(2, dtype=np.int64)
+        _ext.check(_ext.lib().lirec_collate_gather(
+            self._cand_off.ctypes.data, self._cand.ctypes.data,
+            self._ctx_off.ctypes.data if ctx is not None else None, self._ctx_cnt.ctypes.data if ctx is not None else None,
+            self._ctx.ctypes.data if ctx is not None else None, idx.ctypes.data, B, cand.ctypes.data, counts.ctypes.data,
+            cpos.ctypes.data, max_cand, ctx.ctypes.data if ctx is not None else None,
+            ctx_counts.ctypes.data if ctx is not None else None, max_ctx, n[0:].ctypes.data, n[1:].ctypes.data))
+        ni, nx = int(n[0]), int(n[1])
+        cand, cpos = cand[:ni], cpos[:ni]
+        rels = None
+        if ctx is not None:
+            ctx, ctx_counts = ctx[:nx], ctx_counts[:ni]
             rels = self._rels[cpos] if self._track_models else self._rels[idx]
         gt = self._gt[idx] if self._gt is not None else np.zeros((len(idx), 2), dtype=np.int64)
         extras = {"just_zeros": self._just_zeros[idx], "n_names": self._n_names[idx]}

@@ -121,6 +121,42 @@ class EmptyShard:
         return self
 
 
+class _PinnedRing:
+    """A fixed ring of pinned staging buffers for index-only batches: the worker's arena (shared memory) and the
+    multi-label bytes are copied into the next slot and cross PCIe from there.  No pinned allocation happens per
+    batch — the caching host allocator only recycles a block once the events of its last use have completed and
+    falls back to cudaHostAlloc (milliseconds, under the driver lock every kernel launch needs) otherwise, which
+    showed as erratic multi-millisecond stalls of the loader.  A slot is reused after its own H2D copies are done."""
+
+    def __init__(self, slots=6):
+        self.arena, self.ml, self.ev = [None] * slots, [None] * slots, [None] * slots
+        self.k = 0
+
+    def stage(self, pb, copy_stream):
+        """Point `pb` (a host PackedBatch with `_host_arena`) at pinned copies of its arena / multilab."""
+        k = self.k
+        self.k = (k + 1) % len(self.arena)
+        if self.ev[k] is not None:
+            self.ev[k].synchronize()                         # the slot's previous batch has crossed PCIe
+        src = torch.from_numpy(pb._host_arena)
+        n, m = src.numel(), pb.multilab.numel()
+        if self.arena[k] is None or self.arena[k].numel() < n:
+            self.arena[k] = torch.empty(int(n * 1.25) + 1024, dtype=torch.int32).pin_memory()
+        if self.ml[k] is None or self.ml[k].numel() < m:
+            self.ml[k] = torch.empty(int(m * 1.25) + 1024, dtype=torch.uint8).pin_memory()
+        self.arena[k][:n].copy_(src)
+        self.ml[k][:m].copy_(pb.multilab.reshape(-1))
+        pb._arena, pb._layout = self.arena[k][:n], pb._host_layout
+        pb.multilab = self.ml[k][:m].view(pb.multilab.shape)
+        self._last = k
+        return pb
+
+    def mark(self, copy_stream):
+        ev = torch.cuda.Event()
+        ev.record(copy_stream)
+        self.ev[self._last] = ev
+
+
 def plan_batches(n, batch_size, order, rank, world, drop_last=False):
     """[(this rank's clip indices, global batch size)] for one epoch.  EVERY rank gets one entry per global
     batch — an empty index list when the global batch is smaller than the world — so all ranks take the same
@@ -159,7 +195,7 @@ def packed_loader(dataset, batch_size, shuffle, num_workers=0, device="cuda", ra
     loader = torch.utils.data.DataLoader(_IndexView(dataset, batches, group), batch_size=None, shuffle=False,
                                          num_workers=int(num_workers), collate_fn=None,
                                          pin_memory=(int(num_workers) > 0 and
-                                                     os.environ.get("LIREC_LOADER_PIN_THREAD", "1") != "0"),
+                                                     os.environ.get("LIREC_LOADER_PIN_THREAD", "0") != "0"),
                                          prefetch_factor=(int(getattr(opt, "prefetch_factor", 2)) if int(num_workers) > 0
                                                           else None),
                                          persistent_workers=False)
@@ -171,6 +207,8 @@ def packed_loader(dataset, batch_size, shuffle, num_workers=0, device="cuda", ra
         banks = getattr(dataset, "_resident", None) or ResidentBanks(dataset, device)
         dataset._resident = banks
         copy_stream.wait_stream(torch.cuda.current_stream())
+    ring = _PinnedRing() if (banks is not None and os.environ.get("LIREC_LOADER_RING", "1") != "0") else None
+
     def flat(it):
         for item in it:
             if isinstance(item, list):
@@ -189,7 +227,12 @@ def packed_loader(dataset, batch_size, shuffle, num_workers=0, device="cuda", ra
             pending = (dev_pb, ev)
             continue
         with torch.cuda.stream(copy_stream):
-            dev_pb = banks.stage(host_pb) if banks is not None else host_pb.pin().to_device(device, non_blocking=True)
+            if banks is not None and ring is not None and getattr(host_pb, "_host_arena", None) is not None \
+                    and not hasattr(host_pb, "_arena"):
+                dev_pb = banks.stage(ring.stage(host_pb, copy_stream))
+                ring.mark(copy_stream)
+            else:
+                dev_pb = banks.stage(host_pb) if banks is not None else host_pb.pin().to_device(device, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         if pending is not None:

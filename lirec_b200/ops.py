@@ -264,7 +264,7 @@ def adam_flat(param, grad, exp_avg, exp_avg_sq, param_bf16, lr, beta1, beta2, ep
                                  float(eps), float(weight_decay), int(step), float(grad_scale), sp))
 
 
-def dp_reduce_adam_bcast(grad_mc, param, param_mc, bf16_mc, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay,
+def dp_reduce_adam_bcast(grad_mc, param, param_mc, bf16_mc, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
                          step, grad_scale, rank, world, flag_ptrs_dev, channel, stream=None):
     """In-switch gradient sum of this rank's shard + Adam on the shard + multicast of the new parameters and their
     bf16 shadow to every rank (lirec_dp_reduce_adam_bcast)."""
@@ -272,7 +272,7 @@ def dp_reduce_adam_bcast(grad_mc, param, param_mc, bf16_mc, exp_avg, exp_avg_sq,
     sp = _ext.stream_ptr() if stream is None else C.c_void_p(stream.cuda_stream)
     _ext.check(L.lirec_dp_reduce_adam_bcast(
         C.c_void_p(int(grad_mc)), _ext.ptr(param), C.c_void_p(int(param_mc)), C.c_void_p(int(bf16_mc)),
-        _ext.ptr(exp_avg), _ext.ptr(exp_avg_sq), param.numel(), float(lr), float(beta1), float(beta2), float(eps),
+        _ext.ptr(exp_avg), _ext.ptr(exp_avg_sq), int(n), float(lr), float(beta1), float(beta2), float(eps),
         float(weight_decay), int(step), float(grad_scale), int(rank), int(world), C.c_void_p(int(flag_ptrs_dev)),
         int(channel), sp))
 

@@ -64,7 +64,7 @@ def main():
     finals = []
     # the same three steps through lirec_b200.mlp.train.train_step with (a) ncclAllReduce + Adam, (b) the
     # in-switch exchange + Adam after backward, (c) the same with the gate + head bucket overlapped with backward
-    for mode in ("nccl", "shard", "bucket", "bucket_overlap"):
+    for mode in ("nccl", "shard", "shard_overlap", "bucket", "bucket_overlap"):
         torch.manual_seed(0)
         with contextlib.redirect_stdout(io.StringIO()):
             model, loss_fn, optimizer = M.create_model(101, n_rels=15)
@@ -77,7 +77,7 @@ def main():
                 print("SKIP: no NVSwitch multicast support on this box")
             return 0
         if fused is not None:
-            fused.overlap = mode == "bucket_overlap"
+            fused.overlap = mode.endswith("_overlap")
         for i, pb in enumerate(pbs):
             TR.train_step(model, loss_fn, optimizer, pb, world, fused)
         torch.cuda.synchronize()
@@ -88,15 +88,15 @@ def main():
         if fused is not None:
             fused.detach()
     ok = True
-    for j, mode in ((1, "shard"), (2, "bucket"), (3, "bucket_overlap")):
-        for k in (("p", "m", "v", "pb") if mode == "shard" else ("g", "p", "m", "v", "pb")):   # 'shard' never sums g in place
+    for j, mode in ((1, "shard"), (2, "shard_overlap"), (3, "bucket"), (4, "bucket_overlap")):
+        for k in (("p", "m", "v", "pb") if mode.startswith("shard") else ("g", "p", "m", "v", "pb")):   # 'shard' never sums g in place
             a, b = finals[0][k], finals[j][k]
             err = float((a - b).abs().max() / (a.abs().max() + 1e-30))
             tol = 4e-3 if k == "pb" else 2e-6
             if rank == 0:
                 print("%-3s max-norm relative difference %s vs nccl: %.2e" % (k, mode, err))
             ok = ok and err < tol
-    if not torch.equal(finals[2]["p"], finals[3]["p"]) and rank == 0:
+    if not torch.equal(finals[3]["p"], finals[4]["p"]) and rank == 0:
         print("note: overlapped and non-overlapped in-switch steps differ in the last bits (shard boundaries move "
               "with the bucket cut, so the in-switch summation order does)")
     ok = relationship_term_parity(rank, world) and ok

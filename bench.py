@@ -623,7 +623,7 @@ def run_ours(args):
     # timed region is the next e2e_steps batches of the same iterator.
     from lirec_b200.mixed_utils.classification_dataloader import packed_loader
     cores = usable_cores()
-    workers = args.workers if args.workers >= 0 else max(1, min(10, (cores - world) // max(world, 1)))
+    workers = args.workers if args.workers >= 0 else max(1, min(6, (cores - world) // max(world, 1)))
     b.opt.prefetch_factor = 2
 
     def loader(n_steps):
@@ -798,9 +798,10 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_headline, "unit": "clips/s",
                     "h2d_bytes_per_step": int(h2d_loader or in_bytes), "d2h_bytes_per_step": 4,
-                    "what": ("packed_loader(CachedClipsDataset, num_workers=%d): __getitem__, native collate in worker "
-                             "processes, pinning, async H2D of the index tables, device gather from the HBM-resident "
-                             "dataset banks, train step and loss read-back inside the timed region" % workers)
+                    "what": ("packed_loader(CachedClipsDataset, num_workers=%d): batch assembly from the dataset's index-only "
+                             "records (native gather + lirec_collate_tables in worker threads, straight into pinned "
+                             "slots), async H2D of the index tables, device gather from the HBM-resident dataset "
+                             "banks, train step and loss read-back inside the timed region" % workers)
                     if e2e_value is not None else "loader leg failed (%s); pre-collated index-only batches" % e2e_err,
                     "loader_workers": workers, "host_cores": cores, "host_cores_reported": os.cpu_count(),
                     "steps": e2e_steps,

@@ -117,9 +117,16 @@ class CachedClipsDataset(Dataset):
         ends = np.cumsum(counts)
         return np.repeat(starts - (ends - counts), counts) + np.arange(total, dtype=np.int64)
 
-    def get_batch(self, indices):
+    def arena_bound(self, batch_size):
+        """Upper bound of the int32 arena a batch of `batch_size` clips needs (for pre-allocated pinned slots)."""
+        from lirec_b200 import _ext
+        mc = batch_size * self._max_cand
+        return int(_ext.lib().lirec_collate_arena_bound(batch_size, mc, mc * self._max_ctx, int(self._ctx is not None)))
+
+    def get_batch(self, indices, arena_out=None, multilab_out=None):
         """`collate([self[i] for i in indices])` in one go — the same records, gathered from the dataset-level
-        tables (equal batches: tests/test_dataloader_cpu.py)."""
+        tables (equal batches: tests/test_dataloader_cpu.py).  Thread-safe (read-only on the dataset; the native
+        calls release the GIL).  arena_out / multilab_out: pinned torch buffers the batch is built in directly."""
         if self.records is None:
             self.cache()
         from lirec_b200 import _ext
@@ -148,11 +155,17 @@ class CachedClipsDataset(Dataset):
             rels = self._rels[cpos] if self._track_models else self._rels[idx]
         gt = self._gt[idx] if self._gt is not None else np.zeros((len(idx), 2), dtype=np.int64)
         extras = {"just_zeros": self._just_zeros[idx], "n_names": self._n_names[idx]}
+        ml = self._multilab[idx]
         pb = collate_arrays(self, np.ascontiguousarray(cand), np.ascontiguousarray(counts, dtype=np.int32),
                             None if ctx is None else np.ascontiguousarray(ctx),
                             None if ctx is None else np.ascontiguousarray(ctx_counts), self._labels[idx], rels, gt,
-                            self._multilab[idx], extras, self._max_n_tripl if self._track_models else 1,
-                            self.records[0]["n_ctx_slots"], bool(getattr(opt, "resident_banks", 0)))
+                            ml, extras, self._max_n_tripl if self._track_models else 1,
+                            self.records[0]["n_ctx_slots"], bool(getattr(opt, "resident_banks", 0)), arena_out=arena_out)
+        if multilab_out is not None:
+            import torch
+            out = multilab_out[:ml.size].view(ml.shape)
+            out.copy_(torch.from_numpy(ml))
+            pb.multilab = out
         pb.preset = self.preset
         pb.kind = synthetic.PRESETS[self.preset]["kind"]
         return pb

@@ -172,6 +172,64 @@ def plan_batches(n, batch_size, order, rank, world, drop_last=False):
     return batches
 
 
+def _threaded_batches(dataset, batches, num_threads, batch_size, slots_ahead):
+    """Host batches of a dataset with a thread-safe `get_batch`, built by `num_threads` THREADS straight into a ring
+    of pinned slots.  The assembly is native code that releases the GIL (lirec_collate_gather,
+    lirec_collate_tables), so threads scale like the reference's DataLoader worker processes (mlp/train.py:33-37)
+    do — without the per-batch shared-memory segment, pickling, pinning copy and their erratic multi-millisecond
+    stalls.  Yields (host batch, release) in order; `release(cuda_event)` hands the slot back once the batch's H2D
+    copies are recorded."""
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    n_slots = slots_ahead + 2
+    cap = dataset.arena_bound(max(len(b[0]) for b in batches if b[0]) if any(b[0] for b in batches) else 1)
+    ml_cap = batch_size * dataset.n_classes + 64
+    arenas = [torch.empty(cap, dtype=torch.int32).pin_memory() for _ in range(n_slots)]
+    mls = [torch.empty(ml_cap, dtype=torch.uint8).pin_memory() for _ in range(n_slots)]
+    free = [threading.Event() for _ in range(n_slots)]
+    last_ev = [None] * n_slots
+    for f in free:
+        f.set()
+
+    def job(k):
+        idx, global_size = batches[k]
+        if not idx:
+            return EmptyShard(global_size)
+        s = k % n_slots
+        free[s].wait()
+        free[s].clear()
+        if last_ev[s] is not None:
+            last_ev[s].synchronize()                        # the slot's previous batch has crossed PCIe
+        pb = dataset.get_batch(idx, arena_out=arenas[s], multilab_out=mls[s])
+        pb.global_clips = global_size
+        return pb
+
+    def releaser(k):
+        def release(ev):
+            s = k % n_slots
+            last_ev[s] = ev
+            free[s].set()
+        return release
+
+    pool = ThreadPoolExecutor(max_workers=num_threads, thread_name_prefix="lirec-collate")
+    try:
+        futures = {}
+        nxt = 0
+        for k in range(len(batches)):
+            while nxt < len(batches) and nxt < k + slots_ahead:
+                futures[nxt] = pool.submit(job, nxt)
+                nxt += 1
+            pb = futures.pop(k).result()
+            yield pb, (releaser(k) if not isinstance(pb, EmptyShard) else (lambda ev: None))
+    finally:
+        # the consumer stopped early (or we are done): nobody will release slots any more — let the queued jobs
+        # through instead of leaving the pool's threads blocked on them
+        for f in free:
+            f.set()
+        last_ev[:] = [None] * n_slots
+        pool.shutdown(wait=True, cancel_futures=True)
+
+
 def packed_loader(dataset, batch_size, shuffle, num_workers=0, device="cuda", rank=0, world=1, drop_last=False,
                   seed=0, repeat=1):
     """Iterate device-resident PackedBatches with one-batch-ahead async H2D prefetch.
@@ -212,11 +270,21 @@ def packed_loader(dataset, batch_size, shuffle, num_workers=0, device="cuda", ra
     def flat(it):
         for item in it:
             if isinstance(item, list):
-                yield from item
+                for x in item:
+                    yield x, None
             else:
-                yield item
+                yield item, None
 
-    for host_pb in flat(loader):
+    # datasets whose batches are assembled by GIL-free native code (get_batch): worker THREADS, pinned from birth
+    threaded = (int(num_workers) > 0 and banks is not None and hasattr(dataset, "get_batch") and
+                hasattr(dataset, "arena_bound") and os.environ.get("LIREC_LOADER_THREADS", "1") != "0")
+    if threaded:
+        if getattr(dataset, "records", 1) is None:
+            dataset.cache()
+        source = _threaded_batches(dataset, batches, int(num_workers), batch_size, slots_ahead=2 * int(num_workers) + 2)
+    else:
+        source = flat(loader)
+    for host_pb, release in source:
         if isinstance(host_pb, EmptyShard):
             dev_pb, ev = host_pb, None
             if pending is not None:
@@ -235,6 +303,8 @@ def packed_loader(dataset, batch_size, shuffle, num_workers=0, device="cuda", ra
                 dev_pb = banks.stage(host_pb) if banks is not None else host_pb.pin().to_device(device, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
+            if release is not None:
+                release(ev)
         if pending is not None:
             prev, pev = pending
             if pev is not None:

@@ -684,16 +684,23 @@ def collate_indexed(records, dataset, resident=False):
 
 
 def collate_arrays(dataset, cand, counts, ctx, ctx_counts, labels, rels_label, gt, multilab, extras, n_slots,
-                   n_ctx_slots, resident):
+                   n_ctx_slots, resident, arena_out=None):
     """The batch-level half of `collate_indexed`: the concatenated index triples of B clips (int32, C-contiguous)
     -> every integer table by `lirec_collate_tables`, in one arena, -> host PackedBatch.  `ctx is None`: no
-    context branch."""
+    context branch.  `arena_out`: a caller-owned int32 torch tensor (pinned memory, large enough) the tables are
+    written into directly — the batch is then born pinned (`pb._arena`), no staging copy."""
     from lirec_b200 import _ext
     L = _ext.lib()
     B, Ni = int(len(counts)), int(cand.shape[0])
     has_ctx = ctx is not None
     Nx = int(ctx.shape[0]) if has_ctx else 0
-    arena = np.empty(int(L.lirec_collate_arena_bound(B, Ni, Nx, int(has_ctx))), dtype=np.int32)
+    need = int(L.lirec_collate_arena_bound(B, Ni, Nx, int(has_ctx)))
+    if arena_out is not None:
+        if arena_out.numel() < need:
+            raise ValueError("collate_arrays: arena_out holds %d ints, the batch needs %d" % (arena_out.numel(), need))
+        arena = arena_out.numpy()[:need]
+    else:
+        arena = np.empty(need, dtype=np.int32)
     layout = np.empty((24, 2), dtype=np.int64)
     sizes = np.empty(4, dtype=np.int32)
     _ext.check(L.lirec_collate_tables(
@@ -715,6 +722,8 @@ def collate_arrays(dataset, cand, counts, ctx, ctx_counts, labels, rels_label, g
         arena, layout[:22], clip_bank, track_bank, n_clip_ints, n_track_ints, B, Ni, Nx if has_ctx else None,
         labels, rels_label, gt, multilab, n_slots=n_slots, n_ctx_slots=n_ctx_slots, extras=extras, src_layout=src)
     pb.extras["bank_rows"] = (clip_src, track_src)              # views into the arena: they travel (and pin) with it
+    if arena_out is not None:                                   # born pinned: to_device() copies straight from it
+        pb._arena, pb._layout = arena_out[:pb._host_arena.size], pb._host_layout
     return pb
 
 

@@ -54,6 +54,9 @@ constexpr int UMMA_K = 16;
 #else
 #define LIREC_TRACE(field) do { } while (0)
 #endif
+#ifndef LIREC_EPI_STAGE_NATURAL
+#define LIREC_EPI_STAGE_NATURAL 1
+#endif
 #ifndef LIREC_EPI_HOIST
 #define LIREC_EPI_HOIST 1
 #endif
@@ -417,7 +420,15 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpi& e, int M, int N, in
                                                AfterMath&& after_math) {
   if (n0 >= N) return;                                     // warp-uniform
   const bool staged_t = (e.out_kind == LIREC_OUT_SPLIT_BF16_T) && stage != nullptr;
-  if (m_true >= M && !staged_t) return;
+  // natural-layout outputs of a FULL chunk also leave through the staging area: the accumulator arrives one
+  // ROW per thread (tcgen05.ld 32x32b), so direct stores put 16 bytes of 32 different rows into every store
+  // instruction — 32 wavefronts and 32 half-written sectors each (in-kernel trace: the epilogue of the
+  // second-layer data-gradient tiles, alpha * acc -> fp32, took 7.9 us against 5.3 us of MMA).  Staged, a store
+  // instruction carries whole 128-byte lines of 4 rows (fp32) / 64-byte halves of 8 rows (bf16 hi, lo).
+  const bool staged_n = LIREC_EPI_STAGE_NATURAL && stage != nullptr && (N - n0 >= 32) && e.vec_ok &&
+                        ((e.out_kind == LIREC_OUT_F32 && e.out_ld_n == 1 && !e.accumulate) ||
+                         e.out_kind == LIREC_OUT_SPLIT_BF16);
+  if (m_true >= M && !staged_t && !staged_n) return;
   // a staged store is a warp-cooperative step: rows beyond M tag along on the last valid row's
   // inputs (their values are never stored)
   const int m = min(m_true, M - 1);
@@ -499,7 +510,51 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpi& e, int M, int N, in
     }
   }
   after_math();
-  if (e.out_kind == LIREC_OUT_F32) {
+  if (staged_n && e.out_kind == LIREC_OUT_F32) {
+    // [32 rows][8 x 16 B], piece q of row r at slot q ^ (r & 7): conflict-free both ways
+    float4* s4 = reinterpret_cast<float4*>(stage);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      s4[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    __syncwarp();
+    const int mbase = m_true - lane;
+    float* ob = reinterpret_cast<float*>(e.out) + slice_off + n0;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = it * 4 + (lane >> 3), pc = lane & 7;
+      const float4 w = s4[row * 8 + (pc ^ (row & 7))];
+      if (mbase + row < M)
+        *reinterpret_cast<float4*>(ob + static_cast<int64_t>(mbase + row) * e.out_ld_m + pc * 4) = w;
+    }
+    __syncwarp();
+  } else if (staged_n) {
+    // bf16 hi | lo: two [32 rows][4 x 16 B] planes, piece j of row r at slot j ^ ((r >> 1) & 3)
+    uint4* sh = reinterpret_cast<uint4*>(stage);
+    uint4* sl = sh + 128;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) split_bf16x2(v[8 * j + 2 * q], v[8 * j + 2 * q + 1], h[q], l[q]);
+      const int slot = lane * 4 + (j ^ ((lane >> 1) & 3));
+      sh[slot] = make_uint4(h[0], h[1], h[2], h[3]);
+      sl[slot] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    __syncwarp();
+    const int mbase = m_true - lane;
+    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(e.out) + e.out_col_off + n0;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int row = it * 8 + (lane >> 2), pc = lane & 3;
+      const int slot = row * 4 + (pc ^ ((row >> 1) & 3));
+      if (mbase + row < M) {
+        __nv_bfloat16* o = ob + static_cast<int64_t>(mbase + row) * e.out_ld_m + pc * 8;
+        *reinterpret_cast<uint4*>(o) = sh[slot];
+        *reinterpret_cast<uint4*>(o + e.out_lo_off) = sl[slot];
+      }
+    }
+    __syncwarp();
+  } else if (e.out_kind == LIREC_OUT_F32) {
     float* o = reinterpret_cast<float*>(e.out) + slice_off + static_cast<int64_t>(m) * e.out_ld_m +
                static_cast<int64_t>(n0) * e.out_ld_n;
     if (e.out_ld_n == 1 && e.vec_ok && full) {

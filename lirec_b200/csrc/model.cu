@@ -325,6 +325,62 @@ static int validate(const lirec_model_cfg* cfg, const lirec_model_params* P, con
   return LIREC_OK;
 }
 
+// Below this many candidate rows backward multiplies by the weights in place instead of transposing them.
+static bool dgrad_in_place(int Ni) {
+  const char* e = getenv("LIREC_DGRAD_INPLACE_ROWS");   // read per call: the tests switch it
+  return Ni < (e ? atoi(e) : 1536);
+}
+
+// ---- [in, out] copies of the weights the data gradients multiply by (K-major B operands) ----------------
+static int weight_transposes(const Dims& d, const lirec_model_params& P, const Workspace& w, cudaStream_t stream) {
+  const int nbr = d.ctx ? 2 : 1;
+  const int hw = d.gates ? d.Gd : d.F;
+  rows::TransposeJobs tj;
+  tj.n = 0;
+  auto add = [&](const void* src, int out_f, int in_f, bf16* dst, int out_p) {
+    rows::TransposeJob& j = tj.job[tj.n++];
+    j.src = static_cast<const bf16*>(src); j.src_ld = in_f; j.R = out_f; j.C = in_f;
+    j.dst = dst; j.dst_ld = out_p; j.Rp = out_p;
+  };
+  add(P.out_ints.w_bf16, d.C, hw, w.out_intsT, d.CP);
+  if (d.ctx) add(P.out_ctx.w_bf16, d.R, d.F, w.out_ctxT, d.RP);
+  if (d.gates) add(P.gate.w_bf16, d.Gd, 2 * d.F, w.gateT, d.Gd);
+  for (int br = 0; br < nbr; ++br)
+    for (int s = 0; s < 4; ++s)
+      if (d.act[s])
+        add((br ? P.enc_ctx : P.enc_ints).l2[s].w_bf16, d.outw[s], d.J, w.l2T[br][s], d.outw[s]);
+  return rows::transpose_bf16(tj, stream);
+}
+
+// The copies only depend on the weights, which are final when forward starts: a TRAINING forward launches them on
+// a side stream of the library's own, next to the forward GEMMs, and leaves a note for the backward call on the
+// same workspace, which then just waits for them (29 us off the critical path of a 1024-clip step).  A backward
+// without that note (eval-mode autograd, another workspace) transposes inline as before.
+struct SideTranspose {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t in = nullptr, out = nullptr;
+  const void* ws = nullptr;      // workspace whose W^T copies are in flight / done
+  int device = -1;
+};
+static thread_local SideTranspose g_side;
+
+static bool side_ready() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (g_side.stream && g_side.device == dev) return true;
+  const char* e = getenv("LIREC_SIDE_TRANSPOSE");
+  if (e && e[0] == '0') return false;
+  if (g_side.stream) return false;   // created for another device: keep it simple, inline on this one
+  if (cudaStreamCreateWithFlags(&g_side.stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+  if (cudaEventCreateWithFlags(&g_side.in, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&g_side.out, cudaEventDisableTiming) != cudaSuccess) {
+    g_side.stream = nullptr;
+    return false;
+  }
+  g_side.device = dev;
+  return true;
+}
+
 // ---------------------------------------------------------------------------
 int forward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lirec_batch& B, void* ws,
             float* out_ints, float* out_rels, cudaStream_t stream) {
@@ -335,6 +391,15 @@ int forward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lirec
   const int nbr = d.ctx ? 2 : 1;
   const int J = d.J, F = d.F;
   int rc;
+
+  g_side.ws = nullptr;
+  if (B.training && !dgrad_in_place(d.Ni) && side_ready()) {
+    LIREC_CUDA_OK(cudaEventRecord(g_side.in, stream));                 // weights (last Adam) are final here
+    LIREC_CUDA_OK(cudaStreamWaitEvent(g_side.stream, g_side.in, 0));
+    if ((rc = weight_transposes(d, P, w, g_side.stream)) != LIREC_OK) return rc;
+    LIREC_CUDA_OK(cudaEventRecord(g_side.out, g_side.stream));
+    g_side.ws = ws;
+  }
 
   {  // ones column for the bias-gradient GEMMs
     const int64_t n = d.onesP;
@@ -539,11 +604,6 @@ static bool defer_reductions() {
   const char* e = getenv("LIREC_DEFER_REDUCTIONS");
   return !(e && e[0] == '0');
 }
-// Below this many candidate rows backward multiplies by the weights in place instead of transposing them.
-static bool dgrad_in_place(int Ni) {
-  const char* e = getenv("LIREC_DGRAD_INPLACE_ROWS");   // read per call: the tests switch it
-  return Ni < (e ? atoi(e) : 1536);
-}
 static void out_split_t(lirec_gemm_problem& g, bf16* out, int64_t pitch, int row_off, int lo_off) {
   g.epi.out_kind = LIREC_OUT_SPLIT_BF16_T;
   g.epi.out = out; g.epi.out_ld_m = pitch; g.epi.out_col_off = row_off; g.epi.out_lo_off = lo_off;
@@ -612,21 +672,12 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
   // ---- [in, out] copies of the weights the data gradients multiply by ---------------------------
   const bool inplace = dgrad_in_place(Ni);
   if (!inplace) {
-    rows::TransposeJobs tj;
-    tj.n = 0;
-    auto add = [&](const void* src, int out_f, int in_f, bf16* dst, int out_p) {
-      rows::TransposeJob& j = tj.job[tj.n++];
-      j.src = static_cast<const bf16*>(src); j.src_ld = in_f; j.R = out_f; j.C = in_f;
-      j.dst = dst; j.dst_ld = out_p; j.Rp = out_p;
-    };
-    add(P.out_ints.w_bf16, d.C, hw, w.out_intsT, CP);
-    if (d.ctx) add(P.out_ctx.w_bf16, d.R, F, w.out_ctxT, RP);
-    if (d.gates) add(P.gate.w_bf16, Gd, 2 * F, w.gateT, Gd);
-    for (int br = 0; br < nbr; ++br)
-      for (int s = 0; s < 4; ++s)
-        if (d.act[s])
-        add((br ? P.enc_ctx : P.enc_ints).l2[s].w_bf16, d.outw[s], J, w.l2T[br][s], d.outw[s]);
-    if ((rc = rows::transpose_bf16(tj, stream)) != LIREC_OK) return rc;
+    if (g_side.ws == ws && g_side.stream) {               // launched next to this workspace's forward
+      LIREC_CUDA_OK(cudaStreamWaitEvent(stream, g_side.out, 0));
+      g_side.ws = nullptr;
+    } else if ((rc = weight_transposes(d, P, w, stream)) != LIREC_OK) {
+      return rc;
+    }
   }
 
   SplitCtx sc;

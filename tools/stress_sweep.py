@@ -65,6 +65,24 @@ def sweep_seg_max():
                    x.numel() * 4 + out.numel() * 2, ms)
 
 
+def sweep_softmax_pool():
+    """The softmax-weighted member of the segmented-reduction family (parity unpinned: the reference has none)."""
+    rng = np.random.default_rng(2)
+    for dim, mean_len in ((2048, 32), (768, 64), (2048, 128), (2048, 512)):
+        nseg = 2048 if mean_len < 512 else 512
+        lens = rng.integers(0, 2 * mean_len + 1, size=nseg)
+        off = np.zeros(nseg + 1, dtype=np.int32)
+        np.cumsum(lens, out=off[1:])
+        x = torch.randn(int(off[-1]), dim, device="cuda")
+        offd = torch.from_numpy(off).cuda()
+        ms = timeit(lambda: ops.seg_softmax_pool(x, offd, beta=1.5))
+        report("seg_softmax fwd", "dim=%d mean_len=%d nseg=%d" % (dim, mean_len, nseg), x.numel() * 4 + 2 * nseg * dim * 4, ms)
+        out, lse = ops.seg_softmax_pool(x, offd, beta=1.5)
+        dy = torch.randn_like(out)
+        ms = timeit(lambda: ops.seg_softmax_pool_bwd(x, offd, 1.5, None, out, lse, dy))
+        report("seg_softmax bwd", "dim=%d mean_len=%d nseg=%d" % (dim, mean_len, nseg), 2 * x.numel() * 4 + 3 * nseg * dim * 4, ms)
+
+
 def sweep_roi():
     rng = np.random.default_rng(1)
     T, C, H, W = 64, 2048, 13, 30
@@ -147,6 +165,7 @@ if __name__ == "__main__":
     print("# stress sweep on %s; HBM peak %.0f GB/s (MEASURED_PEAKS.json); L2 flushed between launches" % (
         torch.cuda.get_device_name(0), PEAK))
     sweep_seg_max()
+    sweep_softmax_pool()
     sweep_roi()
     sweep_gather()
     sweep_step()

@@ -440,6 +440,12 @@ int lirec_collate_gather(const int64_t* ds_cand_off, const int32_t* ds_cand, con
 int lirec_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                     void* param_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int32_t step, float grad_scale, void* stream);
+/* Same pass; coresident != 0 launches it in CTAs small enough to share an SM with a resident CTA of the
+ * persistent GEMM kernels (which leave ~18 % of the register file), for a range whose gradients are final while
+ * backward is still running on another stream.  Identical results.                                              */
+int lirec_adam_flat_ex(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                       void* param_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, int32_t step, float grad_scale, int32_t coresident, void* stream);
 
 /* ---- data parallel: in-switch gradient exchange, bucket by bucket --------
  * Replaces ncclAllReduce(flat gradient) of a data-parallel step (the reference is single-process, SURVEY.md
@@ -451,7 +457,9 @@ int lirec_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_
  * (multimem.st), and a second barrier — afterwards every rank holds the SUM over ranks in that range.
  * flag_ptrs_dev: device array [world] of every rank's peer-mapped, zero-initialised flag buffer of
  * lirec_dp_flag_words(world) uint32; `channel` (0..3) selects the flag slots, so chains for different buckets may
- * be in flight on different streams at the same time (all ranks must use the same channel for the same bucket). */
+ * be in flight on different streams at the same time (all ranks must use the same channel for the same bucket).
+ * coresident != 0 (all three passes): CTAs small enough to share an SM with a resident CTA of the persistent GEMM
+ * kernels, for a bucket exchanged on a side stream while backward still runs (see lirec_adam_flat_ex).          */
 int lirec_dp_flag_words(int32_t world);
 /* Exchange + optimizer + parameter broadcast in ONE pass (ZeRO-1 style), the default data-parallel step: every
  * rank owns the Adam moments of its 1/world shard.  For its shard it sums the gradients inside the switch
@@ -465,9 +473,9 @@ int lirec_dp_reduce_adam_bcast(const void* grad_multicast, const float* param, v
                                void* param_bf16_multicast, float* exp_avg, float* exp_avg_sq, int64_t n,
                                float lr, float beta1, float beta2, float eps, float weight_decay,
                                int32_t step, float grad_scale, int32_t rank, int32_t world,
-                               const void* flag_ptrs_dev, int32_t channel, void* stream);
+                               const void* flag_ptrs_dev, int32_t channel, int32_t coresident, void* stream);
 int lirec_dp_exchange(void* grad_multicast, int64_t offset, int64_t n, int32_t rank, int32_t world,
-                      const void* flag_ptrs_dev, int32_t channel, void* stream);
+                      const void* flag_ptrs_dev, int32_t channel, int32_t coresident, void* stream);
 
 /* The same pass over plain peer pointers instead of the multicast object (P2P loads of every rank's gradient
  * shard, P2P stores of the new parameters into every rank): the better transport at 2 ranks, where an in-switch
@@ -478,7 +486,7 @@ int lirec_dp_reduce_adam_bcast_peer(const void* peer_bases_dev, int64_t grad_off
                                     int64_t bf16_off, float* exp_avg, float* exp_avg_sq, int64_t n,
                                     float lr, float beta1, float beta2, float eps, float weight_decay,
                                     int32_t step, float grad_scale, int32_t rank, int32_t world,
-                                    const void* flag_ptrs_dev, int32_t channel, void* stream);
+                                    const void* flag_ptrs_dev, int32_t channel, int32_t coresident, void* stream);
 
 #ifdef __cplusplus
 }

@@ -31,6 +31,20 @@ bool pdl_enabled() {
 }
 void reset_launch_count() { g_launches = 0; }
 
+// Largest CTA of `kernel` (a multiple of 32 threads, <= cap) whose registers fit beside one resident GEMM CTA.
+// Registers are allocated per warp, the per-thread count rounded up to a multiple of 8.
+int coresident_threads(const void* kernel, int cap) {
+  cudaFuncAttributes a;
+  if (cudaFuncGetAttributes(&a, kernel) != cudaSuccess) {
+    cudaGetLastError();
+    return 64;
+  }
+  const int per_warp = ((a.numRegs + 7) / 8 * 8) * 32;
+  const int warps = gemm_free_registers() / (per_warp > 0 ? per_warp : 1);
+  const int t = 32 * (warps < 1 ? 1 : warps);
+  return t < cap ? t : cap;
+}
+
 // No CPU fallback and no other architecture: anything but sm_100 is an error.
 int check_arch() {
   static thread_local int cached_dev = -1;

@@ -66,6 +66,16 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// ---- launch shapes that fit NEXT TO a resident GEMM CTA ------------------------------------------------
+// The persistent GEMM kernels hold one CTA per SM for a whole launch: 320 threads x 168 registers (82 % of the
+// register file) and all but ~1.7 KB of shared memory.  A memory-bound pass meant to run CONCURRENTLY with
+// backward (the overlapped part of Adam, the gradient exchange of the gate + head bucket) is only co-scheduled
+// if one of its CTAs fits into what is left — 11.7 k registers, no shared memory: a 256-thread CTA of a
+// 47-register kernel does not (12.3 k), so the first "overlapped" versions simply ran after the GEMM had left
+// the SM.  coresident_threads(kernel) = the largest CTA (multiple of 32, <= cap) of `kernel` that still fits.
+int gemm_free_registers();                           // gemm_tcgen05.cu: 64 K minus one GEMM CTA's allocation
+int coresident_threads(const void* kernel, int cap);
+
 // ---- dropout hash (mirrored bit-for-bit by oracle/dropout.py) ---------------
 __host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
   h ^= h >> 16;

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(THREADS) reduce_adam_bcast_peer_kernel(const P
   const char* base[WORLD];
 #pragma unroll
   for (int r = 0; r < WORLD; ++r) base[r] = a.bases[r];
-  const float4* p_loc = reinterpret_cast<const float4*>(base[a.rank] + a.param_off);
+  const float4* p_loc = reinterpret_cast<const float4*>(a.bases[a.rank] + a.param_off);   // (no dynamic index into base[])
   for (int64_t i = a.beg4 + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < a.end4; i += stride) {
     float4 g[WORLD];
 #pragma unroll
@@ -227,8 +227,15 @@ using namespace lirec;
 
 extern "C" int lirec_dp_flag_words(int32_t world) { return 2 * dp::MAX_CHANNELS * std::max(world, 1); }
 
+// CTA size of a pass: 256 threads alone on the machine, or the largest CTA that fits beside a resident GEMM CTA
+// (common.cuh) when the pass is meant to run during backward
+template <typename K>
+static int pass_threads(K kernel, int32_t coresident) {
+  return coresident ? coresident_threads(reinterpret_cast<const void*>(kernel), dp::THREADS) : dp::THREADS;
+}
+
 extern "C" int lirec_dp_exchange(void* grad_multicast, int64_t offset, int64_t n, int32_t rank, int32_t world,
-                                 const void* flag_ptrs_dev, int32_t channel, void* stream) {
+                                 const void* flag_ptrs_dev, int32_t channel, int32_t coresident, void* stream) {
   LIREC_ENTER();
   LIREC_REQUIRE(grad_multicast && flag_ptrs_dev, "dp_exchange: null argument");
   LIREC_REQUIRE(n > 0 && n % 4 == 0 && offset >= 0 && offset % 4 == 0,
@@ -245,9 +252,10 @@ extern "C" int lirec_dp_exchange(void* grad_multicast, int64_t offset, int64_t n
   LIREC_CUDA_OK(cudaGetLastError());
   note_launch();
   if (end > beg) {
-    const int64_t per_cta = static_cast<int64_t>(dp::THREADS) * 4;
+    const int threads = pass_threads(dp::reduce_bcast_kernel, coresident);
+    const int64_t per_cta = static_cast<int64_t>(threads) * 4;
     const int grid = static_cast<int>(std::min<int64_t>((end - beg + per_cta - 1) / per_cta, 148 * 4));
-    dp::reduce_bcast_kernel<<<grid, dp::THREADS, 0, s>>>(mc, beg, end);
+    dp::reduce_bcast_kernel<<<grid, threads, 0, s>>>(mc, beg, end);
     LIREC_CUDA_OK(cudaGetLastError());
     note_launch();
   }
@@ -261,7 +269,8 @@ extern "C" int lirec_dp_reduce_adam_bcast(const void* grad_multicast, const floa
                                           void* param_bf16_multicast, float* exp_avg, float* exp_avg_sq, int64_t n,
                                           float lr, float beta1, float beta2, float eps, float weight_decay,
                                           int32_t step, float grad_scale, int32_t rank, int32_t world,
-                                          const void* flag_ptrs_dev, int32_t channel, void* stream) {
+                                          const void* flag_ptrs_dev, int32_t channel, int32_t coresident,
+                                          void* stream) {
   LIREC_ENTER();
   LIREC_REQUIRE(grad_multicast && param && param_multicast && param_bf16_multicast && exp_avg && exp_avg_sq &&
                     flag_ptrs_dev, "dp_reduce_adam_bcast: null argument");
@@ -292,9 +301,10 @@ extern "C" int lirec_dp_reduce_adam_bcast(const void* grad_multicast, const floa
   LIREC_CUDA_OK(cudaGetLastError());
   note_launch();
   if (a.end4 > a.beg4) {
-    const int64_t per_cta = static_cast<int64_t>(dp::THREADS) * 2;
+    const int threads = pass_threads(dp::reduce_adam_bcast_kernel, coresident);
+    const int64_t per_cta = static_cast<int64_t>(threads) * 2;
     const int grid = static_cast<int>(std::min<int64_t>((a.end4 - a.beg4 + per_cta - 1) / per_cta, 148 * 8));
-    dp::reduce_adam_bcast_kernel<<<grid, dp::THREADS, 0, s>>>(a);
+    dp::reduce_adam_bcast_kernel<<<grid, threads, 0, s>>>(a);
     LIREC_CUDA_OK(cudaGetLastError());
     note_launch();
   }
@@ -308,7 +318,8 @@ extern "C" int lirec_dp_reduce_adam_bcast_peer(const void* peer_bases_dev, int64
                                                int64_t bf16_off, float* exp_avg, float* exp_avg_sq, int64_t n,
                                                float lr, float beta1, float beta2, float eps, float weight_decay,
                                                int32_t step, float grad_scale, int32_t rank, int32_t world,
-                                               const void* flag_ptrs_dev, int32_t channel, void* stream) {
+                                               const void* flag_ptrs_dev, int32_t channel, int32_t coresident,
+                                               void* stream) {
   LIREC_ENTER();
   LIREC_REQUIRE(peer_bases_dev && exp_avg && exp_avg_sq && flag_ptrs_dev, "dp_reduce_adam_bcast_peer: null argument");
   LIREC_REQUIRE(n > 0 && n % 4 == 0, "dp_reduce_adam_bcast_peer: n=%lld must be a positive multiple of 4", (long long)n);
@@ -337,10 +348,13 @@ extern "C" int lirec_dp_reduce_adam_bcast_peer(const void* peer_bases_dev, int64
   LIREC_CUDA_OK(cudaGetLastError());
   note_launch();
   if (a.end4 > a.beg4) {
-    const int grid = static_cast<int>(std::min<int64_t>((a.end4 - a.beg4 + dp::THREADS - 1) / dp::THREADS, 148 * 8));
-    if (world == 2) dp::reduce_adam_bcast_peer_kernel<2><<<grid, dp::THREADS, 0, s>>>(a);
-    else if (world == 4) dp::reduce_adam_bcast_peer_kernel<4><<<grid, dp::THREADS, 0, s>>>(a);
-    else dp::reduce_adam_bcast_peer_kernel<8><<<grid, dp::THREADS, 0, s>>>(a);
+    const int threads = world == 2   ? pass_threads(dp::reduce_adam_bcast_peer_kernel<2>, coresident)
+                        : world == 4 ? pass_threads(dp::reduce_adam_bcast_peer_kernel<4>, coresident)
+                                     : pass_threads(dp::reduce_adam_bcast_peer_kernel<8>, coresident);
+    const int grid = static_cast<int>(std::min<int64_t>((a.end4 - a.beg4 + threads - 1) / threads, 148 * 8));
+    if (world == 2) dp::reduce_adam_bcast_peer_kernel<2><<<grid, threads, 0, s>>>(a);
+    else if (world == 4) dp::reduce_adam_bcast_peer_kernel<4><<<grid, threads, 0, s>>>(a);
+    else dp::reduce_adam_bcast_peer_kernel<8><<<grid, threads, 0, s>>>(a);
     LIREC_CUDA_OK(cudaGetLastError());
     note_launch();
   }

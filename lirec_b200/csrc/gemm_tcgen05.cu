@@ -1089,6 +1089,25 @@ static int record_end(ProfRec& rec, cudaStream_t stream) {
   return LIREC_OK;
 }
 
+}  // namespace gemm
+// see common.cuh: what one resident GEMM CTA leaves of an SM's 64 K registers (the larger of the two kernels)
+int gemm_free_registers() {
+  static int v = -1;
+  if (v < 0) {
+    int regs = 0;
+    for (const void* k : {reinterpret_cast<const void*>(gemm::lirec_gemm_tcgen05_kernel),
+                          reinterpret_cast<const void*>(gemm::lirec_gemm_tcgen05_pair_kernel)}) {
+      cudaFuncAttributes a;
+      if (cudaFuncGetAttributes(&a, k) == cudaSuccess) regs = a.numRegs > regs ? a.numRegs : regs;
+      else cudaGetLastError();
+    }
+    if (regs == 0) regs = 168;
+    v = 65536 - (gemm::NUM_THREADS / 32) * ((regs + 7) / 8 * 8) * 32;
+  }
+  return v;
+}
+namespace gemm {
+
 constexpr size_t GEMM_SMEM = GSTAGES * GSTAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
                              NUM_EPI_WARPS * EPI_STAGE_BYTES /*epilogue staging*/;
 static_assert(GEMM_SMEM <= 232448, "shared memory budget");

@@ -519,14 +519,26 @@ extern "C" int lirec_predict_tracks(const float* ints, const float* rels, const 
 extern "C" int lirec_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                                void* param_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
                                float weight_decay, int32_t step, float grad_scale, void* stream) {
+  return lirec_adam_flat_ex(param, grad, exp_avg, exp_avg_sq, param_bf16, n, lr, beta1, beta2, eps, weight_decay,
+                            step, grad_scale, 0, stream);
+}
+
+extern "C" int lirec_adam_flat_ex(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                                  void* param_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
+                                  float weight_decay, int32_t step, float grad_scale, int32_t coresident,
+                                  void* stream) {
   LIREC_ENTER();
   LIREC_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "adam: bad arguments");
   if (n == 0) return LIREC_OK;
   // bias corrections in double like torch's Python-side arithmetic
   const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), static_cast<double>(step)));
   const float bc2 = static_cast<float>(1.0 - pow(static_cast<double>(beta2), static_cast<double>(step)));
-  const int grid = static_cast<int>(std::min<int64_t>((n / 4 + 255) / 256 + 1, 148 * 16));
-  LIREC_CUDA_OK(launch_pdl(loss::adam_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), param, grad,
+  // coresident: CTAs that fit next to a resident GEMM CTA (common.cuh), so a pass launched on a side stream really
+  // runs during backward instead of after it; same kernel, same arithmetic, same element -> thread order
+  static const int co_threads = coresident_threads(reinterpret_cast<const void*>(loss::adam_kernel), 256);
+  const int threads = coresident ? co_threads : 256;
+  const int grid = static_cast<int>(std::min<int64_t>((n / 4 + threads - 1) / threads + 1, 148 * 16));
+  LIREC_CUDA_OK(launch_pdl(loss::adam_kernel, dim3(grid), dim3(threads), 0, static_cast<cudaStream_t>(stream), param, grad,
                            exp_avg, exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(param_bf16), n, lr, beta1, beta2, eps,
                            weight_decay, bc1, sqrtf(bc2), grad_scale));
   note_launch();

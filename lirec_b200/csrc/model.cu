@@ -100,6 +100,8 @@ struct Workspace {
   bf16* out_ctxT;     // [3J, RP]
   bf16* gateT;        // [6J, Gd]
   bf16* l2T[2][4];    // [J, outw]
+  int32_t* ref_out[3];  // per-reference tables of the context inverse CSRs (rows::ref_tables), [Nx] each
+  float* ref_w[3];
   float* pool;        // split-K partial gradients
   size_t pool_floats;
   size_t bytes;
@@ -194,6 +196,10 @@ static Workspace carve(const Dims& d, void* base) {
   w.gateT = static_cast<bf16*>(take((size_t)2 * d.F * d.Gd * 2));
   w.pool_floats = split_pool_floats(d);
   w.pool = static_cast<float*>(take(w.pool_floats * 4));
+  for (int y = 0; y < 3; ++y) {            // appended last: lirec_model_workspace_layout keeps its indices
+    w.ref_out[y] = d.ctx ? static_cast<int32_t*>(take((size_t)d.Nx * 4)) : nullptr;
+    w.ref_w[y] = d.ctx ? static_cast<float*>(take((size_t)d.Nx * 4)) : nullptr;
+  }
   w.bytes = off;
   return w;
 }
@@ -356,10 +362,27 @@ static int weight_transposes(const Dims& d, const lirec_model_params& P, const W
 // a side stream of the library's own, next to the forward GEMMs, and leaves a note for the backward call on the
 // same workspace, which then just waits for them (29 us off the critical path of a 1024-clip step).  A backward
 // without that note (eval-mode autograd, another workspace) transposes inline as before.
+static int context_ref_tables(const Dims& d, const lirec_batch& B, const Workspace& w, cudaStream_t stream) {
+  rows::RefTableJobs rj;
+  for (int y = 0; y < 3; ++y) {
+    rj.inv_idx[y] = B.inv_ctx_idx[y];
+    rj.ref_out[y] = w.ref_out[y];
+    rj.ref_w[y] = w.ref_w[y];
+  }
+  rj.owner = B.ctx_owner;
+  rj.seg_off = B.ctx_off;
+  rj.n = d.Nx;
+  return rows::ref_tables(rj, stream);
+}
+static bool has_ref_inputs(const Dims& d, const lirec_batch& B) {
+  return d.ctx && d.Nx > 0 && B.ctx_owner && B.ctx_off && B.inv_ctx_idx[0] && B.inv_ctx_idx[1] && B.inv_ctx_idx[2];
+}
+
 struct SideTranspose {
   cudaStream_t stream = nullptr;
   cudaEvent_t in = nullptr, out = nullptr;
   const void* ws = nullptr;      // workspace whose W^T copies are in flight / done
+  bool refs = false;             // ... and whose per-reference tables were built next to them
   int device = -1;
 };
 static thread_local SideTranspose g_side;
@@ -397,6 +420,8 @@ int forward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lirec
     LIREC_CUDA_OK(cudaEventRecord(g_side.in, stream));                 // weights (last Adam) are final here
     LIREC_CUDA_OK(cudaStreamWaitEvent(g_side.stream, g_side.in, 0));
     if ((rc = weight_transposes(d, P, w, g_side.stream)) != LIREC_OK) return rc;
+    g_side.refs = has_ref_inputs(d, B);       // index tables only: nothing of this step's forward is needed
+    if (g_side.refs && (rc = context_ref_tables(d, B, w, g_side.stream)) != LIREC_OK) return rc;
     LIREC_CUDA_OK(cudaEventRecord(g_side.out, g_side.stream));
     g_side.ws = ws;
   }
@@ -671,14 +696,19 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
 
   // ---- [in, out] copies of the weights the data gradients multiply by ---------------------------
   const bool inplace = dgrad_in_place(Ni);
+  bool refs_ready = false;
   if (!inplace) {
     if (g_side.ws == ws && g_side.stream) {               // launched next to this workspace's forward
       LIREC_CUDA_OK(cudaStreamWaitEvent(stream, g_side.out, 0));
       g_side.ws = nullptr;
+      refs_ready = g_side.refs;
     } else if ((rc = weight_transposes(d, P, w, stream)) != LIREC_OK) {
       return rc;
     }
   }
+  // per-reference tables: used when forward built them on the side stream (a few us off expand_bwd_t); building
+  // them inline would cost what they save
+  const bool use_refs = refs_ready && has_ref_inputs(d, B);
 
   SplitCtx sc;
   sc.pool = w.pool; sc.pool_floats = w.pool_floats; sc.used = 0; sc.jobs.n = 0;
@@ -812,6 +842,8 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
         j.n_unique = (s < 2) ? ncl : ntr;
         j.owner = br ? B.ctx_owner : nullptr;
         j.seg_off = br ? B.ctx_off : nullptr;
+        j.ref_out = (br && use_refs) ? w.ref_out[inv] : nullptr;
+        j.ref_w = (br && use_refs) ? w.ref_w[inv] : nullptr;
         j.drop = mk_drop(p, B.seed, br ? DS_L1_CTX : DS_L1_INTS, 0);
         j.out = w.dz1T[br][s];
         j.out_ld = 0;

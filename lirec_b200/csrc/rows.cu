@@ -11,6 +11,7 @@ namespace lirec {
 namespace rows {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---------------------------------------------------------------------------
 // Segmented max / mean over ragged [total, dim] fp32 rows.
@@ -230,6 +231,22 @@ expand_bwd_kernel(const ExpandBwdJobs jobs) {
 }
 
 
+// Per-reference (owner, 1 / segment length) of the context branch's three inverse CSRs, see rows.cuh.
+__global__ void __launch_bounds__(256)
+ref_tables_kernel(const RefTableJobs jobs) {
+  pdl_wait();
+  pdl_trigger();
+  const int y = blockIdx.y;
+  const int32_t* idx = y == 0 ? jobs.inv_idx[0] : y == 1 ? jobs.inv_idx[1] : jobs.inv_idx[2];
+  int32_t* out = y == 0 ? jobs.ref_out[0] : y == 1 ? jobs.ref_out[1] : jobs.ref_out[2];
+  float* wgt = y == 0 ? jobs.ref_w[0] : y == 1 ? jobs.ref_w[1] : jobs.ref_w[2];
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < jobs.n; q += gridDim.x * blockDim.x) {
+    const int o = jobs.owner[idx[q]];
+    out[q] = o;
+    wgt[q] = 1.0f / static_cast<float>(jobs.seg_off[o + 1] - jobs.seg_off[o]);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Same reduction, TRANSPOSED output: out[(j) * pitch + u] (hi rows [0, J), lo rows [J, 2J)), the
 // K-major B operand of the first-layer weight-gradient GEMM.  One CTA owns 64 consecutive unique rows
@@ -243,6 +260,9 @@ constexpr int EBT_REFS = 1536;
 #define LIREC_EBT_ZSPLIT 4
 #endif
 constexpr int EBT_ZSPLIT = LIREC_EBT_ZSPLIT;   // references cached in shared memory per CTA (the rest is read in place)
+#ifndef LIREC_EBT_PREFETCH
+#define LIREC_EBT_PREFETCH 1
+#endif
 #ifndef LIREC_EBT_MIN_BLOCKS
 #define LIREC_EBT_MIN_BLOCKS 4
 #endif
@@ -276,12 +296,19 @@ expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
   // The references of 64 consecutive unique rows are one contiguous span of the CSR: resolve
   // idx -> owner -> 1/len ONCE per CTA, one reference per thread (three dependent loads, all in flight
   // together), instead of once per thread per column chunk.
+  // With the per-reference tables of ref_tables() the chain is inv_off -> (idx, out, w) -> gradient rows: two
+  // dependent memory round trips less per CTA (a CTA lives for ~6 us, of which this chain was more than half).
+  __shared__ int32_t row_off[EBT_ROWS + 1];
+  if (threadIdx.x <= EBT_ROWS) row_off[threadIdx.x] = jb.inv_off[min(u0 + static_cast<int>(threadIdx.x), jb.n_unique)];
   const int q0 = jb.inv_off[u0], q1 = jb.inv_off[min(u0 + EBT_ROWS, jb.n_unique)];
   for (int q = q0 + threadIdx.x; q < min(q1, q0 + EBT_REFS); q += blockDim.x) {
     const int i = jb.inv_idx[q];
     int o = i;
     float w = 1.0f;
-    if (jb.owner) {
+    if (jb.ref_out) {
+      o = jb.ref_out[q];
+      w = jb.ref_w[q];
+    } else if (jb.owner) {
       o = jb.owner[i];
       w = 1.0f / static_cast<float>(jb.seg_off[o + 1] - jb.seg_off[o]);
     }
@@ -289,7 +316,7 @@ expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
   }
   __syncthreads();
   int beg = 0, end = 0;
-  if (live) { beg = jb.inv_off[u]; end = jb.inv_off[u + 1]; }
+  if (live) { beg = row_off[lr]; end = row_off[lr + 1]; }
   const uint32_t thr = drop_threshold(jb.drop.p);
   // blockIdx.z takes a slice of the column chunks: more, shorter CTAs fill the last wave of the ragged
   // job list (the ints-branch jobs have 10x fewer unique rows than the context-branch ones)
@@ -300,6 +327,20 @@ expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.f;
     const int j = c0 + q4;
+#if LIREC_EBT_PREFETCH
+    // Latency hiding without registers: the ReLU gate of this chunk (read after the reference loop) and the
+    // gradient pieces of the NEXT chunk are pulled into L2 now; a row's 64 columns are two 128-byte lines, taken
+    // by the first two lanes of its quad.
+    if (live && (threadIdx.x & 3) < 2) {
+      const int half = 32 * (threadIdx.x & 3);
+      prefetch_l2(jb.r1 + static_cast<int64_t>(u) * J + c0 + half);
+      if (c0 + EBT_COLS < c_end) {
+        for (int q = beg; q < min(end, beg + 4); ++q)
+          if (q - q0 < EBT_REFS)
+            prefetch_l2(jb.d_in + static_cast<int64_t>(ref_out[q - q0]) * jb.d_ld + c0 + EBT_COLS + half);
+      }
+    }
+#endif
     LIREC_EBT_UNROLL_PRAGMA
     for (int q = beg; q < end; ++q) {
       int i, o;
@@ -308,7 +349,10 @@ expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
         i = ref_row[q - q0]; o = ref_out[q - q0]; w = ref_w[q - q0];
       } else {
         i = jb.inv_idx[q]; o = i; w = 1.0f;
-        if (jb.owner) {
+        if (jb.ref_out) {
+          o = jb.ref_out[q];
+          w = jb.ref_w[q];
+        } else if (jb.owner) {
           o = jb.owner[i];
           w = 1.0f / static_cast<float>(jb.seg_off[o + 1] - jb.seg_off[o]);
         }
@@ -548,23 +592,34 @@ roi_mean_kernel(const float* __restrict__ maps, int C, int HW, int W, const int3
     const float* plane = maps + (static_cast<int64_t>(frame) * C + c0) * HW;
     if (w == W && n == HW && c0 + 3 < C && (reinterpret_cast<uintptr_t>(plane) & 15) == 0) {
       // whole frames (the clip-level pooling, visual_features.py:67-69): the four planes of this warp are ONE
-      // contiguous, 16-byte aligned run of 4 * HW floats — read it as 128-bit pieces (a third of the load
-      // instructions of the strided 4-byte form, which reached 37-44 % of the HBM peak at 32-64 frames) and
-      // file every element under its channel by comparing its index with the plane boundaries
+      // contiguous, 16-byte aligned run of 4 * HW floats, read as 128-bit pieces.  Piece i holds elements
+      // [4i, 4i + 4) and plane k elements [k HW, (k + 1) HW): all pieces in [ceil(k HW / 4), floor((k + 1) HW / 4))
+      // belong to plane k alone and cost one load + four adds; the (at most three) pieces that straddle a plane
+      // boundary are read element-wise by twelve lanes.  The first version classified every element by comparing
+      // its index with the boundaries — ~50 instructions per 16 bytes, issue-bound at 31-38 % of the HBM peak.
       const float4* p4 = reinterpret_cast<const float4*>(plane);
-      const int b1 = HW, b2 = 2 * HW, b3 = 3 * HW;
-#pragma unroll 4
-      for (int i = lane; i < HW; i += 32) {
-        const float4 v = __ldg(p4 + i);
-        const float x[4] = {v.x, v.y, v.z, v.w};
+      int lo[4], hi[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int e = 4 * i + t;
-          const int ch = (e >= b1) + (e >= b2) + (e >= b3);
-          acc[0] += (ch == 0) ? x[t] : 0.f;
-          acc[1] += (ch == 1) ? x[t] : 0.f;
-          acc[2] += (ch == 2) ? x[t] : 0.f;
-          acc[3] += (ch == 3) ? x[t] : 0.f;
+      for (int k = 0; k < 4; ++k) { lo[k] = (k * HW + 3) >> 2; hi[k] = ((k + 1) * HW) >> 2; }
+      // one piece of each of the four planes per iteration: eight independent 16-byte loads in flight per lane
+#pragma unroll 2
+      for (int i = lane; i < (HW >> 2) + 1; i += 32) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (lo[k] + i < hi[k]) {
+            const float4 v = __ldg(p4 + lo[k] + i);
+            acc[k] += (v.x + v.y) + (v.z + v.w);
+          }
+        }
+      }
+      if (lane < 12) {
+        const int k = 1 + (lane >> 2), b = k * HW;
+        if (b & 3) {
+          const int e = (b & ~3) + (lane & 3);
+          const float v = __ldg(plane + e);
+          const int ch = (e >= b) ? k : k - 1;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) acc[t] += (ch == t) ? v : 0.f;
         }
       }
     } else if (w == W) {
@@ -695,6 +750,17 @@ int expand_fwd(const ExpandFwdJobs& jobs, cudaStream_t stream) {
   if (max_out == 0 || jobs.n == 0) return LIREC_OK;
   dim3 grid(max_out, jobs.n);
   LIREC_CUDA_OK(launch_pdl(expand_fwd_kernel, grid, dim3(128), 0, stream, jobs));
+  note_launch();
+  return LIREC_OK;
+}
+
+int ref_tables(const RefTableJobs& jobs, cudaStream_t stream) {
+  if (jobs.n <= 0) return LIREC_OK;
+  LIREC_REQUIRE(jobs.owner && jobs.seg_off, "ref_tables: null argument");
+  for (int y = 0; y < 3; ++y)
+    LIREC_REQUIRE(jobs.inv_idx[y] && jobs.ref_out[y] && jobs.ref_w[y], "ref_tables: null table %d", y);
+  dim3 grid(std::min((jobs.n + 255) / 256, 148 * 4), 3);
+  LIREC_CUDA_OK(launch_pdl(ref_tables_kernel, grid, dim3(256), 0, stream, jobs));
   note_launch();
   return LIREC_OK;
 }
@@ -847,6 +913,7 @@ extern "C" int lirec_rows_expand_bwd(const float* d_in, int64_t d_ld, const floa
   j.d_in = d_in; j.d_ld = d_ld; j.r1 = r1; j.J = J; j.slot = slot;
   j.inv_off = inv_off; j.inv_idx = inv_idx; j.n_unique = n_unique;
   j.owner = owner; j.seg_off = seg_off; j.drop = drop;
+  j.ref_out = nullptr; j.ref_w = nullptr;
   j.out = reinterpret_cast<__nv_bfloat16*>(out_split);
   j.out_ld = out_ld;
   j.out_t_pitch = out_t_pitch;

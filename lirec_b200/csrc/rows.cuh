@@ -39,6 +39,8 @@ struct ExpandBwdJob {
   int32_t n_unique;
   const int32_t* owner;     // NULL (ints) or [n_rows] candidate of each context row
   const int32_t* seg_off;   // NULL or [n_out + 1]
+  const int32_t* ref_out;   // optional, parallel to inv_idx (ref_tables): owner[inv_idx[q]] ...
+  const float* ref_w;       // ... and 1 / its segment length, so the kernel skips two dependent lookups
   lirec_dropout drop;
   __nv_bfloat16* out;       // [n_unique, out_ld] hi|lo, or transposed [2J, out_t_pitch] (hi rows, lo rows)
   int64_t out_ld;
@@ -48,6 +50,18 @@ struct ExpandBwdJobs {
   ExpandBwdJob job[MAX_JOBS];
   int32_t n;
 };
+
+// Per-REFERENCE tables of the context branch's inverse CSRs: ref_out[q] = owner[inv_idx[q]] (the candidate row whose
+// gradient reference q reads) and ref_w[q] = 1 / (its number of context rows).
+struct RefTableJobs {
+  const int32_t* inv_idx[3];
+  int32_t* ref_out[3];
+  float* ref_w[3];
+  const int32_t* owner;
+  const int32_t* seg_off;
+  int32_t n;                // references per table (= context rows)
+};
+int ref_tables(const RefTableJobs& jobs, cudaStream_t stream);
 
 // dst[c, r] = src[r, c] (bf16), zero for R <= r < Rp
 struct TransposeJob {

@@ -56,7 +56,26 @@ fwd_kernel(const float* __restrict__ x, const float* __restrict__ scores, int sc
   Online o[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) o[k].init();
-  for (int r = beg; r < end; ++r) {
+  // rows four at a time: the loads of a batch are issued together (the online update is a dependent chain, and
+  // with one row per iteration a thread had a single 16-byte load in flight: 35-53 % of the HBM peak)
+  int r = beg;
+  for (; r + 3 < end; r += 4) {
+    float4 a[4], s[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[k] = ld4(x + static_cast<int64_t>(r + k) * dim + col);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (score_mode == 0) s[k] = a[k];
+      else if (score_mode == 1) s[k] = ld4(scores + static_cast<int64_t>(r + k) * dim + col);
+      else { const float t = scores[r + k]; s[k] = make_float4(t, t, t, t); }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[0].add(beta * s[k].x, a[k].x); o[1].add(beta * s[k].y, a[k].y);
+      o[2].add(beta * s[k].z, a[k].z); o[3].add(beta * s[k].w, a[k].w);
+    }
+  }
+  for (; r < end; ++r) {
     const float4 a = ld4(x + static_cast<int64_t>(r) * dim + col);
     float4 s;
     if (score_mode == 0) s = a;
@@ -94,6 +113,7 @@ bwd_elem_kernel(const float* __restrict__ x, const float* __restrict__ scores, i
   const float4 yy = ld4(y + static_cast<int64_t>(seg) * y_ld + col);
   const float4 ll = ld4(lse + static_cast<int64_t>(seg) * lse_ld + col);
   const float4 g = ld4(dy + static_cast<int64_t>(seg) * dy_ld + col);
+#pragma unroll 4
   for (int r = beg; r < end; ++r) {
     const int64_t at = static_cast<int64_t>(r) * dim + col;
     const float4 a = ld4(x + at);

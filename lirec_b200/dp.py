@@ -98,6 +98,7 @@ class SwitchReduceAdam:
     torch.distributed._symmetric_memory only allocates and rendezvous-es the buffers."""
 
     overlap = True
+    coresident = True        # overlapped passes in CTAs that fit beside a resident GEMM CTA (LIREC_DP_CORESIDENT=0: A/B)
 
     def __init__(self, model, optimizer, hdl=None, flags=None, flag_hdl=None, mode="bucket", offsets=None):
         self.model, self.optimizer = model, optimizer
@@ -114,6 +115,8 @@ class SwitchReduceAdam:
         first = "gates_ints.fc_out.weight" if "gates_ints.fc_out.weight" in names else "out_ints.weight"
         self.split = int(model._offsets[names.index(first)])
         self.n = int(model._flat.numel())
+        import os
+        self.coresident = os.environ.get("LIREC_DP_CORESIDENT", "1") != "0"
         assert self.split % 64 == 0 and self.n % 64 == 0
         if self.world > 1 and mode == "shard":
             optimizer._shard_sync = self.gather_moments
@@ -234,17 +237,19 @@ class SwitchReduceAdam:
     def _mc(self, what):
         return int(self.hdl.multicast_ptr) + self.offsets[what]
 
-    def _bucket(self, off, n, channel, stream, scale):
+    def _bucket(self, off, n, channel, stream, scale, co=False):
         from lirec_b200 import ops
         m, o = self.model, self.optimizer
         g = o.param_groups[0]
         if self.world > 1:
-            ops.dp_exchange(self._mc("grad"), off, n, self.rank, self.world, self._flag_ptrs.data_ptr(), channel, stream)
+            ops.dp_exchange(self._mc("grad"), off, n, self.rank, self.world, self._flag_ptrs.data_ptr(), channel, stream,
+                            coresident=co)
         ops.adam_flat(m._flat, m._flat_grad, o._m, o._v, m._flat_bf16, g["lr"], g["betas"][0], g["betas"][1],
-                      g["eps"], g["weight_decay"], o._t, scale, offset=off, n=n, stream=stream)
+                      g["eps"], g["weight_decay"], o._t, scale, offset=off, n=n, stream=stream, coresident=co)
 
-    def _shard_pass(self, bucket, channel, stream, scale):
-        """lirec_dp_reduce_adam_bcast over floats [off, off + n) on `stream`."""
+    def _shard_pass(self, bucket, channel, stream, scale, co=False):
+        """lirec_dp_reduce_adam_bcast over floats [off, off + n) on `stream`; co: the pass runs beside backward's
+        GEMMs (CTAs sized to share their SMs)."""
         from lirec_b200 import ops
         m, o = self.model, self.optimizer
         g = o.param_groups[0]
@@ -254,12 +259,12 @@ class SwitchReduceAdam:
                                           self.offsets["flat"] + 4 * off, self.offsets["bf16"] + 2 * off, o._m[off:],
                                           o._v[off:], n, g["lr"], g["betas"][0], g["betas"][1], g["eps"],
                                           g["weight_decay"], o._t, scale, self.rank, self.world,
-                                          self._flag_ptrs.data_ptr(), channel, stream)
+                                          self._flag_ptrs.data_ptr(), channel, stream, coresident=co)
         else:
             ops.dp_reduce_adam_bcast(self._mc("grad") + 4 * off, m._flat[off:], self._mc("flat") + 4 * off,
                                      self._mc("bf16") + 2 * off, o._m[off:], o._v[off:], n, g["lr"], g["betas"][0],
                                      g["betas"][1], g["eps"], g["weight_decay"], o._t, scale, self.rank, self.world,
-                                     self._flag_ptrs.data_ptr(), channel, stream)
+                                     self._flag_ptrs.data_ptr(), channel, stream, coresident=co)
 
     @torch.no_grad()
     def step(self, local_clips=None, global_clips=None):
@@ -281,7 +286,7 @@ class SwitchReduceAdam:
             bk = self.buckets()
             if armed and len(bk) == 2:
                 self.side.wait_event(self.ev_heads)          # recorded mid-backward on the main stream
-                self._shard_pass(bk[0], 0, self.side, scale)
+                self._shard_pass(bk[0], 0, self.side, scale, co=self.coresident)
                 self.ev_done.record(self.side)
                 self._shard_pass(bk[1], 1, main, scale)
                 main.wait_event(self.ev_done)
@@ -290,7 +295,7 @@ class SwitchReduceAdam:
                     self._shard_pass(b, ch, main, scale)
         elif armed:
             self.side.wait_event(self.ev_heads)              # recorded mid-backward on the main stream
-            self._bucket(self.split, self.n - self.split, 0, self.side, scale)
+            self._bucket(self.split, self.n - self.split, 0, self.side, scale, co=self.coresident)
             self.ev_done.record(self.side)
             if self.split:
                 self._bucket(0, self.split, 1, main, scale)

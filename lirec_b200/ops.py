@@ -252,20 +252,22 @@ def predict_tracks(ints, rels, cand_off, labels, rels_label, gt_tracks, n_rels):
 
 
 def adam_flat(param, grad, exp_avg, exp_avg_sq, param_bf16, lr, beta1, beta2, eps, weight_decay, step,
-              grad_scale=1.0, offset=0, n=None, stream=None):
-    """Fused Adam over floats [offset, offset + n) of the flat buffers (default: everything) on `stream`."""
+              grad_scale=1.0, offset=0, n=None, stream=None, coresident=False):
+    """Fused Adam over floats [offset, offset + n) of the flat buffers (default: everything) on `stream`.
+    coresident: CTAs that fit beside a resident GEMM CTA (a pass overlapped with backward on a side stream)."""
     L = _ext.lib()
     n = param.numel() - offset if n is None else n
     sp = _ext.stream_ptr() if stream is None else C.c_void_p(stream.cuda_stream)
-    _ext.check(L.lirec_adam_flat(_ext.ptr(param) + 4 * offset, _ext.ptr(grad) + 4 * offset,
+    _ext.check(L.lirec_adam_flat_ex(_ext.ptr(param) + 4 * offset, _ext.ptr(grad) + 4 * offset,
                                  _ext.ptr(exp_avg) + 4 * offset, _ext.ptr(exp_avg_sq) + 4 * offset,
                                  (_ext.ptr(param_bf16) + 2 * offset) if param_bf16 is not None else None, int(n),
                                  float(lr), float(beta1), float(beta2),
-                                 float(eps), float(weight_decay), int(step), float(grad_scale), sp))
+                                 float(eps), float(weight_decay), int(step), float(grad_scale), int(bool(coresident)),
+                                    sp))
 
 
 def dp_reduce_adam_bcast(grad_mc, param, param_mc, bf16_mc, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
-                         step, grad_scale, rank, world, flag_ptrs_dev, channel, stream=None):
+                         step, grad_scale, rank, world, flag_ptrs_dev, channel, stream=None, coresident=False):
     """In-switch gradient sum of this rank's shard + Adam on the shard + multicast of the new parameters and their
     bf16 shadow to every rank (lirec_dp_reduce_adam_bcast)."""
     L = _ext.lib()
@@ -274,24 +276,26 @@ def dp_reduce_adam_bcast(grad_mc, param, param_mc, bf16_mc, exp_avg, exp_avg_sq,
         C.c_void_p(int(grad_mc)), _ext.ptr(param), C.c_void_p(int(param_mc)), C.c_void_p(int(bf16_mc)),
         _ext.ptr(exp_avg), _ext.ptr(exp_avg_sq), int(n), float(lr), float(beta1), float(beta2), float(eps),
         float(weight_decay), int(step), float(grad_scale), int(rank), int(world), C.c_void_p(int(flag_ptrs_dev)),
-        int(channel), sp))
+        int(channel), int(bool(coresident)), sp))
 
 
 def dp_reduce_adam_bcast_peer(peer_bases_dev, grad_off, param_off, bf16_off, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                              weight_decay, step, grad_scale, rank, world, flag_ptrs_dev, channel, stream=None):
+                              weight_decay, step, grad_scale, rank, world, flag_ptrs_dev, channel, stream=None,
+                              coresident=False):
     """lirec_dp_reduce_adam_bcast over plain peer pointers (P2P loads / stores instead of multicast)."""
     L = _ext.lib()
     sp = _ext.stream_ptr() if stream is None else C.c_void_p(stream.cuda_stream)
     _ext.check(L.lirec_dp_reduce_adam_bcast_peer(
         C.c_void_p(int(peer_bases_dev)), int(grad_off), int(param_off), int(bf16_off), _ext.ptr(exp_avg),
         _ext.ptr(exp_avg_sq), int(n), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
-        float(grad_scale), int(rank), int(world), C.c_void_p(int(flag_ptrs_dev)), int(channel), sp))
+        float(grad_scale), int(rank), int(world), C.c_void_p(int(flag_ptrs_dev)), int(channel), int(bool(coresident)),
+        sp))
 
 
-def dp_exchange(grad_multicast_ptr, offset, n, rank, world, flag_ptrs_dev, channel, stream=None):
+def dp_exchange(grad_multicast_ptr, offset, n, rank, world, flag_ptrs_dev, channel, stream=None, coresident=False):
     """In-switch sum over ranks of floats [offset, offset + n) of the symmetric flat gradient buffer
     (lirec_dp_exchange: barrier, multimem reduce + broadcast of this rank's shard, barrier) on `stream`."""
     L = _ext.lib()
     sp = _ext.stream_ptr() if stream is None else C.c_void_p(stream.cuda_stream)
     _ext.check(L.lirec_dp_exchange(C.c_void_p(int(grad_multicast_ptr)), int(offset), int(n), int(rank), int(world),
-                                   C.c_void_p(int(flag_ptrs_dev)), int(channel), sp))
+                                   C.c_void_p(int(flag_ptrs_dev)), int(channel), int(bool(coresident)), sp))

@@ -153,6 +153,31 @@ def test_flat_adam_matches_torch_adam():
     assert torch.equal(pb, p.to(torch.bfloat16))
 
 
+def test_coresident_adam_launch_shape_is_bit_identical():
+    """lirec_adam_flat_ex(coresident=1) — CTAs sized to share an SM with a resident GEMM CTA, used for the pass
+    overlapped with backward — is the same arithmetic on the same elements: bit-identical buffers, also on a
+    sub-range and on a side stream."""
+    from lirec_b200 import ops
+    torch.manual_seed(1)
+    n = 1 << 20
+    p0, g = torch.randn(n, device="cuda"), torch.randn(n, device="cuda")
+    outs = []
+    for co in (False, True):
+        p, m, v = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+        pb = torch.zeros(n, device="cuda", dtype=torch.bfloat16)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        for step in (1, 2):
+            ops.adam_flat(p, g, m, v, pb, 1e-3, 0.9, 0.999, 1e-8, 1e-5, step, grad_scale=0.5, offset=4096,
+                          n=n - 8192, stream=side if co else None, coresident=co)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        outs.append((p, m, v, pb))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert torch.equal(outs[1][0][:4096], p0[:4096]) and torch.equal(outs[1][0][-4096:], p0[-4096:])
+
+
 @pytest.mark.parametrize("with_rels", [True, False])
 def test_prediction_argmaxes_are_bit_exact(with_rels):
     """Device-side evaluation arg-maxes (utils/evaluation.py:114-271) equal the numpy restatement on

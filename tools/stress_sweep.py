@@ -115,6 +115,22 @@ def sweep_roi():
         out = torch.empty(1, C, dtype=torch.bfloat16, device="cuda")
         ms = timeit(lambda: ops.roi_max_pool(maps, eld, offd, out_bf16=out))
         report("roi_max_pool (clip)", "frames=%d full %dx%d maps" % (nfr, H, W), nfr * C * H * W * 4, ms)
+    # the cache() shape of the same pooling (visual_features.py:60-69 for every clip of a movie): many clips per
+    # launch over distinct frames — a single 32-frame clip is 102 MB = 16 us at the HBM peak, less than the fixed
+    # cost of timing one launch with a flushed L2 (~20 us on every kernel of this sweep)
+    del maps
+    T2 = 512
+    maps2 = torch.rand(T2, C, H, W, device="cuda")
+    for nclip, nfr in ((16, 32), (8, 64), (64, 8)):
+        el = np.zeros((nclip * nfr, 5), dtype=np.int32)
+        el[:, 0], el[:, 2], el[:, 4] = np.arange(nclip * nfr), H, W
+        eld = torch.from_numpy(el).cuda()
+        offd = torch.from_numpy(np.arange(nclip + 1, dtype=np.int32) * nfr).cuda()
+        out = torch.empty(nclip, C, dtype=torch.bfloat16, device="cuda")
+        ms = timeit(lambda: ops.roi_max_pool(maps2, eld, offd, out_bf16=out))
+        report("roi_max_pool (clips)", "%d clips x %d frames, full %dx%d maps" % (nclip, nfr, H, W),
+               nclip * nfr * C * H * W * 4, ms)
+    del maps2
 
 
 def sweep_gather():
@@ -164,8 +180,8 @@ def sweep_step():
 if __name__ == "__main__":
     print("# stress sweep on %s; HBM peak %.0f GB/s (MEASURED_PEAKS.json); L2 flushed between launches" % (
         torch.cuda.get_device_name(0), PEAK))
-    sweep_seg_max()
-    sweep_softmax_pool()
-    sweep_roi()
-    sweep_gather()
-    sweep_step()
+    only = [t for t in os.environ.get("LIREC_SWEEP_ONLY", "").split(",") if t]      # e.g. roi,softmax
+    for name, fn in (("seg_max", sweep_seg_max), ("softmax", sweep_softmax_pool), ("roi", sweep_roi),
+                     ("gather", sweep_gather), ("step", sweep_step)):
+        if not only or name in only:
+            fn()

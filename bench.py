@@ -107,8 +107,9 @@ def parse_args():
                          "'bucket' = in-switch sum and full-replica Adam per bucket")
     ap.add_argument("--no_overlap", action="store_true",
                     help="N > 1, --dp_mode bucket: run the whole exchange after backward (no bucket overlapped with it)")
-    ap.add_argument("--overlap_adam", action="store_true",
-                    help="N = 1: run the gate + head bucket's Adam pass on a side stream during backward")
+    ap.add_argument("--overlap_adam", type=int, default=1,
+                    help="N = 1: run the gate + head bucket's Adam pass on a side stream during backward (default 1, "
+                         "as lirec_b200/mlp/train.py does; 0 = one Adam launch after backward)")
     ap.add_argument("--autograd_step", action="store_true",
                     help="drive the step through model()/loss()/backward()/optimizer.step() and the autograd engine "
                          "(the drop-in surface) instead of lirec_b200.mlp.train.train_step's native sequence")
@@ -297,6 +298,9 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+PROFILE_EVERY = 8
+
+
 class Bench:
     """One (preset, clips-per-GPU) configuration: model, loss, optimizer, cached dataset, staged batches."""
 
@@ -384,6 +388,8 @@ class Bench:
             sampler.region(True)
         e0.record()
         for i in range(steps):
+            if profile:                       # per-launch GEMM events on every PROFILE_EVERY-th step only: an event
+                _ext.profile_sample(i % PROFILE_EVERY == 0)      # pair per launch breaks the PDL chain of the step
             self.step(self.resident[i % len(self.resident)])
         e1.record()
         self.barrier()
@@ -393,9 +399,11 @@ class Bench:
             torch.cuda.cudart().cudaProfilerStop()
         ms = self.max_over_ranks(e0.elapsed_time(e1))
         prof = _ext.profile_end() if profile else []
+        self.profiled_steps = len(range(0, steps, PROFILE_EVERY)) if profile else 0
         return ms, prof, _ext.launch_counter - launches0
 
     def roofline(self, prof, steps, region_ms, clocks, pk):
+        steps = max(1, getattr(self, "profiled_steps", steps))      # the steps whose launches carried events
         gemm_ms = sum(p[0] for p in prof)
         exec_flops = sum(p[1] for p in prof)
         alg = algorithmic_flops(self.preset, self.n_cand, self.n_ctx)
@@ -552,13 +560,15 @@ def run_ours(args):
                                                 ncu_window=args.ncu_window)
     clips_total = args.batch * world * steps
     value = clips_total / (ms_total / 1e3)
+    profiled_steps_main = b.profiled_steps
     if args.only_value:
         if rank == 0:
             sampler.stop()
-            per = max(1, int(round(len(prof) / float(steps))))
+            psteps = max(1, b.profiled_steps)
+            per = max(1, int(round(len(prof) / float(psteps))))
             launches_ms = [float(np.mean([r[0] for r in prof[j::per]])) for j in range(per)] if prof else []
             print(json.dumps({"value": value, "ms_per_step": ms_total / steps, "only_value": True,
-                              "gemm_ms_per_step": sum(p[0] for p in prof) / steps,
+                              "gemm_ms_per_step": sum(p[0] for p in prof) / psteps,
                               "gemm_launch_ms": [round(x, 4) for x in launches_ms]}))
         return
 
@@ -764,9 +774,10 @@ def run_ours(args):
     if rank != 0:
         return
     if args.dump_profile:
-        per = int(round(len(prof) / float(steps)))
+        psteps = max(1, profiled_steps_main)
+        per = int(round(len(prof) / float(psteps)))
         with open(args.dump_profile, "w") as f:
-            f.write("# GEMM launches of one step (mean over %d steps): idx ms executed_GFLOP TFLOP/s tiles problems\n" % steps)
+            f.write("# GEMM launches of one step (mean over %d profiled steps of %d): idx ms executed_GFLOP TFLOP/s tiles problems\n" % (psteps, steps))
             for j in range(per):
                 rows = prof[j::per]
                 ms = float(np.mean([r[0] for r in rows]))
@@ -774,8 +785,11 @@ def run_ours(args):
                 f.write("%d %.4f %.2f %.1f %d %d\n" % (j, ms, fl / 1e9, fl / ms / 1e9 if ms > 0 else 0, rows[0][2], rows[0][3]))
     if world == 1 and not args.no_traffic:
         roofline["traffic"], roofline["traffic_note"] = measure_traffic(args)
+    roofline["profiled_steps"] = profiled_steps_main
     roofline["note"] = ("achieved = algorithmic fwd+bwd FLOPs of the step (SURVEY.md §8d, valid rows, no credit for "
-                        "dedup) / summed CUDA-event duration of the GEMM launches; executed = MMA FLOPs actually "
+                        "dedup) / summed CUDA-event duration of the GEMM launches, events recorded live on every "
+                        "8th step of the timed region (an event pair per launch on every step breaks the "
+                        "programmatic-dependent-launch chain and slows the region it measures); executed = MMA FLOPs actually "
                         "issued (layer 1 runs once per unique bank row; hi/lo split passes count 2-3x)")
     cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline_line(args.preset, args.cpu_clips, steps=3, warmup=1)
     e2e_headline = e2e_value if e2e_value is not None else e2e_pre

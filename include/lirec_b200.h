@@ -93,7 +93,11 @@ enum lirec_post {
   LIREC_POST_NONE = 0,
   LIREC_POST_DROPOUT = 1, /* v *= keep(m,n) / (1-p)                          */
   LIREC_POST_DRELU = 2,   /* v *= post_scale * [aux_hi(m,n) > 0]             */
-  LIREC_POST_DTANH = 3    /* v *= keep(m,n)/(1-p) * (1 - ((aux_hi+aux_lo)*(1-p))^2) */
+  LIREC_POST_DTANH = 3,   /* v *= keep(m,n)/(1-p) * (1 - ((aux_hi+aux_lo)*(1-p))^2) */
+  LIREC_POST_SIGN_MASK = 4 /* v unchanged; SIDE OUTPUT: bit (n & 31) of ((uint32_t*)aux)[m*aux_ld + (n >> 5)] =
+                            * [v > 0] — the ReLU gate of a forward layer as 1 bit per element, so the backward
+                            * scatter (lirec_rows_expand_bwd) need not re-read the fp32 activations.  Needs
+                            * N % 32 == 0, aux_ld >= N / 32 (in 32-bit words), no split-K.                  */
 };
 enum lirec_out {
   LIREC_OUT_F32 = 0,
@@ -143,6 +147,10 @@ int lirec_gemm_grouped(const lirec_gemm_problem* problems_host, int num_problems
  * roofline line: begin() starts recording, end() synchronises on the recorded events and returns
  * the number of launches, filling duration (ms), executed MMA flops, tile and problem counts. */
 int lirec_profile_begin(void);
+/* Pause (0) / resume (1) the recording between begin() and end() without dropping what was recorded: an event pair
+ * around every launch costs host time and breaks the programmatic-dependent-launch chain (13 % of a 64-clip step),
+ * so bench.py records the launches of every 8th step of its timed region only.                                 */
+int lirec_profile_sample(int32_t on);
 int lirec_profile_end(float* ms_host, double* flops_host, int32_t* tiles_host, int32_t* problems_host,
                       int max_records);
 /* Number of kernels the last lirec_* call on this thread launched. */

@@ -16,7 +16,7 @@ MAX_PASSES = 4
 MAX_PROBLEMS = 32
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
-POST_NONE, POST_DROPOUT, POST_DRELU, POST_DTANH = 0, 1, 2, 3
+POST_NONE, POST_DROPOUT, POST_DRELU, POST_DTANH, POST_SIGN_MASK = 0, 1, 2, 3, 4
 OUT_F32, OUT_SPLIT, OUT_SPLIT_T = 0, 1, 2
 
 
@@ -153,6 +153,7 @@ def lib():
                                                                                   C.c_void_p]
     L.lirec_adam_flat_ex.argtypes = [C.c_void_p] * 5 + [C.c_int64] + [C.c_float] * 5 + [C.c_int32, C.c_float,
                                                                                      C.c_int32, C.c_void_p]
+    L.lirec_profile_sample.argtypes = [C.c_int32]
     L.lirec_dp_flag_words.argtypes = [C.c_int32]
     L.lirec_dp_flag_words.restype = C.c_int
     L.lirec_dp_reduce_adam_bcast.argtypes = [C.c_void_p] * 6 + [C.c_int64] + [C.c_float] * 5 + [
@@ -189,7 +190,7 @@ EXPORTED_SYMBOLS = [
     "lirec_abi_version", "lirec_last_error", "lirec_device_check", "lirec_dropout_keep_host", "lirec_last_launch_count",
     "lirec_gemm_grouped", "lirec_profile_begin", "lirec_profile_end", "lirec_seg_reduce_f32", "lirec_seg_reduce_gather_f32", "lirec_seg_softmax_pool_fwd", "lirec_seg_softmax_pool_bwd", "lirec_rows_expand_fwd", "lirec_rows_expand_bwd",
     "lirec_split_f32", "lirec_cast_bf16", "lirec_gather_rows", "lirec_roi_max_pool_f32", "lirec_loss_track_fwd_bwd", "lirec_loss_rowmargin_fwd_bwd", "lirec_loss_ce_fwd_bwd", "lirec_predict_tracks",
-    "lirec_model_workspace_bytes", "lirec_model_workspace_layout", "lirec_model_forward", "lirec_model_backward", "lirec_model_backward_ex", "lirec_adam_flat", "lirec_adam_flat_ex", "lirec_dp_flag_words", "lirec_dp_exchange", "lirec_dp_reduce_adam_bcast", "lirec_dp_reduce_adam_bcast_peer",
+    "lirec_model_workspace_bytes", "lirec_model_workspace_layout", "lirec_model_forward", "lirec_model_backward", "lirec_model_backward_ex", "lirec_adam_flat", "lirec_adam_flat_ex", "lirec_profile_sample", "lirec_dp_flag_words", "lirec_dp_exchange", "lirec_dp_reduce_adam_bcast", "lirec_dp_reduce_adam_bcast_peer",
     "lirec_collate_arena_bound", "lirec_collate_tables", "lirec_collate_gather",
 ]
 
@@ -244,6 +245,10 @@ def gemm_grouped(problems):
 
 def profile_begin():
     check(lib().lirec_profile_begin())
+
+
+def profile_sample(on):
+    lib().lirec_profile_sample(1 if on else 0)
 
 
 def profile_end(max_records=65536):

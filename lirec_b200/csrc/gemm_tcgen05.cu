@@ -509,6 +509,13 @@ __device__ __forceinline__ void epilogue_chunk(const DevEpi& e, int M, int N, in
       v[j + 1] = k1 ? v[j + 1] * keep_scale * (1.0f - t1 * t1) : 0.f;
     }
   }
+  if (e.post == LIREC_POST_SIGN_MASK && m_true < M && full) {
+    // this thread holds 32 consecutive columns of row m: its ReLU gate is one 32-bit word
+    uint32_t mk = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mk |= (v[j] > 0.f ? 1u : 0u) << j;
+    reinterpret_cast<uint32_t*>(const_cast<__nv_bfloat16*>(e.aux))[static_cast<int64_t>(m_true) * e.aux_ld + (n0 >> 5)] = mk;
+  }
   after_math();
   if (staged_n && e.out_kind == LIREC_OUT_F32) {
     // [32 rows][8 x 16 B], piece q of row r at slot q ^ (r & 7): conflict-free both ways
@@ -1376,8 +1383,11 @@ int run_grouped(const lirec_gemm_problem* probs, int nprobs, cudaStream_t stream
     de.out_col_off = e.out_col_off;
     de.out_lo_off = e.out_lo_off;
     de.accumulate = e.accumulate;
-    if ((e.post == LIREC_POST_DRELU || e.post == LIREC_POST_DTANH) && e.aux == nullptr)
+    if ((e.post == LIREC_POST_DRELU || e.post == LIREC_POST_DTANH || e.post == LIREC_POST_SIGN_MASK) && e.aux == nullptr)
       return fail(LIREC_ERR_ARG, "problem %d: post op needs aux", idx);
+    if (e.post == LIREC_POST_SIGN_MASK &&
+        (g.N % 32 != 0 || e.aux_ld < g.N / 32 || (reinterpret_cast<uintptr_t>(e.aux) & 3) != 0))
+      return fail(LIREC_ERR_ARG, "problem %d: sign mask needs N %% 32 == 0 and aux_ld >= N / 32 words", idx);
     const uintptr_t ob = reinterpret_cast<uintptr_t>(e.out);
     if (e.out_kind == LIREC_OUT_F32)
       de.vec_ok = (e.out_ld_n == 1 && (ob & 15) == 0 && (e.out_ld_m % 4) == 0) ? 1 : 0;
@@ -1425,6 +1435,11 @@ extern "C" int lirec_profile_begin(void) {
   for (auto& r : g_prof) g_prof_pool.push_back(r);
   g_prof.clear();
   g_prof_on = true;
+  return LIREC_OK;
+}
+
+extern "C" int lirec_profile_sample(int32_t on) {
+  lirec::gemm::g_prof_on = on != 0;
   return LIREC_OK;
 }
 

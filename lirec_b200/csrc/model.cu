@@ -100,6 +100,7 @@ struct Workspace {
   bf16* out_ctxT;     // [3J, RP]
   bf16* gateT;        // [6J, Gd]
   bf16* l2T[2][4];    // [J, outw]
+  uint32_t* sgn[2][4];  // [n_unique, J / 32] ReLU gate of layer 1, one bit per element (LIREC_POST_SIGN_MASK)
   int32_t* ref_out[3];  // per-reference tables of the context inverse CSRs (rows::ref_tables), [Nx] each
   float* ref_w[3];
   float* pool;        // split-K partial gradients
@@ -196,6 +197,14 @@ static Workspace carve(const Dims& d, void* base) {
   w.gateT = static_cast<bf16*>(take((size_t)2 * d.F * d.Gd * 2));
   w.pool_floats = split_pool_floats(d);
   w.pool = static_cast<float*>(take(w.pool_floats * 4));
+  for (int br = 0; br < 2; ++br)
+    for (int s = 0; s < 4; ++s) {
+      w.sgn[br][s] = nullptr;
+      if (br < nbr && d.act[s] && d.J % 64 == 0) {
+        const int nu = (s < 2) ? (br ? d.nc : d.nci) : (br ? d.nt : d.nti);
+        w.sgn[br][s] = static_cast<uint32_t*>(take((size_t)nu * (d.J / 32) * 4));
+      }
+    }
   for (int y = 0; y < 3; ++y) {            // appended last: lirec_model_workspace_layout keeps its indices
     w.ref_out[y] = d.ctx ? static_cast<int32_t*>(take((size_t)d.Nx * 4)) : nullptr;
     w.ref_w[y] = d.ctx ? static_cast<float*>(take((size_t)d.Nx * 4)) : nullptr;
@@ -449,6 +458,11 @@ int forward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lirec
       g.epi.bias = enc.l1[s].bias;
       g.epi.act = LIREC_ACT_RELU;
       out_f32(g, w.r1[br][s], J);
+      if (w.sgn[br][s]) {                    // the gate of relu, 1 bit per element, for backward's scatter-reduce
+        g.epi.post = LIREC_POST_SIGN_MASK;
+        g.epi.aux = w.sgn[br][s];
+        g.epi.aux_ld = J / 32;
+      }
       pr.push_back(g);
     }
   }
@@ -835,6 +849,8 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
         j.d_in = w.da2[br] + s * J;
         j.d_ld = 4 * J;
         j.r1 = w.r1[br][s];
+        j.sign = w.sgn[br][s];
+        j.sign_ld = J / 32;
         j.J = J;
         j.slot = s;
         j.inv_off = br ? B.inv_ctx_off[inv] : B.inv_cand_off[inv];

@@ -327,13 +327,15 @@ expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.f;
     const int j = c0 + q4;
+    uint2 gate = make_uint2(0u, 0u);       // issued ahead of the reference loop (c0 % 64 == 0: 8-byte aligned)
+    if (live && jb.sign) gate = *reinterpret_cast<const uint2*>(jb.sign + static_cast<int64_t>(u) * jb.sign_ld + (c0 >> 5));
 #if LIREC_EBT_PREFETCH
     // Latency hiding without registers: the ReLU gate of this chunk (read after the reference loop) and the
     // gradient pieces of the NEXT chunk are pulled into L2 now; a row's 64 columns are two 128-byte lines, taken
     // by the first two lanes of its quad.
     if (live && (threadIdx.x & 3) < 2) {
       const int half = 32 * (threadIdx.x & 3);
-      prefetch_l2(jb.r1 + static_cast<int64_t>(u) * J + c0 + half);
+      if (!jb.sign) prefetch_l2(jb.r1 + static_cast<int64_t>(u) * J + c0 + half);
       if (c0 + EBT_COLS < c_end) {
         for (int q = beg; q < min(end, beg + 4); ++q)
           if (q - q0 < EBT_REFS)
@@ -377,7 +379,16 @@ expand_bwd_t_kernel(const ExpandBwdJobs jobs) {
         acc[4 * k + 2] += w * g[k].z; acc[4 * k + 3] += w * g[k].w;
       }
     }
-    if (live) {
+    if (live && jb.sign) {
+      // ReLU gate from the 1-bit-per-element mask of the forward GEMM (8 bytes per row and chunk instead of 256)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t bits = ((k < 2) ? gate.x : gate.y) >> (16 * (k & 1) + q4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (!((bits >> e) & 1u)) acc[4 * k + e] = 0.f;
+      }
+    } else if (live) {
       const float* rp = jb.r1 + static_cast<int64_t>(u) * J + j;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -783,6 +794,9 @@ int expand_bwd(const ExpandBwdJobs& jobs, cudaStream_t stream) {
       LIREC_REQUIRE(j.J % EBT_COLS == 0 && j.out_t_pitch % 8 == 0 && j.out_t_pitch >= j.n_unique &&
                         (reinterpret_cast<uintptr_t>(j.out) & 15) == 0,
                     "expand_bwd: transposed output needs J %% 64 == 0 and a 16-byte aligned pitch");
+      LIREC_REQUIRE(!j.sign || ((reinterpret_cast<uintptr_t>(j.sign) & 7) == 0 && j.sign_ld % 2 == 0 &&
+                                j.sign_ld >= j.J / 32),
+                    "expand_bwd: sign mask must be 8-byte aligned with an even pitch >= J / 32 words");
     }
     int max_j = 0;
     for (int i = 0; i < jobs.n; ++i) max_j = std::max(max_j, jobs.job[i].J);
@@ -914,6 +928,7 @@ extern "C" int lirec_rows_expand_bwd(const float* d_in, int64_t d_ld, const floa
   j.inv_off = inv_off; j.inv_idx = inv_idx; j.n_unique = n_unique;
   j.owner = owner; j.seg_off = seg_off; j.drop = drop;
   j.ref_out = nullptr; j.ref_w = nullptr;
+  j.sign = nullptr; j.sign_ld = 0;
   j.out = reinterpret_cast<__nv_bfloat16*>(out_split);
   j.out_ld = out_ld;
   j.out_t_pitch = out_t_pitch;

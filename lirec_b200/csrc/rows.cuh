@@ -33,6 +33,8 @@ struct ExpandBwdJob {
   const float* d_in;        // [n_out, d_ld] fp32 (column offset of the slot already applied)
   int64_t d_ld;
   const float* r1;          // [n_unique, J]
+  const uint32_t* sign;     // optional (transposed form): bit (j & 31) of sign[u * sign_ld + (j >> 5)] = [r1[u, j] > 0],
+  int64_t sign_ld;          // as the layer-1 GEMM epilogue writes it (LIREC_POST_SIGN_MASK); read INSTEAD of r1
   int32_t J, slot;
   const int32_t* inv_off;   // [n_unique + 1]
   const int32_t* inv_idx;   // table rows referencing each unique row

@@ -213,3 +213,24 @@ def test_transposed_split_store_edges(rows, in_f, pitch):
     got = (dxT[:in_f, :rows].double() + dxT[in_p:in_p + in_f, :rows].double()).t()
     assert _rel(got, ref) < 2e-5
     assert (dxT[:, rows:] == 7).all() and (dxT[in_f:in_p] == 7).all() and (dxT[in_p + in_f:] == 7).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(20000, 512, 768), (530, 512, 2048), (64, 64, 64)])      # pair kernel, single-CTA
+def test_sign_mask_side_output(M, N, K):
+    """LIREC_POST_SIGN_MASK: next to relu(a b^T + bias) the epilogue writes [v > 0] as one bit per element
+    (word n >> 5 of row m, bit n & 31) — the ReLU gate backward's scatter-reduce reads instead of the activations."""
+    from lirec_b200 import _ext, ops
+    a, b = _rnd(M, K), _rnd(N, K)
+    bias = torch.randn(N, device="cuda") * 3
+    out = torch.full((M, N), float("nan"), device="cuda")
+    mask = torch.full((M + 3, N // 32 + 2), -1, dtype=torch.int32, device="cuda")     # wider pitch, guard rows
+    ops.gemm_grouped([ops.gemm_problem(M, N, [(_ext.operand(a), 0, 0, _ext.operand(b), 0, 0, K)], bias=bias,
+                                       act=ops.ACT_RELU, post=ops.POST_SIGN_MASK, aux=mask, out=out)])
+    torch.cuda.synchronize()
+    ref = torch.relu(a.double() @ b.double().t() + bias.double())
+    assert _rel(out, ref) < TOL
+    bits = (out > 0).view(M, N // 32, 32).to(torch.int64)
+    words = (bits << torch.arange(32, device="cuda")).sum(-1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+    assert torch.equal(mask[:M, :N // 32], words)
+    assert bool((mask[M:] == -1).all()) and bool((mask[:, N // 32:] == -1).all())

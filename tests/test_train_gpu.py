@@ -151,3 +151,33 @@ def test_native_train_step_equals_autograd_path(opt_preset, preset):
         finals.append({k: v.clone() for k, v in model.state_dict().items()})
     for k in finals[0]:
         assert torch.equal(finals[0][k], finals[1][k]), k
+
+
+@pytest.mark.parametrize("preset", ["int_rel_ch", "modalities"])
+def test_overlapped_adam_takes_the_same_steps(opt_preset, preset):
+    """--overlap_adam 1 (the single-GPU default): the gate + head parameters' Adam pass runs on a side stream behind
+    backward's heads-final event, in co-resident CTAs; the encoder parameters follow after backward.  Same kernel,
+    same elements: the trajectory is bit-identical to the plain optimizer step."""
+    from lirec_b200 import dp
+    from lirec_b200.mixed_utils import synthetic
+    from helpers import make_model
+    import lirec_b200.mlp.train as TR
+    pbs = [synthetic.make_batch(16, seed=30 + i, preset=preset).to_device("cuda") for i in range(3)]
+    finals = []
+    for overlap in (False, True):
+        opt_preset(preset, fused_adam=1, lr=1e-3)
+        model, loss, optimizer = make_model(seed=5)
+        model.train()
+        fused = dp.SwitchReduceAdam.attach(model, optimizer, single_gpu=True) if overlap else None
+        assert (fused is not None) == overlap
+        for s in range(3):
+            TR.train_step(model, loss, optimizer, pbs[s], 1, fused)
+        torch.cuda.synchronize()
+        finals.append(({k: v.clone() for k, v in model.state_dict().items()}, optimizer._m.clone(), optimizer._v.clone(),
+                       model._flat_bf16.clone()))
+        if fused is not None:
+            fused.detach()
+    for k in finals[0][0]:
+        assert torch.equal(finals[0][0][k], finals[1][0][k]), k
+    for a, b in zip(finals[0][1:], finals[1][1:]):
+        assert torch.equal(a, b)

@@ -182,7 +182,9 @@ int lirec_seg_reduce_gather_f32(const float* x, const int32_t* row_idx, const in
  * `scores` [total, dim]; 2: one score per row `scores` [total] (attention pooling).  An empty segment gives zeros.
  * lse: log-normaliser the backward needs, [nseg, lse_ld] (modes 0 / 1) or [nseg] (mode 2); may be NULL in fwd.
  * bwd writes d_x [total, dim] for every row of every segment and, if not NULL, d_scores ([total, dim] in mode 1,
- * [total] in mode 2; in mode 0 the score path is folded into d_x).                                            */
+ * [total] in mode 2; in mode 0 the score path is folded into d_x).  total_rows > 0: the rows of d_x / d_scores
+ * outside [seg_off[0], seg_off[nseg]) — rows no segment owns — are zero-filled by the same launch, so the caller
+ * need not clear the buffers first (a memset of d_x costs half the kernel's own time); 0: they are left untouched. */
 int lirec_seg_softmax_pool_fwd(const float* x, const float* scores, int32_t score_mode,
                                const int32_t* seg_off, int32_t nseg, int32_t dim, float beta,
                                float* out, int64_t out_ld, float* lse, int64_t lse_ld, void* stream);
@@ -190,7 +192,7 @@ int lirec_seg_softmax_pool_bwd(const float* x, const float* scores, int32_t scor
                                const int32_t* seg_off, int32_t nseg, int32_t dim, float beta,
                                const float* out, int64_t out_ld, const float* lse, int64_t lse_ld,
                                const float* d_out, int64_t d_out_ld, float* d_x, float* d_scores,
-                               void* stream);
+                               int64_t total_rows, void* stream);
 
 /* ---- ragged row kernels of the modality encoder --------------------------
  * Layer-1 outputs are computed once per UNIQUE bank row (clip text, clip
@@ -347,13 +349,17 @@ typedef struct lirec_model_cfg {
   int32_t joint_dim;                         /* J = 512                                */
   int32_t gate_dim;                          /* joint_dim * mid_m_ints = 3072          */
   int32_t n_classes, n_rels;
-  int32_t ctx, gates;                        /* opt.ctx, opt.gates (opt.ints is 1)     */
+  int32_t ctx, gates;                        /* opt.ctx, opt.gates (opt.ints: no_ints) */
   int32_t guard_zero;                        /* 1: MaxTracks divider guard (model.py:303) */
   float dropout_p;                           /* opt.dropout                            */
   int32_t slot_mask;                         /* bit s: modality slot present (0 txt, 1 vis, 2 tracks1,
                                                 3 tracks2); 0 = all.  Modalities with opt.modality 't' / 'v'
                                                 or without tracks (model.py:27-46, 78-86) drop slots; the
                                                 concatenated feature shrinks accordingly               */
+  int32_t no_ints;                           /* 1: opt.ints == 0 (model.py:102, 140, 151, 208, 220, 256, 278, 335) — no
+                                                interaction branch and no interaction head: the model is the context
+                                                branch + relationship head (needs ctx = 1, gates = 0; out_ints /
+                                                d_ints / enc_ints / out_ints parameters are ignored and may be NULL) */
 } lirec_model_cfg;
 
 /* Packed ragged batch (device pointers).  Every encoder row — candidate row or context

@@ -81,7 +81,7 @@ class ModelCfg(C.Structure):
                 ("joint_dim", C.c_int32), ("gate_dim", C.c_int32),
                 ("n_classes", C.c_int32), ("n_rels", C.c_int32),
                 ("ctx", C.c_int32), ("gates", C.c_int32), ("guard_zero", C.c_int32),
-                ("dropout_p", C.c_float), ("slot_mask", C.c_int32)]
+                ("dropout_p", C.c_float), ("slot_mask", C.c_int32), ("no_ints", C.c_int32)]
 
 
 class Batch(C.Structure):
@@ -124,7 +124,7 @@ def lib():
                                              C.c_float, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
     L.lirec_seg_softmax_pool_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                              C.c_float, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
-                                             C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+                                             C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.lirec_rows_expand_fwd.argtypes = [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                                            C.c_int32, Dropout, C.c_void_p, C.c_int64,
                                                            C.c_void_p, C.c_void_p]

@@ -42,6 +42,8 @@ struct Dims {
   int ones_rows;
   int NiP, ncP[2], ntP[2], onesP;   // row pitches of the transposed gradient buffers (multiples of 64)
   bool ctx, gates;
+  bool ints;           // interaction (candidate) branch present: opt.ints (reference model.py:102, 140, 151, 208)
+  int br0;             // first branch of the loops over {0: ints, 1: ctx}
 };
 
 static Dims make_dims(const lirec_model_cfg& c, const lirec_batch& b) {
@@ -69,6 +71,8 @@ static Dims make_dims(const lirec_model_cfg& c, const lirec_batch& b) {
   d.inw[0] = c.text_dim; d.inw[1] = c.visual_dim; d.inw[2] = c.track_dim; d.inw[3] = c.track_dim;
   d.ctx = c.ctx != 0;
   d.gates = c.gates != 0;
+  d.ints = c.no_ints == 0;
+  d.br0 = d.ints ? 0 : 1;
   d.ones_rows = std::max(std::max(d.Ni, d.nc), d.nt);
   d.NiP = (int)round_up(d.Ni, 64);
   d.ncP[0] = (int)round_up(d.nci, 64); d.ncP[1] = (int)round_up(d.nc, 64);
@@ -135,10 +139,10 @@ static size_t split_pool_floats(const Dims& d) {
     if (S > 1) n += (size_t)S * out_f * in_f;
   };
   const int hw = d.gates ? d.Gd : d.F;
-  add(d.C, hw, 3, d.Ni); add(d.C, 1, 2, d.Ni);
+  if (d.ints) { add(d.C, hw, 3, d.Ni); add(d.C, 1, 2, d.Ni); }
   if (d.ctx) { add(d.R, d.F, 3, d.Ni); add(d.R, 1, 2, d.Ni); }
   if (d.gates) { add(d.Gd, d.F, 3, d.Ni); add(d.Gd, d.F, 3, d.Ni); add(d.Gd, 1, 2, d.Ni); }
-  for (int br = 0; br < (d.ctx ? 2 : 1); ++br) {
+  for (int br = d.br0; br < (d.ctx ? 2 : 1); ++br) {
     const int ncl = br ? d.nc : d.nci, ntr = br ? d.nt : d.nti;
     for (int s = 0; s < 4; ++s) {
       if (!d.act[s]) continue;
@@ -148,7 +152,7 @@ static size_t split_pool_floats(const Dims& d) {
     }
   }
   // forward reuses the pool for the split interaction head (backward starts after forward has drained it)
-  const int hs = head_split(d.Ni, hw);
+  const int hs = d.ints ? head_split(d.Ni, hw) : 1;
   if (hs > 1) n = std::max(n, (size_t)hs * d.Ni * d.C);
   return n;
 }
@@ -168,9 +172,10 @@ static Workspace carve(const Dims& d, void* base) {
       w.dz1T[br][s] = nullptr;
       w.l2T[br][s] = nullptr;
     }
+  w.a2[0] = w.f2[0] = w.dz2T[0] = nullptr;
   w.a2[1] = w.f2[1] = w.dz2T[1] = nullptr;
-  w.da2[1] = nullptr;
-  for (int br = 0; br < nbr; ++br) {
+  w.da2[0] = w.da2[1] = nullptr;
+  for (int br = d.br0; br < nbr; ++br) {
     const int ncl = br ? d.nc : d.nci, ntr = br ? d.nt : d.nti;
     for (int s = 0; s < 4; ++s) {
       if (!d.act[s]) continue;
@@ -200,7 +205,7 @@ static Workspace carve(const Dims& d, void* base) {
   for (int br = 0; br < 2; ++br)
     for (int s = 0; s < 4; ++s) {
       w.sgn[br][s] = nullptr;
-      if (br < nbr && d.act[s] && d.J % 64 == 0) {
+      if (br >= d.br0 && br < nbr && d.act[s] && d.J % 64 == 0) {
         const int nu = (s < 2) ? (br ? d.nc : d.nci) : (br ? d.nt : d.nti);
         w.sgn[br][s] = static_cast<uint32_t*>(take((size_t)nu * (d.J / 32) * 4));
       }
@@ -319,10 +324,13 @@ static int validate(const lirec_model_cfg* cfg, const lirec_model_params* P, con
   LIREC_REQUIRE(cfg->text_dim % 8 == 0 && cfg->visual_dim % 8 == 0 && cfg->track_dim % 8 == 0,
                 "model: feature dims must be multiples of 8");
   LIREC_REQUIRE(!cfg->gates || cfg->ctx, "model: gates need the context branch");
+  LIREC_REQUIRE(!cfg->no_ints || (cfg->ctx && !cfg->gates),
+                "model: without the interaction branch (opt.ints = 0) the model is the context branch and its "
+                "relationship head alone: ctx = 1, gates = 0 (the reference's GatingUnit needs both, model.py:349-352)");
   LIREC_REQUIRE(!cfg->ctx || (cfg->slot_mask & 15) == 0 || (cfg->slot_mask & 15) == 15,
                 "model: the context models always use all four modality slots (slot_mask=%d)", cfg->slot_mask);
   LIREC_REQUIRE(!cfg->gates || cfg->gate_dim % 8 == 0, "model: gate_dim=%d", cfg->gate_dim);
-  LIREC_REQUIRE(cfg->n_classes > 0 && (!cfg->ctx || cfg->n_rels > 0), "model: n_classes=%d n_rels=%d",
+  LIREC_REQUIRE((cfg->no_ints || cfg->n_classes > 0) && (!cfg->ctx || cfg->n_rels > 0), "model: n_classes=%d n_rels=%d",
                 cfg->n_classes, cfg->n_rels);
   LIREC_REQUIRE(B->n_cand > 0, "model: empty batch");
   LIREC_REQUIRE(B->n_clip_ints > 0 && B->n_track_ints > 0 && B->n_clip >= B->n_clip_ints &&
@@ -357,10 +365,10 @@ static int weight_transposes(const Dims& d, const lirec_model_params& P, const W
     j.src = static_cast<const bf16*>(src); j.src_ld = in_f; j.R = out_f; j.C = in_f;
     j.dst = dst; j.dst_ld = out_p; j.Rp = out_p;
   };
-  add(P.out_ints.w_bf16, d.C, hw, w.out_intsT, d.CP);
+  if (d.ints) add(P.out_ints.w_bf16, d.C, hw, w.out_intsT, d.CP);
   if (d.ctx) add(P.out_ctx.w_bf16, d.R, d.F, w.out_ctxT, d.RP);
   if (d.gates) add(P.gate.w_bf16, d.Gd, 2 * d.F, w.gateT, d.Gd);
-  for (int br = 0; br < nbr; ++br)
+  for (int br = d.br0; br < nbr; ++br)
     for (int s = 0; s < 4; ++s)
       if (d.act[s])
         add((br ? P.enc_ctx : P.enc_ints).l2[s].w_bf16, d.outw[s], d.J, w.l2T[br][s], d.outw[s]);
@@ -443,7 +451,7 @@ int forward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lirec
 
   // ---- layer 1 on the unique bank rows: relu(x W1^T + b1) -------------------
   std::vector<lirec_gemm_problem> pr;
-  for (int br = 0; br < nbr; ++br) {
+  for (int br = d.br0; br < nbr; ++br) {
     const lirec_encoder& enc = br ? P.enc_ctx : P.enc_ints;
     const int ncl = br ? d.nc : d.nci, ntr = br ? d.nt : d.nti;
     for (int s = 0; s < 4; ++s) {
@@ -472,9 +480,9 @@ int forward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lirec
   {
     rows::ExpandFwdJobs jobs;
     memset(&jobs, 0, sizeof(jobs));
-    jobs.n = nbr;
-    for (int br = 0; br < nbr; ++br) {
-      rows::ExpandFwdJob& j = jobs.job[br];
+    jobs.n = nbr - d.br0;
+    for (int br = d.br0; br < nbr; ++br) {
+      rows::ExpandFwdJob& j = jobs.job[br - d.br0];
       for (int s = 0; s < 4; ++s) j.r1[s] = w.r1[br][s];
       j.J = J;
       j.rows = br ? B.ctx_rows : B.cand_rows;
@@ -492,7 +500,7 @@ int forward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lirec
 
   // ---- layer 2 + tanh + dropout into the concat slices -------------------------
   pr.clear();
-  for (int br = 0; br < nbr; ++br) {
+  for (int br = d.br0; br < nbr; ++br) {
     const lirec_encoder& enc = br ? P.enc_ctx : P.enc_ints;
     for (int s = 0; s < 4; ++s) {
       if (!d.act[s]) continue;
@@ -545,7 +553,8 @@ int forward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lirec
 
   // ---- interaction head -----------------------------------------------------------
   pr.clear();
-  {
+  if (d.ints) {
+    LIREC_REQUIRE(out_ints != nullptr, "model: out_ints is null");
     const int width = d.gates ? d.Gd : F;
     const bf16* x = d.gates ? w.g2 : w.f2[0];
     lirec_gemm_problem g = mk_problem(d.Ni, d.C, false, false);
@@ -699,9 +708,9 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
   const int nbr = d.ctx ? 2 : 1;
   const int J = d.J, F = d.F, Ni = d.Ni, Gd = d.Gd, CP = d.CP, RP = d.RP, NiP = d.NiP;
   int rc;
-  LIREC_REQUIRE(d_ints != nullptr && (!d.ctx || d_rels != nullptr), "model backward: null logit gradient");
+  LIREC_REQUIRE((!d.ints || d_ints != nullptr) && (!d.ctx || d_rels != nullptr), "model backward: null logit gradient");
   for (int s = 0; s < 3; ++s) {
-    LIREC_REQUIRE(B.inv_cand_off[s] && B.inv_cand_idx[s], "model backward: inverse candidate tables missing");
+    LIREC_REQUIRE(!d.ints || (B.inv_cand_off[s] && B.inv_cand_idx[s]), "model backward: inverse candidate tables missing");
     LIREC_REQUIRE(!d.ctx || (B.inv_ctx_off[s] && (d.Nx == 0 || B.inv_ctx_idx[s])),
                   "model backward: inverse context tables missing");
   }
@@ -726,7 +735,7 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
 
   SplitCtx sc;
   sc.pool = w.pool; sc.pool_floats = w.pool_floats; sc.used = 0; sc.jobs.n = 0;
-  if ((rc = rows::split_f32_t(d_ints, d.C, Ni, d.C, w.dliT, NiP, CP, stream)) != LIREC_OK) return rc;
+  if (d.ints && (rc = rows::split_f32_t(d_ints, d.C, Ni, d.C, w.dliT, NiP, CP, stream)) != LIREC_OK) return rc;
   if (d.ctx && (rc = rows::split_f32_t(d_rels, d.R, Ni, d.R, w.dlrT, NiP, RP, stream)) != LIREC_OK) return rc;
   const TGrad dli{w.dliT, 2 * CP, NiP, 0, CP};
   const TGrad dlr{w.dlrT, 2 * RP, NiP, 0, RP};
@@ -739,15 +748,17 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
   std::vector<lirec_gemm_problem> pr, head_red;
   const bool defer_heads = d.gates && defer_reductions();
   std::vector<lirec_gemm_problem>& hr = defer_heads ? head_red : pr;
-  push_reduction(hr, wgrad_t(d.C, hw, dli, hx, 2 * hw, 2 * hw, 0, hw, Ni, 1.f, P.out_ints.grad_w, hw), d.C, hw, Ni,
-                 true, sc);
-  push_reduction(hr, bgrad_t(d.C, dli, w.onesT, Ni, P.out_ints.grad_b), d.C, 1, Ni, false, sc);
+  if (d.ints) {
+    push_reduction(hr, wgrad_t(d.C, hw, dli, hx, 2 * hw, 2 * hw, 0, hw, Ni, 1.f, P.out_ints.grad_w, hw), d.C, hw, Ni,
+                   true, sc);
+    push_reduction(hr, bgrad_t(d.C, dli, w.onesT, Ni, P.out_ints.grad_b), d.C, 1, Ni, false, sc);
+  }
   if (d.ctx) {
     push_reduction(hr, wgrad_t(d.R, F, dlr, w.f2[1], 2 * F, 2 * F, 0, F, Ni, 1.f, P.out_ctx.grad_w, F), d.R, F, Ni,
                    true, sc);
     push_reduction(hr, bgrad_t(d.R, dlr, w.onesT, Ni, P.out_ctx.grad_b), d.R, 1, Ni, false, sc);
   }
-  {
+  if (d.ints) {
     lirec_gemm_problem g = mk_problem(Ni, hw, true, false);
     if (inplace) add_dgrad_passes_inplace(g, dli, Ni, P.out_ints.w_bf16, d.C, hw, 0);
     else add_dgrad_passes(g, dli, Ni, w.out_intsT, hw, CP, 0, CP);
@@ -816,7 +827,7 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
   std::vector<lirec_gemm_problem> l2_red;
   const bool defer_l2 = defer_reductions();
   std::vector<lirec_gemm_problem>& lr = defer_l2 ? l2_red : pr;
-  for (int br = 0; br < nbr; ++br) {
+  for (int br = d.br0; br < nbr; ++br) {
     const lirec_encoder& enc = br ? P.enc_ctx : P.enc_ints;
     for (int s = 0; s < 4; ++s) {
       if (!d.act[s]) continue;
@@ -840,7 +851,7 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
     rows::ExpandBwdJobs jobs;
     memset(&jobs, 0, sizeof(jobs));
     int n = 0;
-    for (int br = 0; br < nbr; ++br) {
+    for (int br = d.br0; br < nbr; ++br) {
       const int ncl = br ? d.nc : d.nci, ntr = br ? d.nt : d.nti;
       for (int s = 0; s < 4; ++s) {
         if (!d.act[s]) continue;
@@ -872,7 +883,7 @@ int backward(const lirec_model_cfg& cfg, const lirec_model_params& P, const lire
 
   // ---- stage L1: first-layer wgrad/bgrad on the unique rows (inputs carry no grad) ----
   pr = l2_red;
-  for (int br = 0; br < nbr; ++br) {
+  for (int br = d.br0; br < nbr; ++br) {
     const lirec_encoder& enc = br ? P.enc_ctx : P.enc_ints;
     const int ncl = br ? d.nc : d.nci, ntr = br ? d.nt : d.nti;
     for (int s = 0; s < 4; ++s) {
@@ -934,7 +945,6 @@ extern "C" int lirec_model_forward(const lirec_model_cfg* cfg, const lirec_model
   LIREC_ENTER();
   int rc = model::validate(cfg, params, batch, workspace, workspace_bytes);
   if (rc != LIREC_OK) return rc;
-  LIREC_REQUIRE(out_ints != nullptr, "model: out_ints is null");
   return model::forward(*cfg, *params, *batch, workspace, out_ints, out_rels, static_cast<cudaStream_t>(stream));
 }
 

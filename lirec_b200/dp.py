@@ -110,9 +110,9 @@ class SwitchReduceAdam:
         self.ev_heads = torch.cuda.Event()
         self.ev_done = torch.cuda.Event()
         self.ev_heads.record()                       # creates the cudaEvent_t the library re-records
-        # bucket boundary: the first parameter of the gate (models with a gate) or of out_ints
+        # bucket boundary: the first parameter of the gate (models with a gate) or of the first head
         names = [n for n, _ in model.named_parameters()]
-        first = "gates_ints.fc_out.weight" if "gates_ints.fc_out.weight" in names else "out_ints.weight"
+        first = next(n for n in ("gates_ints.fc_out.weight", "out_ints.weight", "out_ctx.weight") if n in names)
         self.split = int(model._offsets[names.index(first)])
         self.n = int(model._flat.numel())
         import os

@@ -406,8 +406,12 @@ class IndexedMixedFeaturesDataset(Dataset):
         rec = {"inter_id": i_id, "labels": label, "n_ctx_slots": self.rels_n_clips if opt.rels_multi_clip else 0}
         if not (opt.tracks and len(inter.triplets)):
             if opt.tracks:
-                raise EnvironmentError
-            raise NotImplementedError("lirec_b200 datasets always carry person tracks (opt.tracks)")
+                raise EnvironmentError                     # reference :585-586
+            # opt.tracks off (reference :587-588): the item is the clip's pooled text|visual vector alone — one
+            # candidate row whose two track slots point at the all-zero track row (the model drops those slots)
+            rec["cand_rows"] = np.asarray([(i_id, 0, 0)], dtype=np.int32)
+            rec["no_tracks"] = True
+            return self._soft_labels(rec, movie, scene, name, label, lab_col)
         trip = inter.triplets[t_idx]
         tr = self.track_row
         T, S, NONE = self._max_n_tripl, self.rels_n_clips, "None"
@@ -530,6 +534,10 @@ class IndexedMixedFeaturesDataset(Dataset):
         if opt.rels_multitask and self.triplets:
             rec["rels_label"] = np.asarray(rels_labs, dtype=np.int64)
 
+        return self._soft_labels(rec, movie, scene, name, label, lab_col)
+
+    def _soft_labels(self, rec, movie, scene, name, label, lab_col):
+        """multilab_weights / soft_labels of an item (reference :590-616)."""
         soft = self.iou2_clips[(movie, scene)][name]
         if opt.multilab_weights:
             w, w_axl = np.ones(self.n_classes), np.ones(len(self.interidx2mgdidx))
@@ -614,7 +622,7 @@ class IndexedMixedFeaturesDataset(Dataset):
             out["features"], out["labels"], out["rels_mask"] = blk, gt, mask.reshape(-1, 1)
             out["rels_label"] = rec["rels_label"]
         else:
-            out["features"] = cand[:1]
+            out["features"] = cand[:1, :clip.shape[1]] if rec.get("no_tracks") else cand[:1]
             if "rels_label" in rec:
                 out["rels_label"] = rec["rels_label"]
         return out

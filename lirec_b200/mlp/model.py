@@ -76,11 +76,15 @@ class _ModelFn(torch.autograd.Function):
             none = inters.new_empty(0)
             ctx.mark_non_differentiable(none)
             return inters, none
+        if inters is None:                       # opt.ints == 0: relationship logits only
+            none = rels.new_empty(0)
+            ctx.mark_non_differentiable(none)
+            return none, rels
         return inters, rels
 
     @staticmethod
     def backward(ctx, d_inters, d_rels):
-        ctx.module._run_backward(ctx.batch_c, ctx.ws, d_inters, d_rels)
+        ctx.module._run_backward(ctx.batch_c, ctx.ws, d_inters if ctx.module._ints else None, d_rels)
         ctx.ws = None
         return None, None, None, None, None
 
@@ -90,10 +94,17 @@ class _HotPath(nn.Module):
     kind = None
 
     def _build(self, n_classes, n_rels, ints, ctx, gates):
-        if not ints:
-            raise NotImplementedError("opt.ints must be 1")
         self.n_classes, self.n_rels = n_classes, n_rels
-        self._ctx, self._gates = bool(ctx), bool(gates and ctx)
+        self._ints, self._ctx, self._gates = bool(ints), bool(ctx), bool(gates and ctx)
+        if not self._ints:
+            # opt.ints == 0 (reference model.py:102, 140, 151, 208): no interaction branch, no interaction head —
+            # the context branch and the relationship head alone.  The reference's GatingUnit reads both features
+            # (model.py:349-352: None.view fails), so gates must be off, and there must be a context branch.
+            if not self._ctx:
+                raise ValueError("opt.ints == 0 needs opt.ctx == 1 (a model without either branch has no output)")
+            if self._gates:
+                raise ValueError("opt.ints == 0 needs opt.gates == 0 (the reference's GatingUnit fails on the "
+                                 "missing interaction feature, mlp/model.py:349-352)")
         J = opt.joint_dim
         dims = {"txt": opt.text_dim, "vis": opt.visual_dim, "tracks1": opt.track_dim, "tracks2": opt.track_dim}
         # Modality slots.  Only Modalities switches on opt.modality / opt.tracks (model.py:27-46); the
@@ -110,7 +121,7 @@ class _HotPath(nn.Module):
         self._slot_mask = (1 if txt else 0) | (2 if vis else 0) | (12 if tracks else 0)
         # same construction order as the reference (mlp/model.py:29-50, 104-143, 222-259) so that the
         # same torch seed gives bit-identical initial weights
-        for br in (["ints"] + (["ctx"] if self._ctx else [])):
+        for br in ((["ints"] if self._ints else []) + (["ctx"] if self._ctx else [])):
             if txt:
                 setattr(self, "txt_%s" % br, nn.Linear(dims["txt"], J))
                 setattr(self, "txt2_%s" % br, nn.Linear(J, J))
@@ -126,7 +137,8 @@ class _HotPath(nn.Module):
         if self._gates:
             out_dim_ints = J * opt.mid_m_ints
             self.gates_ints = GatingUnit(in_dim1=3 * J, in_dim2=3 * J, out_dim=out_dim_ints)
-        self.out_ints = nn.Linear(out_dim_ints, n_classes)
+        if self._ints:
+            self.out_ints = nn.Linear(out_dim_ints, n_classes)
         if self._ctx:
             self.out_ctx = nn.Linear(3 * J, n_rels)
         self.dropout = nn.Dropout(p=opt.dropout)   # holder of p, as in the reference (model.py:52)
@@ -252,7 +264,7 @@ class _HotPath(nn.Module):
     def _build_structs(self):
         P = _ext.ModelParams()
         for br, enc in (("ints", P.enc_ints), ("ctx", P.enc_ctx)):
-            if br == "ctx" and not self._ctx:
+            if (br == "ctx" and not self._ctx) or (br == "ints" and not self._ints):
                 continue
             for s in range(4):
                 if not (self._slot_mask >> s) & 1:
@@ -261,7 +273,8 @@ class _HotPath(nn.Module):
                 enc.l2[s] = self._linear_struct(getattr(self, "%s_%s" % (_SECOND[s], br)))
         if self._gates:
             P.gate = self._linear_struct(self.gates_ints.fc_out)
-        P.out_ints = self._linear_struct(self.out_ints)
+        if self._ints:
+            P.out_ints = self._linear_struct(self.out_ints)
         if self._ctx:
             P.out_ctx = self._linear_struct(self.out_ctx)
         cfg = _ext.ModelCfg()
@@ -272,6 +285,7 @@ class _HotPath(nn.Module):
         cfg.guard_zero = int(self.kind == "maxtracks")
         cfg.dropout_p = float(self.dropout.p)
         cfg.slot_mask = int(self._slot_mask)
+        cfg.no_ints = int(not self._ints)
         self._params_c, self._cfg_c = P, cfg
         self._grad_views = [self._grad_view(i) for i in range(len(self._param_list))]
         # index, not the Parameter itself: assigning a Parameter to a module attribute would register it
@@ -318,16 +332,20 @@ class _HotPath(nn.Module):
         nbytes = L.lirec_model_workspace_bytes(C.byref(self._cfg_c), C.byref(batch_c))
         ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=pb.device)
         Ni = pb.n_cand
-        inters = torch.empty(Ni, self.n_classes, dtype=torch.float32, device=pb.device)
+        inters = torch.empty(Ni, self.n_classes, dtype=torch.float32, device=pb.device) if self._ints else None
         rels = torch.empty(Ni, self.n_rels, dtype=torch.float32, device=pb.device) if self._ctx else None
         _ext.check(L.lirec_model_forward(
             C.byref(self._cfg_c), C.byref(self._params_c), C.byref(batch_c), ws.data_ptr(), ws.numel(),
-            inters.data_ptr(), rels.data_ptr() if rels is not None else None, _ext.stream_ptr()))
+            inters.data_ptr() if inters is not None else None, rels.data_ptr() if rels is not None else None,
+            _ext.stream_ptr()))
         return batch_c, ws, inters, rels
 
     def _run_backward(self, batch_c, ws, d_inters, d_rels):
         """lirec_model_backward: every parameter gradient of the step into the flat gradient buffer."""
-        d_inters = d_inters.contiguous()
+        d_inters_ptr = None
+        if self._ints:
+            d_inters = d_inters.contiguous()
+            d_inters_ptr = d_inters.data_ptr()
         d_rels_ptr = None
         if self._ctx:
             d_rels = d_rels.contiguous()
@@ -336,11 +354,11 @@ class _HotPath(nn.Module):
         if ev is not None:
             _ext.check(_ext.lib().lirec_model_backward_ex(
                 C.byref(self._cfg_c), C.byref(self._params_c), C.byref(batch_c), ws.data_ptr(), ws.numel(),
-                d_inters.data_ptr(), d_rels_ptr, _ext.stream_ptr(), C.c_void_p(ev.cuda_event)))
+                d_inters_ptr, d_rels_ptr, _ext.stream_ptr(), C.c_void_p(ev.cuda_event)))
         else:
             _ext.check(_ext.lib().lirec_model_backward(
                 C.byref(self._cfg_c), C.byref(self._params_c), C.byref(batch_c), ws.data_ptr(), ws.numel(),
-                d_inters.data_ptr(), d_rels_ptr, _ext.stream_ptr()))
+                d_inters_ptr, d_rels_ptr, _ext.stream_ptr()))
         self._publish_grads()
 
     # ---- batches -------------------------------------------------------------------------------
@@ -389,6 +407,8 @@ class _HotPath(nn.Module):
             anchor = self._param_list[self._anchor_idx]
         if torch.is_grad_enabled() and anchor.requires_grad:
             inters, rels = _ModelFn.apply(self, pb, training, seed, anchor)
+            if not self._ints:
+                inters = None
         else:                                    # inference (mlp/test.py runs under no_grad): no autograd node
             _, _, inters, rels = self._run_forward(pb, training, seed)
         return ModelOutput(pb, inters, rels if self._ctx else None, dense_tracks=(self.kind == "maxtracks"))
@@ -565,6 +585,9 @@ class _TrackLoss(_FusedLoss):
         self._draws = getattr(self, "_draws", 0) + 1
         pb = _batch_of(x, args)
         li, lr = x.ragged_inters, x.ragged_rels if n_rels else None
+        if li is None:
+            raise ValueError("the track-assignment losses need interaction logits: opt.ints == 0 only works with "
+                             "MultiTaskMaxMargin, as in the reference (mlp/model.py:455, 507 dereference x['inters'])")
         terms, assign, d_i, d_r = ops.loss_track(
             li, lr, pb["cand_off"], pb["labels"], pb["rels_label"] if n_rels else None, pb["gt_tracks"],
             pb.multilab, self.m, lymbda, n_rels, tr_correct=opt.tr_correct,
@@ -653,7 +676,7 @@ def train_step(model, loss, x, seed=None):
         out = ModelOutput(pb, inters, rels if model._ctx else None, dense_tracks=(model.kind == "maxtracks"))
         terms, d_i, d_r = loss.terms_and_grads(out, x if isinstance(x, dict) else {})
         value = terms.sum()
-        if d_i is None:
+        if d_i is None and model._ints:
             d_i = torch.zeros_like(inters)
         if d_r is None and model._ctx:
             d_r = torch.zeros_like(rels)

@@ -59,7 +59,10 @@ def testing(test_dataset, model, loss, total_iter=1, mode="val", train_start_tim
             if opt.tr_maximize:
                 _update_track_meters(tracks, out, pb, n_rels if opt.ctx == 1 else 0)
             else:
-                top.update(out.ragged_inters, pb["labels"])
+                if opt.ints == 1:                                # mlp/test.py:74-79
+                    top.update(out.ragged_inters, pb["labels"])
+                else:                                            # relationship-only model: count the clips
+                    top.c[0] += pb.B
                 if opt.rels_multitask and opt.ctx == 1:
                     lab = pb["rels_label"].long()
                     sel = (lab != n_rels).nonzero().reshape(-1)          # mlp/test.py:80-87
@@ -84,7 +87,8 @@ def testing(test_dataset, model, loss, total_iter=1, mode="val", train_start_tim
     def ratio(a, b):
         return float(a) / float(b) if b else 0.0
     out_val = out_val_ints = out_val_rels = out_val_tr = out_val_joint = 0.0
-    print("%s loss: %f" % (mode.upper(), losses.avg))
+    if opt.ints == 1:                                           # the reference prints the loss with pr@1 (:102-103)
+        print("%s loss: %f" % (mode.upper(), losses.avg))
     if opt.tr_maximize:
         r = TrackMeters.ratios(tc)                              # the reference's accessors (evaluation.py:329-360)
         out_val_joint, out_val_tr, out_val_ints = r["top1"], r["trks_top1"], r["cls_top1"]
@@ -97,10 +101,11 @@ def testing(test_dataset, model, loss, total_iter=1, mode="val", train_start_tim
             print("%s pr@rels: %f" % (mode.upper(), out_val_rels))
             out_val += out_val_rels
     else:
-        out_val_ints = out_val_joint = ratio(top_c[1], top_c[0])
-        print("%s pr@1: %f" % (mode.upper(), out_val_ints))
-        print("%s pr@5: %f" % (mode.upper(), ratio(top_c[3], top_c[0])))
-        out_val = out_val_ints
+        if opt.ints == 1:                                       # mlp/test.py:102-109
+            out_val_ints = out_val_joint = ratio(top_c[1], top_c[0])
+            print("%s pr@1: %f" % (mode.upper(), out_val_ints))
+            print("%s pr@5: %f" % (mode.upper(), ratio(top_c[3], top_c[0])))
+            out_val = out_val_ints
         if opt.rels_multitask and opt.ctx == 1:
             if racc is not None:                                # pair-level ranking, as the reference (evaluation.py:399-417)
                 rc = racc.compute()

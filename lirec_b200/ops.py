@@ -110,12 +110,12 @@ def seg_softmax_pool_bwd(x, seg_off, beta, scores, out, lse, d_out, need_d_score
     mode = _score_mode(x, scores)
     nseg, dim = seg_off.numel() - 1, x.shape[1]
     d_out = d_out.contiguous()
-    d_x = torch.zeros_like(x)
-    d_s = torch.zeros_like(scores) if (mode != 0 and need_d_scores) else None
+    d_x = torch.empty_like(x)                      # rows outside the segments are zero-filled by the launch itself
+    d_s = torch.empty_like(scores) if (mode != 0 and need_d_scores) else None
     _ext.check(_ext.lib().lirec_seg_softmax_pool_bwd(
         _ext.ptr(x), _ext.ptr(scores), mode, _ext.ptr(seg_off), nseg, dim, float(beta), _ext.ptr(out), out.stride(0),
         _ext.ptr(lse), lse.stride(0) if lse.dim() == 2 else 0, _ext.ptr(d_out), d_out.stride(0), _ext.ptr(d_x),
-        _ext.ptr(d_s), _ext.stream_ptr()))
+        _ext.ptr(d_s), x.shape[0], _ext.stream_ptr()))
     return d_x, d_s
 
 

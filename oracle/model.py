@@ -137,15 +137,18 @@ def maxtracks_forward(sd, features, rels_mask, cfg, masks=None):
     B, T = features.shape[0], features.shape[1]
     x = features.reshape(B * T, -1, features.shape[-1])       # model.py:272-274
     out_c = None
-    f_i = _tape(cfg, "z2_ints", torch.cat(encode(sd, "ints", x[:, 0, :], cfg, masks), dim=-1))
-    f_i = _drop(torch.tanh(f_i), masks, ("cat", "ints"), cfg.dropout)
+    out_i = f_i = None
+    if cfg.ints:                                              # model.py:278
+        f_i = _tape(cfg, "z2_ints", torch.cat(encode(sd, "ints", x[:, 0, :], cfg, masks), dim=-1))
+        f_i = _drop(torch.tanh(f_i), masks, ("cat", "ints"), cfg.dropout)
     if cfg.ctx:
         f_c = _ctx_feature(sd, x[:, 1:, :], rels_mask.reshape(B * T, -1), cfg, masks, guard_zero=True)
     if cfg.gates:
         f_i = gating_unit(sd, f_i, f_c, cfg, masks)
     if cfg.ctx:
         out_c = _lin(sd, "out_ctx", f_c).reshape(B, T, -1)
-    out_i = _lin(sd, "out_ints", f_i).reshape(B, T, -1)
+    if cfg.ints:                                              # model.py:335
+        out_i = _lin(sd, "out_ints", f_i).reshape(B, T, -1)
     return {"inters": out_i, "rels": out_c}
 
 
@@ -162,7 +165,7 @@ def init_state_dict(cfg, n_classes, n_rels, kind, seed=0, dtype=torch.float32):
 
     J = cfg.joint_dim
     ins = {"txt": cfg.text_dim, "vis": cfg.visual_dim, "tracks1": cfg.track_dim, "tracks2": cfg.track_dim}
-    branches = ["ints"] + (["ctx"] if (kind != "modalities" and cfg.ctx) else [])
+    branches = (["ints"] if (kind == "modalities" or cfg.ints) else []) + (["ctx"] if (kind != "modalities" and cfg.ctx) else [])
     for br in branches:
         for slot in SLOTS:
             lin("%s_%s" % (slot, br), J, ins[slot])
@@ -172,7 +175,8 @@ def init_state_dict(cfg, n_classes, n_rels, kind, seed=0, dtype=torch.float32):
     if kind != "modalities" and cfg.gates:
         width = J * cfg.mid_m_ints
         lin("gates_ints.fc_out", width, 6 * J)
-    lin("out_ints", n_classes, width)
+    if kind == "modalities" or cfg.ints:
+        lin("out_ints", n_classes, width)
     if kind != "modalities" and cfg.ctx:
         lin("out_ctx", n_rels, 3 * J)
     return sd

@@ -157,7 +157,7 @@ def replay_dropout(model, masks, p, modality="m", tracks=True):
     return queue
 
 
-def random_masks(kind, rows, S, J, gate_dim, p, gen, ctx=True, gates=True, modality="m", tracks=True):
+def random_masks(kind, rows, S, J, gate_dim, p, gen, ctx=True, gates=True, modality="m", tracks=True, ints=True):
     """Random 0/1 dropout masks in the layout of oracle/model.py's `masks` dict.  rows = encoder rows of
     the ints branch (B, or B*T for the track models); context masks are [rows, S, J]."""
     slots = [s for s in ("txt", "vis", "tracks1", "tracks2")
@@ -167,8 +167,10 @@ def random_masks(kind, rows, S, J, gate_dim, p, gen, ctx=True, gates=True, modal
 
     def draw(*shape):
         return torch.rand(*shape, generator=gen) >= p
-    masks = {("l1", "ints", s): draw(rows, J) for s in slots}
-    masks[("cat", "ints")] = draw(rows, width)
+    masks = {}
+    if ints or kind == "modalities":
+        masks = {("l1", "ints", s): draw(rows, J) for s in slots}
+        masks[("cat", "ints")] = draw(rows, width)
     if ctx and kind != "modalities":
         for s in slots:
             masks[("l1", "ctx", s)] = draw(rows, S, J)

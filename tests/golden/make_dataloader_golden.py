@@ -1,7 +1,7 @@
 """Generate tests/golden/dataloader_*.npz from the UNMODIFIED reference dataloader (run in the build
 container only; /root/reference does not exist on the GPU box).
 
-    python tests/golden/make_dataloader_golden.py
+    python tests/golden/make_dataloader_golden.py [preset alias ...]
 
 A small synthetic annotation world (lirec_b200/mixed_utils/synthetic_world.py, reduced feature dims so
 the fixtures stay small) is built out of the reference's own AnnotatedInter / Relationship classes and
@@ -20,6 +20,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+ONLY = sys.argv[1:]            # optional: preset aliases to (re)generate, e.g. `notracks`; default all
 sys.argv = sys.argv[:1]
 
 from oracle import reference_shim as rs  # noqa: E402
@@ -35,6 +36,10 @@ CASES = [
     ("int_rels", "train", 18, 0, 5, {}), ("int_rels", "train", 3, 1, 6, {}),
     ("int_rels", "test", 18, 0, 5, {}), ("int_rels", "test", 3, 1, 6, {}),
     ("modalities", "train", 18, 0, 5, dict(soft_gt=True)), ("modalities", "test", 18, 1, 6, dict(soft_gt=True)),
+    # opt.tracks off (classification_dataloader.py:75-77, 587-588): one item per interaction in train mode, the
+    # clip's text|visual vector alone; stored as preset "notracks"
+    ("modalities", "train", 18, 0, 5, dict(tracks=False, soft_gt=True), "notracks"),
+    ("modalities", "test", 18, 1, 6, dict(tracks=False, soft_gt=True), "notracks"),
 ]
 
 
@@ -45,7 +50,11 @@ def case_name(preset, mode, n_clips, wseed):
 def main():
     opt, _ = rs.load_dataloader()
     uf = rs._state["util_functions"]
-    for preset, mode, n_clips, wseed, seed, extra in CASES:
+    for case in CASES:
+        preset, mode, n_clips, wseed, seed, extra = case[:6]
+        alias = case[6] if len(case) > 6 else preset
+        if ONLY and alias not in ONLY:
+            continue
         w = sw.build_world(wseed, inter_cls=uf.AnnotatedInter, rel_cls=uf.Relationship, **WORLD[wseed])
         opt.soft_gt = False
         ds = rs.reference_dataset(sw.subset(w, mode), w, mode, preset, rels_n_clips=n_clips, **extra)
@@ -59,7 +68,7 @@ def main():
                 assert np.array_equal(arr.astype(np.float16).astype(np.float64), arr)
                 arr = arr.astype(np.float16)
             out["item_" + k] = arr
-        path = os.path.join(HERE, case_name(preset, mode, n_clips, wseed))
+        path = os.path.join(HERE, case_name(alias, mode, n_clips, wseed))
         np.savez_compressed(path, **out)
         print("%-48s %3d items  %6.1f KB" % (os.path.basename(path), len(items), os.path.getsize(path) / 1e3))
     opt.soft_gt = False

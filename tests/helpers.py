@@ -39,7 +39,8 @@ def oracle_forward_loss(pb, sd, preset, opt, masks, tape=None, relu_gate=None):
     from oracle import losses as ol, model as om
     kind = synthetic.PRESETS[preset]["kind"]
     dense = pb.to_dense(np.float64)
-    cfg = om.default_cfg(ctx=int(opt.ctx), gates=int(opt.gates), dropout=opt.dropout)
+    cfg = om.default_cfg(ctx=int(opt.ctx), gates=int(opt.gates), dropout=opt.dropout,
+                         ints=1 if kind == "modalities" else int(opt.ints))
     if kind == "modalities":
         cfg.modality, cfg.tracks = opt.modality, bool(opt.tracks)
     if tape is not None:
@@ -57,7 +58,7 @@ def oracle_forward_loss(pb, sd, preset, opt, masks, tape=None, relu_gate=None):
         o = om.midfusion_forward(sd, f.reshape(B, -1, f.shape[-1]), dense["rels_mask"].reshape(B, -1, 1), cfg, masks)
         l = ol.multitask_max_margin(o["inters"], o["rels"], dense["labels"].reshape(B, 1, 1),
                                     dense["rels_label"].reshape(B), dense["multilab_weights"], opt.margin,
-                                    opt.lymbda, N_RELS)
+                                    opt.lymbda, N_RELS, ints=int(opt.ints))
         ragged = {"inters": o["inters"], "rels": o["rels"]}
     else:
         o = om.maxtracks_forward(sd, f, dense.get("rels_mask"), cfg, masks)

@@ -84,6 +84,37 @@ def test_forward_loss_backward_parity(preset, train, opt_preset):
             assert rel_err(p.grad, sd[k].grad) < TOL, (k, rel_err(p.grad, sd[k].grad))
 
 
+@pytest.mark.parametrize("train", [False, True])
+def test_relationship_only_model_parity(train, opt_preset):
+    """opt.ints == 0 (reference mlp/model.py:102, 140, 151, 208; loss :391): no interaction branch, no interaction
+    head — the context branch and the relationship head alone, trained by the relationship term of
+    MultiTaskMaxMargin.  The reference's GatingUnit needs both features, so gates are off.  The oracle of this
+    configuration is pinned against the unmodified reference in tests/test_oracle_vs_reference.py."""
+    import lirec_b200.mlp.model as M
+    opt = opt_preset("int_rels", ints=0, gates=0)
+    for seed in (3, 4):
+        model, loss_fn, out, lv, sd, ragged, l, extra, tape = _run("int_rels", opt, 6, seed, train)
+        names = [k for k, _ in model.named_parameters()]
+        assert names and all("_ctx" in k for k in names), names          # the reference's parameter set
+        assert out.ragged_inters is None and out["inters"] is None and ragged["inters"] is None
+        assert rel_err(out.ragged_rels, ragged["rels"]) < TOL
+        assert abs(lv.item() - l.item()) / abs(l.item()) < TOL
+        for k, p in model.named_parameters():
+            assert p.grad is not None, k
+            assert rel_err(p.grad, sd[k].grad) < TOL, (k, rel_err(p.grad, sd[k].grad))
+        # the autograd-free step (mlp/train.py's default) lands the same gradients, bit for bit
+        grads = {k: p.grad.clone() for k, p in model.named_parameters()}
+        pbd = out.batch
+        v2 = M.train_step(model, loss_fn, pbd, seed=1000 + seed)
+        torch.cuda.synchronize()
+        assert float(v2) == float(lv)
+        for k, p in model.named_parameters():
+            assert torch.equal(p.grad, grads[k]), k
+    with pytest.raises(ValueError):
+        opt_preset("int_rels", ints=0, gates=1)
+        M.MidFusionMultiClip(N_CLASSES, N_RELS)
+
+
 @pytest.mark.parametrize("preset", ["int_rel_ch", "int_rels", "int_ch", "modalities"])
 def test_reference_batch_size_parity_train_mode(preset, opt_preset):
     """B = 64 — the reference's batch size (utils/arg_pars.py:150) and BASELINE.md's parity point — in TRAIN

@@ -18,7 +18,10 @@ def _rel(a, b):
 @pytest.mark.parametrize("train", [False, True], ids=["eval", "train"])
 @pytest.mark.parametrize("preset,over", [("int_rel_ch", {}), ("int_rel_ch", dict(tr_correct=True)),
                                          ("int_rel_ch", dict(tr_max_neg=True)), ("int_ch", {}),
-                                         ("int_rels", {}), ("modalities", {})])
+                                         ("int_rels", {}), ("modalities", {}),
+                                         # opt.ints == 0: the context branch and the relationship head alone
+                                         # (mlp/model.py:102, 140, 151, 208; loss :391); the gate needs both features
+                                         ("int_rels", dict(ints=0, gates=0))])
 def test_full_size_forward_loss_backward(preset, over, train):
     """eval: dropout off on both sides.  train: the UNMODIFIED reference forward runs in train mode with
     its nn.Dropout modules (mlp/model.py:52, 347) replaced by a replayer that applies, in the reference's
@@ -37,7 +40,7 @@ def test_full_size_forward_loss_backward(preset, over, train):
         ctx0 = preset in ("int_rels", "int_rel_ch")
         rows = B * dense["features"].shape[1] if kind0 == "maxtracks" else B
         masks = rs.random_masks(kind0, rows, 18, 512, 3072, 0.3, torch.Generator().manual_seed(77), ctx=ctx0,
-                                gates=ctx0)
+                                gates=ctx0 and bool(over.get("gates", 1)), ints=bool(over.get("ints", 1)))
         queue = rs.replay_dropout(model, masks, 0.3)
     batch = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in dense.items()}
     kind = synthetic.PRESETS[preset]["kind"]
@@ -57,7 +60,7 @@ def test_full_size_forward_loss_backward(preset, over, train):
 
     sd = {k: v.detach().clone().double().requires_grad_(True) for k, v in model.state_dict().items()}
     ctx = preset in ("int_rels", "int_rel_ch")
-    cfg = om.default_cfg(ctx=int(ctx), gates=int(ctx), dropout=0.3)
+    cfg = om.default_cfg(ctx=int(ctx), gates=int(ctx and over.get("gates", 1)), ints=int(over.get("ints", 1)), dropout=0.3)
     f = dense["features"]
     if kind == "modalities":
         o = om.modalities_forward(sd, f.reshape(B, 1, -1), cfg, masks)
@@ -65,7 +68,9 @@ def test_full_size_forward_loss_backward(preset, over, train):
     elif kind == "midfusion":
         o = om.midfusion_forward(sd, f.reshape(B, -1, f.shape[-1]), dense["rels_mask"].reshape(B, -1, 1), cfg, masks)
         l = ol.multitask_max_margin(o["inters"], o["rels"], dense["labels"].reshape(B, 1, 1),
-                                    dense["rels_label"].reshape(B), dense["multilab_weights"], 0.101, 1.0, 15)
+                                    dense["rels_label"].reshape(B), dense["multilab_weights"], 0.101, 1.0, 15,
+                                    ints=int(over.get("ints", 1)))
+        assert (o["inters"] is None) == (out["inters"] is None)
     elif ctx:
         o = om.maxtracks_forward(sd, f, dense["rels_mask"], cfg, masks)
         l = ol.margin_track_rels(o["inters"], o["rels"], dense["labels"], dense["rels_label"], dense["mem_mask"],

@@ -146,13 +146,22 @@ def _np_softpool_bwd(x, off, beta, scores, out, ws, dy):
     return dx, ds
 
 
+@pytest.mark.parametrize("lanes", ["4", "1"])
+@pytest.mark.parametrize("many", [False, True])
 @pytest.mark.parametrize("kind", ["self", "elem", "row"])
-def test_softmax_pool_forward_backward_vs_numpy(kind):
+def test_softmax_pool_forward_backward_vs_numpy(kind, many, lanes, monkeypatch):
+    """Both CTA shapes of the kernels (four row lanes of 128 columns merged in shared memory — the default — and one
+    lane of 512 columns, LIREC_SP_LANES=1), a handful of segments and thousands of them, ragged lengths around the
+    four-row batches and the row chunks of the per-row-score backward."""
     from lirec_b200 import ops
+    monkeypatch.setenv("LIREC_SP_LANES", lanes)
     rng = np.random.default_rng(3)
     lens = [5, 0, 1, 37, 12, 0, 64, 3]                       # ragged, with empty segments
-    off = np.concatenate(([0], np.cumsum(lens))).astype(np.int32)
     dim, beta = 768, 1.7
+    if many:
+        lens = lens + [int(v) for v in rng.integers(0, 23, size=1900)]
+        dim = 1024
+    off = np.concatenate(([0], np.cumsum(lens))).astype(np.int32)
     x = rng.standard_normal((off[-1], dim)).astype(np.float32)
     scores = None if kind == "self" else (rng.standard_normal((off[-1], dim)) if kind == "elem"
                                           else rng.standard_normal(off[-1])).astype(np.float32)
@@ -169,6 +178,27 @@ def test_softmax_pool_forward_backward_vs_numpy(kind):
     assert float(np.abs(xd.grad.cpu().numpy() - rdx).max()) < 3e-5 * np.abs(rdx).max()
     if scores is not None:
         assert float(np.abs(sd.grad.cpu().numpy() - rds).max()) < 3e-5 * np.abs(rds).max()
+
+
+@pytest.mark.parametrize("kind", ["self", "elem", "row"])
+def test_softmax_pool_backward_zero_fills_rows_no_segment_owns(kind):
+    """The offsets need not tile x: rows before the first and after the last offset get zero gradients from the
+    backward launch itself (the wrapper hands it uninitialised buffers, no memset)."""
+    from lirec_b200 import ops
+    rng = np.random.default_rng(8)
+    total, dim, beta = 40, 256, 0.9
+    off = torch.tensor([3, 3, 11, 30], dtype=torch.int32, device="cuda")
+    x = torch.from_numpy(rng.standard_normal((total, dim)).astype(np.float32)).cuda()
+    scores = None if kind == "self" else torch.from_numpy(
+        (rng.standard_normal((total, dim)) if kind == "elem" else rng.standard_normal(total)).astype(np.float32)).cuda()
+    out, lse = ops.seg_softmax_pool(x, off, beta, scores)
+    junk = torch.full((64, total, dim), float("nan"), device="cuda")          # dirty the allocator's free blocks
+    del junk
+    d_x, d_s = ops.seg_softmax_pool_bwd(x, off, beta, scores, out, lse, torch.ones_like(out))
+    assert bool((d_x[:3] == 0).all()) and bool((d_x[30:] == 0).all()) and bool(torch.isfinite(d_x).all())
+    assert bool((d_x[3:30].abs().sum(1) > 0).all())
+    if d_s is not None:
+        assert bool((d_s[:3] == 0).all()) and bool((d_s[30:] == 0).all()) and bool(torch.isfinite(d_s).all())
 
 
 def test_softmax_pool_limits_are_the_reference_poolings():

@@ -81,6 +81,15 @@ def sweep_softmax_pool():
         dy = torch.randn_like(out)
         ms = timeit(lambda: ops.seg_softmax_pool_bwd(x, offd, 1.5, None, out, lse, dy))
         report("seg_softmax bwd", "dim=%d mean_len=%d nseg=%d" % (dim, mean_len, nseg), 2 * x.numel() * 4 + 3 * nseg * dim * 4, ms)
+        # attention pooling: one score per row, shared by the columns
+        sc = torch.randn(x.shape[0], device="cuda")
+        ms = timeit(lambda: ops.seg_softmax_pool(x, offd, beta=1.5, scores=sc))
+        report("seg_softmax fwd (row scores)", "dim=%d mean_len=%d nseg=%d" % (dim, mean_len, nseg),
+               x.numel() * 4 + sc.numel() * 4 + nseg * dim * 4, ms)
+        out, lse = ops.seg_softmax_pool(x, offd, beta=1.5, scores=sc)
+        ms = timeit(lambda: ops.seg_softmax_pool_bwd(x, offd, 1.5, sc, out, lse, dy))
+        report("seg_softmax bwd (row scores)", "dim=%d mean_len=%d nseg=%d" % (dim, mean_len, nseg),
+               2 * x.numel() * 4 + 2 * sc.numel() * 4 + 2 * nseg * dim * 4, ms)
 
 
 def sweep_roi():

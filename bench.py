@@ -646,6 +646,9 @@ def run_ours(args):
     e2e_err = None
     e2e_value = e2e_host_rate = None
     h2d_loader = 0
+    import gc
+    gc.collect()
+    gc.freeze()             # as lirec_b200/mlp/train.py does: the cached records never reach a full collection again
     try:
         it = loader(warmup + e2e_steps)
         for _ in range(warmup):

@@ -80,6 +80,12 @@ def training(train_dataset, **kwargs):
     model_saver_val = ModelSaver(path=opt.store_root)
     dev = torch.device("cuda", torch.cuda.current_device())
     epoch = 0
+    # The dataset's records are a few million long-lived Python objects: parked in the permanent generation, a
+    # full collection no longer walks them in the middle of an epoch (tens of milliseconds = a dozen 64-clip steps
+    # during which the launch thread holds the GIL and the GPU drains its queue).
+    import gc
+    gc.collect()
+    gc.freeze()
     for epoch in range(opt.epochs):
         model.to(opt.device)
         model.train()

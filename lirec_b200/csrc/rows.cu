@@ -670,12 +670,37 @@ roi_mean_kernel(const float* __restrict__ maps, int C, int HW, int W, const int3
 
 // ---------------------------------------------------------------------------
 // Row gather: out[i, :] = bank[idx[i], :] (bf16 rows, 16-byte column groups).  Builds the per-batch
-// feature banks from dataset banks that stay resident in HBM; one warp-wide 128-bit load and store
-// per 512 bytes of row, grid-strided over (row, column-group) pairs so short rows still fill the SMs.
+// feature banks from dataset banks that stay resident in HBM.  One warp per row (warp-strided over the rows):
+// the row index is read once, the lanes walk the row's 16-byte groups four at a time (four 128-bit loads in
+// flight per lane, then four stores), no division anywhere.  The loader launches it on its copy stream while the
+// step's persistent GEMM CTAs hold the SMs: 256 threads x <= 40 registers fit beside one of them, so the gather
+// overlaps the (tensor-bound) GEMMs instead of waiting for a gap between launches — hence the depth per lane.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const uint4* __restrict__ bank, int64_t bank_ld16, int n_bank, const int32_t* __restrict__ idx,
                    int n, int cols16, uint4* __restrict__ out, int64_t out_ld16) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+    const int src = idx[r];
+    const bool ok = src >= 0 && src < n_bank;                    // out of range -> zero row
+    const uint4* in = bank + static_cast<int64_t>(ok ? src : 0) * bank_ld16;
+    uint4* o = out + static_cast<int64_t>(r) * out_ld16;
+    int c = lane;
+    for (; c + 96 < cols16; c += 128) {
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = ok ? in[c + 32 * k] : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[c + 32 * k] = v[k];
+    }
+    for (; c < cols16; c += 32) o[c] = ok ? in[c] : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gather_rows_flat_kernel(const uint4* __restrict__ bank, int64_t bank_ld16, int n_bank, const int32_t* __restrict__ idx,
+                        int n, int cols16, uint4* __restrict__ out, int64_t out_ld16) {
   const int64_t total = static_cast<int64_t>(n) * cols16;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -721,10 +746,17 @@ int gather_rows(const void* bank, int64_t bank_ld, int n_bank, const int32_t* id
   LIREC_REQUIRE(bank && idx && out && n_bank > 0, "gather_rows: null argument");
   if (n <= 0) return LIREC_OK;
   const int cols16 = dim / 8;
-  const int64_t total = static_cast<int64_t>(n) * cols16;
-  const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16));
-  gather_rows_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(bank), bank_ld / 8, n_bank, idx, n, cols16,
-                                               static_cast<uint4*>(out), out_ld / 8);
+  const char* flat = getenv("LIREC_GATHER_FLAT");                // A/B knob: the element-strided form
+  if (flat && flat[0] == '1') {
+    const int64_t total = static_cast<int64_t>(n) * cols16;
+    const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 16));
+    gather_rows_flat_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(bank), bank_ld / 8, n_bank, idx, n,
+                                                      cols16, static_cast<uint4*>(out), out_ld / 8);
+  } else {
+    const int grid = std::min((n + 7) / 8, 148 * 16);            // eight rows (warps) per CTA
+    gather_rows_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(bank), bank_ld / 8, n_bank, idx, n, cols16,
+                                                 static_cast<uint4*>(out), out_ld / 8);
+  }
   LIREC_CUDA_OK(cudaGetLastError());
   note_launch();
   return LIREC_OK;

@@ -330,7 +330,11 @@ class _HotPath(nn.Module):
         batch_c = self._batch_struct(pb, training, seed)
         L = _ext.lib()
         nbytes = L.lirec_model_workspace_bytes(C.byref(self._cfg_c), C.byref(batch_c))
-        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=pb.device)
+        # high-water capacity: the workspace follows the batch's row counts (+- 1 % from batch to batch), and a
+        # request a little larger than every cached block costs a cudaMalloc behind the GPU's queue
+        if int(nbytes) > getattr(self, "_ws_cap", 0):
+            self._ws_cap = -(-int(int(nbytes) * 1.05 + 256) // 4096) * 4096
+        ws = torch.empty(self._ws_cap, dtype=torch.uint8, device=pb.device)
         Ni = pb.n_cand
         inters = torch.empty(Ni, self.n_classes, dtype=torch.float32, device=pb.device) if self._ints else None
         rels = torch.empty(Ni, self.n_rels, dtype=torch.float32, device=pb.device) if self._ctx else None

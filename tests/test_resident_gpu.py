@@ -84,3 +84,45 @@ def test_world_dataset_trains_and_evaluates(resident, tmp_path, opt_preset):
     res = T.testing(val_ds, model, loss, mode="val")
     assert set(res) == {"total", "ints", "rels", "tracks", "joint"}
     assert not torch.equal(w0, model.state_dict()["gates_ints.fc_out.weight"])
+
+
+@pytest.mark.parametrize("case", ["relationship_only", "no_tracks"])
+def test_world_dataset_rare_configurations(case, tmp_path, opt_preset):
+    """The two configurations no released preset uses, through the whole loop (dataset -> packed loader -> train step
+    -> evaluation): opt.ints == 0 (context branch + relationship head alone, reference mlp/model.py:102-210,
+    mlp/test.py:74-109) and a dataset without person tracks (opt.tracks off, classification_dataloader.py:587-588)."""
+    common = dict(synthetic=2, resident_banks=1, world_movies=3, world_scenes=8, epochs=1, batch_size=16, num_workers=0,
+                  test=True, test_fr=1, save_model=False, save_model_often=False, store_root=str(tmp_path),
+                  resume=False, resume_train=False, fused_adam=1, dp=0, lr=1e-3, tr_sum_max=False, inter_class="all",
+                  merged=True, multilab_weights=True, rels=False, soft_gt=False, seed=0)
+    if case == "relationship_only":
+        opt = opt_preset("int_rels", ints=0, gates=0, **common)
+    else:
+        opt = opt_preset("modalities", tracks=False, **common)
+    from lirec_b200.mixed_utils import classification_dataloader as cd
+    import lirec_b200.mlp.model as M
+    import lirec_b200.mlp.test as T
+    import lirec_b200.mlp.train as TR
+    train_ds, val_ds = cd.MixedFeaturesDataset("train").cache(), cd.MixedFeaturesDataset("val").cache()
+    if opt.rels_multitask:
+        train_ds.init_relships(), val_ds.init_relships()
+    torch.manual_seed(0)
+    model, loss, optimizer = M.create_model(train_ds.n_classes, n_rels=max(len(train_ds.rels_list) - 1, 0))
+    names = [k for k, _ in model.named_parameters()]
+    if case == "relationship_only":
+        assert all("_ctx" in k for k in names)
+        probe = "out_ctx.weight"
+    else:
+        assert not any("tracks" in k for k in names)
+        rec = train_ds[0]
+        assert rec["cand_rows"].shape == (1, 3) and not rec["cand_rows"][0, 1:].any()
+        probe = "out_ints.weight"
+    w0 = model.state_dict()[probe].clone()
+    TR.training(train_ds, model=model, loss=loss, optimizer=optimizer, name="w", val_dataset=val_ds)
+    res = T.testing(val_ds, model, loss, mode="val")
+    assert not torch.equal(w0, model.state_dict()[probe])
+    assert all(np.isfinite(v) for v in res.values())
+    if case == "relationship_only":
+        assert set(res) == {"total", "ints", "rels"} and res["ints"] == 0 and res["total"] == res["rels"]
+    else:
+        assert set(res) == {"total", "ints"}

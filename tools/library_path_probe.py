@@ -37,7 +37,7 @@ def eager_gpu(preset, pb, steps, warmup):
         e1.record()
         torch.cuda.synchronize()
     finally:
-        torch.set_default_device("cpu")
+        torch.set_default_device(None)                          # "cpu" would leave a function mode on every torch call
     return e0.elapsed_time(e1) / steps, dense["features"].numel() * 4
 
 
@@ -73,9 +73,9 @@ def main():
           "on %s, preset %s, train step = fwd + loss + bwd + Adam" % (torch.cuda.get_device_name(0), a.preset))
     for B in [int(x) for x in a.batches.split(",")]:
         pb = synthetic.make_batch(B, seed=0, preset=a.preset)
-        ms_e, nbytes = eager_gpu(a.preset, pb, a.steps, 2)
-        torch.cuda.empty_cache()
         ms_o = ours(a.preset, pb, 20 * a.steps, 5)
+        torch.cuda.empty_cache()
+        ms_e, nbytes = eager_gpu(a.preset, pb, a.steps, 2)
         print("B=%4d  dense batch %7.1f MB  eager %9.3f ms/step %9.0f clips/s | lirec_b200 %7.3f ms/step %9.0f clips/s "
               "| x%.1f" % (B, nbytes / 1e6, ms_e, B / ms_e * 1e3, ms_o, B / ms_o * 1e3, ms_e / ms_o))
         sys.stdout.flush()

@@ -107,7 +107,7 @@ def test_relationship_only_model_parity(train, opt_preset):
         pbd = out.batch
         v2 = M.train_step(model, loss_fn, pbd, seed=1000 + seed)
         torch.cuda.synchronize()
-        assert float(v2) == float(lv)
+        assert float(v2.detach()) == float(lv.detach())
         for k, p in model.named_parameters():
             assert torch.equal(p.grad, grads[k]), k
     with pytest.raises(ValueError):

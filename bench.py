@@ -129,6 +129,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.sm, self.power, self.reasons, self.mx = index, [], [], set(), None
+        self.tag, self.by_tag = "value", {}          # samples per named region: tag -> ([sm], [power], {reasons})
         self._stop = threading.Event()
         self.thread = self.proc = None
         self.active = False
@@ -152,18 +153,16 @@ class ClockSampler:
         while not self._stop.is_set():
             if self.active:
                 try:
-                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                    sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
                     try:
                         bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                     except Exception:
                         bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                    for name, _, bit in self.REASONS:
-                        if bits & bit:
-                            self.reasons.add(name)
+                    self._add(sm, pw, [name for name, _, bit in self.REASONS if bits & bit])
                 except Exception:
                     pass
-            time.sleep(float(os.environ.get("LIREC_BENCH_SAMPLE_S", "0.02")))
+            time.sleep(float(os.environ.get("LIREC_BENCH_SAMPLE_S", "0.01")))
 
     def _start_smi(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -171,7 +170,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "10"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
@@ -185,17 +184,32 @@ class ClockSampler:
             if len(f) < 7 or not self.active:
                 continue
             try:
-                self.sm.append(float(f[0]))
+                sm, pw = float(f[0]), float(f[2])
                 self.mx = float(f[1])
-                self.power.append(float(f[2]))
             except ValueError:
                 continue
-            for name, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    self.reasons.add(name)
+            self._add(sm, pw, [name for name, v in zip(names, f[3:7]) if v.lower().startswith("active")])
 
-    def region(self, on):
+    def _add(self, sm, pw, reasons):
+        self.sm.append(sm)
+        self.power.append(pw)
+        self.reasons.update(reasons)
+        t = self.by_tag.setdefault(self.tag, ([], [], set()))
+        t[0].append(sm), t[1].append(pw), t[2].update(reasons)
+
+    def region(self, on, tag=None):
+        """Sampling on / off; `tag` names the timed region the samples belong to ("value" = the K timed steps the
+        headline number comes from, "e2e" = the end-to-end legs, ...)."""
+        if tag is not None:
+            self.tag = tag
         self.active = bool(on)
+
+    def summary(self, tag):
+        sm, pw, rs = self.by_tag.get(tag, ([], [], set()))
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(np.min(sm)), "sm_max_mhz": self.mx,
+                "power_w_max": float(np.max(pw)) if pw else None, "reasons": sorted(rs), "samples": len(sm)}
 
     def stop(self):
         self._stop.set()
@@ -203,9 +217,14 @@ class ClockSampler:
             self.proc.terminate()
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": ["no samples"], "samples": 0}
-        return {"sm_mhz": float(np.median(self.sm)), "sm_min_mhz": float(np.min(self.sm)), "sm_max_mhz": self.mx,
-                "power_w_max": float(np.max(self.power)) if self.power else None, "reasons": sorted(self.reasons),
-                "samples": len(self.sm), "how": "NVML / nvidia-smi polled every 10-20 ms inside the timed regions only"}
+        # the headline `clocks` are those of the region `value` was timed in; the other regions ride along
+        main = self.summary("value") or {"sm_mhz": float(np.median(self.sm)), "sm_min_mhz": float(np.min(self.sm)),
+                                         "sm_max_mhz": self.mx, "power_w_max": float(np.max(self.power)) if self.power else None,
+                                         "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        main["how"] = ("NVML / nvidia-smi polled every 10-20 ms inside the timed regions only; these are the samples of "
+                       "the K timed steps `value` comes from, `by_region` has the other timed legs")
+        main["by_region"] = {t: self.summary(t) for t in sorted(self.by_tag) if t != "value"}
+        return main
 
 
 def usable_cores():
@@ -385,7 +404,7 @@ class Bench:
         if ncu_window:
             torch.cuda.cudart().cudaProfilerStart()
         if sampler is not None:
-            sampler.region(True)
+            sampler.region(True, "value")
         e0.record()
         for i in range(steps):
             if profile:                       # per-launch GEMM events on every PROFILE_EVERY-th step only: an event
@@ -664,7 +683,7 @@ def run_ours(args):
         for leg in range(n_legs):
             b.barrier()
             if rank == 0:
-                sampler.region(True)
+                sampler.region(True, "e2e")
             e0.record()
             t_wait = t_step = w_max = 0.0
             for i in range(e2e_steps):

@@ -1,7 +1,7 @@
 #!/bin/bash
 # compute-sanitizer over the single-GPU suite and smoke (round 2 build)
 out=gpurun_out; mkdir -p $out
-f=$out/t31_compute_sanitizer.txt
+f=$out/r02_compute_sanitizer.txt
 echo "# compute-sanitizer on B200 (round 2 build)" > $f
 echo "## --tool memcheck python -m pytest tests -m gpu -q  (whole single-GPU suite)" >> $f
 timeout 1200 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests -m gpu -q 2>&1 | grep -v "^\.\|^$" | tail -25 >> $f

@@ -121,7 +121,8 @@ def parse_args():
 
 class ClockSampler:
     """SM clock, power and throttle reasons sampled DURING the timed regions (NVML, every ~10 ms; falls back to
-    an `nvidia-smi -lms` child process)."""
+    an `nvidia-smi -lms` child process).  The poller runs for the whole bench and stamps every sample with its host
+    time; region(True / False) only records the interval, and the samples are sorted into the regions at the end."""
     REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", 0x8),
                ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
                ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
@@ -130,6 +131,10 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.sm, self.power, self.reasons, self.mx = index, [], [], set(), None
         self.tag, self.by_tag = "value", {}          # samples per named region: tag -> ([sm], [power], {reasons})
+        # the poller runs from start() to stop() at its own cadence (an idle poller needs 10-20 ms to deliver its
+        # first sample: too long for a 40 ms region); every sample carries its host time and is assigned to the
+        # timed region whose [begin, end] interval it falls into
+        self.samples, self.spans, self._open = [], [], None
         self._stop = threading.Event()
         self.thread = self.proc = None
         self.active = False
@@ -151,17 +156,18 @@ class ClockSampler:
     def _poll(self):
         nv = self.nv
         while not self._stop.is_set():
-            if self.active:
+            try:
+                t0 = time.perf_counter()
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
                 try:
-                    sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
-                    try:
-                        bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                    except Exception:
-                        bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                    self._add(sm, pw, [name for name, _, bit in self.REASONS if bits & bit])
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
-                    pass
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((0.5 * (t0 + time.perf_counter()), sm, pw,
+                                     [name for name, _, bit in self.REASONS if bits & bit]))
+            except Exception:
+                pass
             time.sleep(float(os.environ.get("LIREC_BENCH_SAMPLE_S", "0.01")))
 
     def _start_smi(self):
@@ -181,14 +187,15 @@ class ClockSampler:
         names = [r[0] for r in self.REASONS]
         for line in self.proc.stdout:
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7 or not self.active:
+            if len(f) < 7:
                 continue
             try:
                 sm, pw = float(f[0]), float(f[2])
                 self.mx = float(f[1])
             except ValueError:
                 continue
-            self._add(sm, pw, [name for name, v in zip(names, f[3:7]) if v.lower().startswith("active")])
+            self.samples.append((time.perf_counter(), sm, pw,
+                                 [name for name, v in zip(names, f[3:7]) if v.lower().startswith("active")]))
 
     def _add(self, sm, pw, reasons):
         self.sm.append(sm)
@@ -202,7 +209,23 @@ class ClockSampler:
         headline number comes from, "e2e" = the end-to-end legs, ...)."""
         if tag is not None:
             self.tag = tag
+        now = time.perf_counter()
+        if on and self._open is None:
+            self._open = (self.tag, now)
+        elif not on and self._open is not None:
+            self.spans.append((self._open[0], self._open[1], now))
+            self._open = None
         self.active = bool(on)
+
+    def _assign(self):
+        """Sort the time-stamped samples into the timed regions (idempotent)."""
+        self.sm, self.power, self.reasons, self.by_tag = [], [], set(), {}
+        for t, sm, pw, rs in list(self.samples):
+            for tag, a, b in self.spans:
+                if a <= t <= b:
+                    self.tag = tag
+                    self._add(sm, pw, rs)
+                    break
 
     def summary(self, tag):
         sm, pw, rs = self.by_tag.get(tag, ([], [], set()))
@@ -215,14 +238,16 @@ class ClockSampler:
         self._stop.set()
         if self.proc is not None:
             self.proc.terminate()
+        self._assign()
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": ["no samples"], "samples": 0}
         # the headline `clocks` are those of the region `value` was timed in; the other regions ride along
         main = self.summary("value") or {"sm_mhz": float(np.median(self.sm)), "sm_min_mhz": float(np.min(self.sm)),
                                          "sm_max_mhz": self.mx, "power_w_max": float(np.max(self.power)) if self.power else None,
                                          "reasons": sorted(self.reasons), "samples": len(self.sm)}
-        main["how"] = ("NVML / nvidia-smi polled every 10-20 ms inside the timed regions only; these are the samples of "
-                       "the K timed steps `value` comes from, `by_region` has the other timed legs")
+        main["how"] = ("NVML (fallback: nvidia-smi -lms) polled every ~10 ms for the whole run, every sample time-stamped; "
+                       "counted here are the samples that fall INSIDE the K timed steps `value` comes from, `by_region` "
+                       "has those inside the other timed legs")
         main["by_region"] = {t: self.summary(t) for t in sorted(self.by_tag) if t != "value"}
         return main
 

@@ -635,7 +635,7 @@ def run_ours(args):
                 ev.record(copy_stream)
             return pb, ev
         copy_stream.wait_stream(main)
-        for i in range(2):
+        for i in range(max(2 * args.n_batches, warmup)):          # every distinct batch twice: allocator pools, struct caches
             pb, ev = prefetch(i)
             main.wait_event(ev)
             pb.record_stream(main)
@@ -643,16 +643,25 @@ def run_ours(args):
         b.barrier()
         e0.record()
         nxt = prefetch(0)
+        dbg = [] if os.environ.get("LIREC_BENCH_DEBUG") else None
         for i in range(n_steps):
+            t0 = time.perf_counter()
             pb, ev = nxt
             main.wait_event(ev)
             pb.record_stream(main)
             if i + 1 < n_steps:
                 nxt = prefetch(i + 1)
+            t1 = time.perf_counter()
             lv = b.step(pb)
             loss_host[i:i + 1].copy_(lv.detach().reshape(1), non_blocking=True)
+            if dbg is not None:
+                dbg.append((t1 - t0, time.perf_counter() - t1, i))
         e1.record()
         b.barrier()
+        if dbg:
+            print("[rank %d] pre-staged leg: longest host times staging a batch %s, issuing a step %s (ms, step)" % (
+                rank, [(round(1e3 * a, 2), i) for a, _, i in sorted(dbg, reverse=True)[:3]],
+                [(round(1e3 * c, 2), i) for _, c, i in sorted(dbg, key=lambda r: -r[1])[:3]]), file=sys.stderr, flush=True)
         assert bool(torch.isfinite(loss_host[:n_steps]).all()), "pre-collated leg: non-finite loss read back"
         return args.batch * world * n_steps / (b.max_over_ranks(e0.elapsed_time(e1)) / 1e3)
 
@@ -701,8 +710,9 @@ def run_ours(args):
         # 100-step leg lasts 0.2 s: a single host hiccup (one run in eight showed a 0.5 s stall in one leg, the other
         # legs and all other runs within 5 % of each other) would otherwise decide the headline.
         n_legs = 3
-        it = loader(warmup + n_legs * e2e_steps)
-        for _ in range(warmup):
+        e2e_warm = max(warmup, 10)          # loader threads up, slot ring filled, allocator pools at their high-water marks
+        it = loader(e2e_warm + n_legs * e2e_steps)
+        for _ in range(e2e_warm):
             b.step(next(it))
         e2e_legs, e2e_max_wait = [], []
         for leg in range(n_legs):

@@ -391,6 +391,8 @@ class Bench:
                      for i in range(n_batches)]
         self.resident = [self.banks.stage(h) for h in self.host]
         torch.cuda.synchronize()
+        for pb in self.resident:                   # setup, not warm-up: the workspace covers every staged batch
+            self.model.reserve_workspace(pb)
         self.n_cand = float(np.mean([h.n_cand for h in self.host]))
         self.n_ctx = float(np.mean([h.n_ctx_rows for h in self.host]))
         import lirec_b200.mlp.train as TR
@@ -705,12 +707,13 @@ def run_ours(args):
     if os.environ.get("LIREC_BENCH_NO_FREEZE") != "1":
         gc.freeze()         # as lirec_b200/mlp/train.py does: the cached records never reach a full collection again
     try:
-        # THREE consecutive legs of e2e_steps batches each over the same iterator, each bracketed like the main timed
-        # region (barrier + events, max over ranks); the reported e2e is their MEDIAN and all three are listed.  One
-        # 100-step leg lasts 0.2 s: a single host hiccup (one run in eight showed a 0.5 s stall in one leg, the other
-        # legs and all other runs within 5 % of each other) would otherwise decide the headline.
-        n_legs = 3
-        e2e_warm = max(warmup, 10)          # loader threads up, slot ring filled, allocator pools at their high-water marks
+        # FIVE consecutive legs of e2e_steps batches each over the same iterator, each bracketed like the main timed
+        # region (barrier + events, max over ranks); the reported e2e is their MEDIAN and all five are listed.  One
+        # 100-step leg lasts 0.2 s, and during the first minutes on a freshly started box the host side shows
+        # sporadic 20-120 ms stalls (any thread, any leg — the pre-staged leg too; they fade as the process's pages
+        # get touched) that hit one or two legs of a run and leave the others within 3 % of each other.
+        n_legs = 5
+        e2e_warm = max(warmup, 30)          # loader threads up, slot ring cycled, allocator pools at their high-water marks
         it = loader(e2e_warm + n_legs * e2e_steps)
         for _ in range(e2e_warm):
             b.step(next(it))

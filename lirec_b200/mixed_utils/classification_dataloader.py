@@ -230,6 +230,32 @@ def _threaded_batches(dataset, batches, num_threads, batch_size, slots_ahead):
         pool.shutdown(wait=True, cancel_futures=True)
 
 
+_MALLOC_TUNED = False
+
+
+def _tune_malloc():
+    """Keep the loader's per-batch temporaries (index arrays of a few MB, allocated and freed once per batch by
+    several threads) inside glibc's heaps instead of a fresh mmap / munmap pair each: above the default 128 KB
+    threshold every such array is new anonymous memory that has to be faulted in page by page — and on a freshly
+    started VM every never-touched guest page is a round trip to the hypervisor, seen as sporadic 20-100 ms waits
+    for a batch during the first minutes of a process.  OPT-IN (LIREC_MALLOPT=1): four A/B runs on two fresh boxes
+    showed the stalls with and without it (they also hit legs that never allocate host memory), so the default
+    leaves the allocator alone."""
+    global _MALLOC_TUNED
+    if _MALLOC_TUNED or os.environ.get("LIREC_MALLOPT", "0") != "1":
+        return
+    _MALLOC_TUNED = True
+    try:
+        import ctypes
+        libc = ctypes.CDLL(None)
+        M_TRIM_THRESHOLD, M_TOP_PAD, M_MMAP_THRESHOLD = -1, -2, -3
+        libc.mallopt(M_MMAP_THRESHOLD, 1 << 30)
+        libc.mallopt(M_TRIM_THRESHOLD, (1 << 31) - 1)
+        libc.mallopt(M_TOP_PAD, 256 << 20)
+    except Exception:
+        pass
+
+
 def packed_loader(dataset, batch_size, shuffle, num_workers=0, device="cuda", rank=0, world=1, drop_last=False,
                   seed=0, repeat=1):
     """Iterate device-resident PackedBatches with one-batch-ahead async H2D prefetch.
@@ -238,6 +264,7 @@ def packed_loader(dataset, batch_size, shuffle, num_workers=0, device="cuda", ra
     global batch (lirec_b200/dp.py:shard_range), so the global batch equals the single-GPU one.  A rank whose
     share is empty receives an `EmptyShard` for that step (see there).  `repeat` > 1 chains that many epochs
     (each its own permutation) behind ONE set of worker processes instead of re-forking them per epoch."""
+    _tune_malloc()
     g = torch.Generator()
     g.manual_seed(int(seed) * 1000003 + int(getattr(dataset, "epoch", 0)))
     n = len(dataset)

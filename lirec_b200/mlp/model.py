@@ -323,6 +323,16 @@ class _HotPath(nn.Module):
         b.seed, b.training = int(seed) & 0xFFFFFFFF, int(bool(training))
         return b
 
+    def reserve_workspace(self, pb):
+        """Size the step workspace for device batch `pb` ahead of its first step (setup, no kernel runs): the
+        high-water capacity `_run_forward` allocates from then already covers it, and the batch's C struct is cached."""
+        self._sync_flat()
+        batch_c = self._batch_struct(pb, False, 0)
+        nbytes = int(_ext.lib().lirec_model_workspace_bytes(C.byref(self._cfg_c), C.byref(batch_c)))
+        if nbytes > getattr(self, "_ws_cap", 0):
+            self._ws_cap = -(-int(nbytes * 1.05 + 256) // 4096) * 4096
+        return self._ws_cap
+
     # ---- the two native calls ------------------------------------------------------------------
     def _run_forward(self, pb, training, seed):
         """lirec_model_forward on `pb`.  Returns (batch struct, workspace, inters [Ni,C], rels [Ni,R] | None);

@@ -646,6 +646,9 @@ def run_ours(args):
         e0.record()
         nxt = prefetch(0)
         dbg = [] if os.environ.get("LIREC_BENCH_DEBUG") else None
+        if dbg is not None:
+            import lirec_b200.mixed_utils.indexed_dataset as _ids
+            _ids.STAGE_TRACE = []
         for i in range(n_steps):
             t0 = time.perf_counter()
             pb, ev = nxt
@@ -661,6 +664,13 @@ def run_ours(args):
         e1.record()
         b.barrier()
         if dbg:
+            import lirec_b200.mixed_utils.indexed_dataset as _ids
+            if _ids.STAGE_TRACE:
+                tr = _ids.STAGE_TRACE
+                print("[rank %d] staging phases, longest (ms): table copies %.2f, bank allocations %.2f, gather launches %.2f"
+                      % (rank, 1e3 * max(t[0] for t in tr), 1e3 * max(t[1] for t in tr), 1e3 * max(t[2] for t in tr)),
+                      file=sys.stderr, flush=True)
+                del tr[:]
             print("[rank %d] pre-staged leg: longest host times staging a batch %s, issuing a step %s (ms, step)" % (
                 rank, [(round(1e3 * a, 2), i) for a, _, i in sorted(dbg, reverse=True)[:3]],
                 [(round(1e3 * c, 2), i) for _, c, i in sorted(dbg, key=lambda r: -r[1])[:3]]), file=sys.stderr, flush=True)

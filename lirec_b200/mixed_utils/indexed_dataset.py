@@ -817,6 +817,9 @@ def collate_indexed_numpy(records, dataset, resident=False):
     return pb
 
 
+STAGE_TRACE = None      # measurement aid (bench.py, LIREC_BENCH_DEBUG): a list that ResidentBanks.stage appends its phase times to
+
+
 class ResidentBanks:
     """The split's pooled feature banks resident in HBM (bf16; the whole MovieGraphs pooled table is
     < 1 GB).  A step's host->device traffic is then the packed batch's integer tables plus two row-index
@@ -840,12 +843,29 @@ class ResidentBanks:
         caps = self.__dict__.setdefault("_caps", {})
         if n > caps.get(which, 0):
             caps[which] = -(-int(n * 1.06 + 64) // 512) * 512
+        # The allocator's pools are per stream and only as deep as the number of blocks that were ever pending at
+        # once: whenever the consumer falls one batch further behind than before, the pool grows by a cudaMalloc —
+        # measured as sporadic 14-34 ms stalls of `stage` (bench.py, LIREC_BENCH_DEBUG) during a process's first
+        # seconds.  The first request of a (bank, capacity, stream) therefore fills the pool to its working depth.
+        key = (which, caps[which], torch.cuda.current_stream(self.device).cuda_stream)
+        warmed = self.__dict__.setdefault("_warmed", set())
+        if key not in warmed:
+            warmed.add(key)
+            hold = [torch.empty(caps[which], dim, dtype=torch.bfloat16, device=self.device)
+                    for _ in range(int(os.environ.get("LIREC_BANK_POOL_DEPTH", "6")))]
+            del hold
         return torch.empty(caps[which], dim, dtype=torch.bfloat16, device=self.device)[:n]
 
     def stage(self, pb, non_blocking=True):
         """Host PackedBatch from `collate_indexed` -> device PackedBatch whose banks were gathered on the GPU."""
         from lirec_b200 import ops
+        trace = STAGE_TRACE
+        if trace is not None:
+            import time as _t
+            t0 = _t.perf_counter()
         dev = pb.to_device(self.device, non_blocking=non_blocking, banks=False)
+        if trace is not None:
+            t1 = _t.perf_counter()
         src = getattr(pb, "_src_layout", None)
         if src is not None:                                     # the row lists crossed PCIe inside the arena
             idx_c = dev._arena_dev[src[0]:src[0] + src[1]]
@@ -855,9 +875,15 @@ class ResidentBanks:
                 pb._pin_bank_rows()
             idx_c = pb._bank_rows_pinned[0].to(self.device, non_blocking=non_blocking)
             idx_t = pb._bank_rows_pinned[1].to(self.device, non_blocking=non_blocking)
-        dev.clip_bank = ops.gather_rows(self.clip, idx_c, out=self._rows("clip", idx_c.numel(), self.clip.shape[1]))
-        dev.track_bank = ops.gather_rows(self.track, idx_t, out=self._rows("track", idx_t.numel(), self.track.shape[1]))
+        out_c = self._rows("clip", idx_c.numel(), self.clip.shape[1])
+        out_t = self._rows("track", idx_t.numel(), self.track.shape[1])
+        if trace is not None:
+            t2 = _t.perf_counter()
+        dev.clip_bank = ops.gather_rows(self.clip, idx_c, out=out_c)
+        dev.track_bank = ops.gather_rows(self.track, idx_t, out=out_t)
         dev._bank_idx = (idx_c, idx_t)
+        if trace is not None:                      # (table copies, bank allocations, gather launches) in seconds
+            trace.append((t1 - t0, t2 - t1, _t.perf_counter() - t2))
         return dev
 
     @staticmethod

@@ -1,12 +1,12 @@
 """Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container only).
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [file stem ...]
 
 For each preset / loss variant a small random model of the reference (reduced dims so the fixtures
 stay small) is built with the reference's own create_model, run forward + loss + backward on a
 random dense batch, and inputs, parameters, outputs, loss, the in-place masked logits and all
-parameter gradients are stored.  Twelve cases run in eval mode; four more (`*_train.npz`, one per
-preset) run the reference in TRAIN mode with its nn.Dropout modules replaced by a replayer
+parameter gradients are stored.  Thirteen cases run in eval mode; five more (`*_train.npz`, one per
+preset and one for the relationship-only model, opt.ints == 0) run the reference in TRAIN mode with its nn.Dropout modules replaced by a replayer
 (oracle/reference_shim.py:DropoutReplay) over random 0/1 masks that are stored with the case, which
 pins the dropout sites of the restatement.  tests/test_oracle_golden.py checks oracle/ against them
 everywhere (the GPU box has no /root/reference).
@@ -19,6 +19,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+ONLY_NAMES = sys.argv[1:]       # optional: file stems to (re)generate, e.g. int_rels_gates-0_ints-0; default all
 sys.argv = sys.argv[:1]
 
 from oracle import reference_shim as rs  # noqa: E402
@@ -35,7 +36,11 @@ CASES = [
     # train mode (dropout masks replayed): one per preset
     ("modalities", dict(train=True)), ("int_rels", dict(train=True)), ("int_ch", dict(train=True)),
     ("int_rel_ch", dict(train=True)),
+    # opt.ints == 0: the context branch + relationship head alone (mlp/model.py:102, 140, 151, 208; loss :391); the
+    # reference's GatingUnit needs the interaction feature, so gates are off
+    ("int_rels", dict(ints=0, gates=0)), ("int_rels", dict(ints=0, gates=0, train=True)),
 ]
+
 
 
 def make_batch(preset, rng):
@@ -86,9 +91,14 @@ def main():
         opt.modality, opt.tracks = "m", True
         over = dict(over)
         train = bool(over.pop("train", False))
+        batch = make_batch(preset, rng)          # always drawn: the cases share one generator, in this order
+        stem = "%s%s" % (preset, "".join("_" + (k if v is True else "%s-%s" % (k, v))
+                                          for k, v in sorted(dict(over, **({"train": True} if train else {})).items())))
+        if ONLY_NAMES and stem not in ONLY_NAMES:
+            continue
+        opt.ints, opt.gates = 1, 1               # presets set ctx / gates; a case may override ints / gates
         model, loss = rs.create_model(preset, C, R, seed=idx, **over)
         model.eval()
-        batch = make_batch(preset, rng)
         inp = {k: v.clone() for k, v in batch.items()}
         masks = None
         if train:
@@ -96,7 +106,8 @@ def main():
             ctx = preset in ("int_rels", "int_rel_ch")
             rows = B * T if kind == "maxtracks" else B
             masks = rs.random_masks(kind, rows, S, DIMS["joint_dim"], DIMS["joint_dim"] * DIMS["mid_m_ints"], opt.dropout,
-                                    torch.Generator().manual_seed(1000 + idx), ctx=ctx, gates=ctx)
+                                    torch.Generator().manual_seed(1000 + idx), ctx=ctx,
+                                    gates=ctx and bool(over.get("gates", 1)), ints=bool(over.get("ints", 1)))
             queue = rs.replay_dropout(model, masks, opt.dropout)
         out = model(batch)                     # MaxTracks reshapes batch['features'] in place
         if train:
@@ -125,6 +136,7 @@ def main():
     # restore the full-size dims for anything else importing the shim in this process
     opt.text_dim, opt.visual_dim, opt.track_dim, opt.joint_dim, opt.mlp_dim = 768, 2048, 2048, 512, 6912
     opt.modality, opt.tracks = "m", True
+    opt.ints = 1
 
 
 if __name__ == "__main__":

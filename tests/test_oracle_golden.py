@@ -18,7 +18,9 @@ C, R = 11, 5
 
 
 def test_golden_files_present():
-    assert len(GOLDEN) == 16          # 12 eval-mode cases + one train-mode (replayed dropout masks) case per preset
+    # 12 eval-mode cases + one train-mode (replayed dropout masks) case per preset + the relationship-only model
+    # (opt.ints == 0, gates off) in eval and train mode
+    assert len(GOLDEN) == 18
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -31,13 +33,14 @@ def test_oracle_reproduces_reference(path):
     feats = inp["features"].float()
     kind = {"modalities": "modalities", "int_rels": "midfusion"}.get(preset, "maxtracks")
     ctx = preset in ("int_rels", "int_rel_ch")
-    cfg = om.default_cfg(ctx=int(ctx), gates=int(ctx), modality=over.get("modality", "m"),
-                         tracks=over.get("tracks", True), **DIMS)
+    ints = int(over.get("ints", 1))
+    cfg = om.default_cfg(ctx=int(ctx), gates=int(ctx and over.get("gates", 1)), ints=ints,
+                         modality=over.get("modality", "m"), tracks=over.get("tracks", True), **DIMS)
     masks = None
     if over.get("train"):                      # the dropout masks the reference replayed (make_golden.py)
         cfg.dropout = float(z["dropout_p"])
         masks = {tuple(k[5:].split("/")): torch.from_numpy(z[k]) for k in z.files if k.startswith("mask_")}
-        assert ("cat", "ints") in masks
+        assert (("cat", "ints") in masks) == bool(ints)
     masked = {}
     if kind == "modalities":
         o = om.modalities_forward(sd, feats, cfg, masks)
@@ -45,7 +48,8 @@ def test_oracle_reproduces_reference(path):
     elif kind == "midfusion":
         o = om.midfusion_forward(sd, feats, inp["rels_mask"], cfg, masks)
         l = ol.multitask_max_margin(o["inters"], o["rels"], inp["labels"], inp["rels_label"],
-                                    inp["multilab_weights"].float(), 0.101, 1.0, R)
+                                    inp["multilab_weights"].float(), 0.101, 1.0, R, ints=ints)
+        assert (o["inters"] is None) == (not ints) == ("out_inters" not in z.files)
     else:
         o = om.maxtracks_forward(sd, feats, inp.get("rels_mask"), cfg, masks)
         if ctx:

@@ -315,11 +315,21 @@ def cpu_baseline_line(preset, cpu_clips, steps, warmup):
     else:
         pb = synthetic.make_batch(cpu_clips, seed=0, preset=model)
     dense = pb.to_dense(np.float64)
-    r = cb.time_train(model, dense, steps=steps, warmup=warmup)
-    return {"value": r["clips_per_s_mean"], "unit": "clips/s", "cores": r["threads"], "kind": "port",
+    # the unmodified reference itself where its tree is mounted (the build container); its oracle port elsewhere
+    # (the GPU box has no /root/reference: a Python reference cannot travel)
+    kind = "port"
+    from oracle import reference_shim as rs
+    if rs.available() and preset != "stress" and os.environ.get("LIREC_BENCH_LIVE_REFERENCE", "1") != "0":
+        r = cb.time_train_reference(model, dense, steps=steps, warmup=warmup)
+        kind = "reference"
+    else:
+        r = cb.time_train(model, dense, steps=steps, warmup=warmup)
+    return {"value": r["clips_per_s_mean"], "unit": "clips/s", "cores": r["threads"], "kind": kind,
             "sample": "%d-clip dense float64 batch (reference dataloader format, %s), %d timed train steps "
-                      "(fwd+loss+bwd+Adam, dropout 0.3, fp32 torch CPU) after %d warm-up" % (
-                          cpu_clips, preset, steps, warmup),
+                      "(fwd+loss+bwd+Adam, dropout 0.3, fp32 torch CPU) after %d warm-up%s" % (
+                          cpu_clips, preset, steps, warmup,
+                          "; the UNMODIFIED reference model / loss / torch Adam (tree mounted)" if kind == "reference"
+                          else "; oracle port of the reference (its tree is not on this box)"),
             "ms_per_step": 1e3 * cpu_clips / r["clips_per_s_mean"]}
 
 

@@ -84,3 +84,47 @@ def time_train(preset, dense, steps=3, warmup=1, threads=None):
         total += dt
     return {"clips_per_s_best": B / best, "clips_per_s_mean": B * steps / total, "s_per_step_best": best,
             "threads": torch.get_num_threads(), "clips": B}
+
+
+def time_train_reference(preset, dense, steps=3, warmup=1, threads=None, lr=3e-5, weight_decay=1e-5):
+    """The same measurement with the UNMODIFIED reference (mlp/model.py's create_model output: its model and loss
+    classes, torch.optim.Adam with the reference's hyper-parameters, the loop body of mlp/train.py:57-63) — only
+    where the reference tree is mounted (this build container; never the GPU box).  Same dense batch, same
+    thread count, train mode with torch's own dropout RNG.  bench.py reports it as kind "reference"."""
+    from . import reference_shim as rs
+    if threads:
+        torch.set_num_threads(threads)
+    model, loss = rs.create_model(preset, 101, 15, seed=0)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
+    kind = {"modalities": "modalities", "int_rels": "midfusion"}.get(preset, "maxtracks")
+    batch = {k: v for k, v in dense.items()}
+    B = batch["features"].shape[0]
+    if kind == "modalities":
+        batch["features"] = batch["features"].reshape(B, 1, -1)
+    elif kind == "midfusion":
+        S1 = batch["features"].shape[2]
+        batch["features"] = batch["features"].reshape(B, S1, -1)
+        batch["rels_mask"] = batch["rels_mask"].reshape(B, -1, 1)
+        batch["labels"] = batch["labels"].reshape(B, 1, 1).expand(B, S1, 1).contiguous()
+        batch["rels_label"] = batch["rels_label"].reshape(B)
+
+    def step():
+        x = dict(batch)                       # MaxTracks re-points x['features'] at a reshaped view (model.py:272-274)
+        out = model(x)
+        lv = rs.run_loss(loss, out, x)
+        opt.zero_grad()
+        lv.backward()
+        opt.step()
+        return float(lv.item())
+
+    for _ in range(warmup):
+        step()
+    best, total = float("inf"), 0.0
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        best, total = min(best, dt), total + dt
+    return {"clips_per_s_best": B / best, "clips_per_s_mean": B * steps / total, "s_per_step_best": best,
+            "threads": torch.get_num_threads(), "clips": B}
